@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 tracking-correlator hot path (BASELINE.json metric
+"Msamples/s through N-channel E/P/L correlator"), workload = BASELINE configs[1] (SURVEY 8d "C2"):
+GPS L1 C/A, 32 channels, 25 Msps synthetic IQ, 3 taps (E/P/L), 1 s of signal per step
+(1000 epochs of 25000 samples per channel => 8e8 channel-samples per step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "Msamples/s through N-channel E/P/L correlator"
+UNIT = "Msamples/s"
+
+# ---- workload C2 -------------------------------------------------------------------------------
+FS = 25e6
+N_CH = 32
+EPOCH = 25000           # vector_length at 25 Msps (gps_l1_ca_dll_pll_tracking.cc:59)
+N_EPOCHS = 1000         # 1 s of signal per step
+TAPS = 3
+SHIFTS = [-0.5, 0.0, 0.5]
+SEED = 2
+ALGO_BYTES_PER_CHANNEL_SAMPLE = 8   # one cf32 read per channel-sample
+
+
+def config_dict(n_gpus):
+    return {"workload": "C2: GPS L1 C/A, 32 channels x 25 Msps x 1 s (1000 epochs of 25000 samples), 3 taps E/P/L, "
+                        "open-loop per-epoch NCO parameters",
+            "channels_per_gpu": N_CH, "fs_sps": FS, "epoch_samples": EPOCH, "epochs_per_step": N_EPOCHS, "taps": TAPS,
+            "channel_samples_per_step_per_gpu": N_CH * EPOCH * N_EPOCHS,
+            "l2_policy": "IQ band (200 MB) exceeds L2 (126 MB); streamed once per step, shared by the 32 channels",
+            "sharding": "channels sharded across ranks, no data-path collective" if n_gpus > 1 else "single GPU"}
+
+
+def svs_for_rank(rank):
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    return [dict(prn=p, doppler=float(rng.uniform(-5000, 5000)), code_phase_chips=float(rng.uniform(0, 1023)),
+                 cn0=45.0, phase0=float(rng.uniform(0, 2 * np.pi))) for p in range(1, N_CH + 1)]
+
+
+def build_items(capi, svs, cids, first_index):
+    from gnss_synth import trk_params_for
+    items = np.zeros(N_CH * N_EPOCHS, capi.TRK_ITEM_DTYPE)
+    v = items.reshape(N_EPOCHS, N_CH)      # epoch-major: the 32 channels of one epoch are neighbours (L2 sharing)
+    for c, sv in enumerate(svs):
+        s, rc, dp, rcode, st = trk_params_for(sv, FS, EPOCH, N_EPOCHS)
+        v["channel"][:, c] = cids[c]
+        v["n"][:, c] = EPOCH
+        v["sample_index"][:, c] = first_index + s
+        v["rem_carrier_phase_rad"][:, c] = rc
+        v["phase_step_rad"][:, c] = dp
+        v["rem_code_phase_chips"][:, c] = rcode
+        v["code_phase_step_chips"][:, c] = st
+    return items
+
+
+def synth_iq_device(torch, codes, svs, n, seed, device):
+    """Sum of 32 SV signals + AWGN, generated on the GPU in chunks (same model as tests/gnss_synth.make_iq)."""
+    from gnss_synth import ca_amplitude, CA_RATE, GPS_L1_FREQ
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, 2), dtype=torch.float32, device=device)
+    chunk = 1 << 22
+    tabs = {p: torch.from_numpy(codes[p]).to(device) for p in codes}
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        t = torch.arange(a, b, dtype=torch.float64, device=device)
+        re = torch.randn(b - a, generator=g, device=device, dtype=torch.float32).double()
+        im = torch.randn(b - a, generator=g, device=device, dtype=torch.float32).double()
+        for sv in svs:
+            rate = CA_RATE * (1.0 + sv["doppler"] / GPS_L1_FREQ)
+            idx = torch.floor(sv["code_phase_chips"] + t * (rate / FS)).long() % 1023
+            c = tabs[sv["prn"]][idx].double() * ca_amplitude(sv["cn0"], FS)
+            ph = sv["phase0"] + 2 * np.pi * sv["doppler"] / FS * t
+            re += c * torch.cos(ph)
+            im += c * torch.sin(ph)
+        out[a:b, 0] = re.float()
+        out[a:b, 1] = im.float()
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_bytes():
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("trk_correlate_kernel_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ---- CPU baseline (the reference's own SIMD path, timed like its own harness) --------------------
+def cpu_baseline(budget_s=12.0):
+    import oracle
+    cores = os.cpu_count() or 1
+    if oracle.ref is not None:
+        kind = "reference"
+        oracle.ref.select_arch("u_avx")   # GNU Radio buffers are unaligned: VOLK dispatches to u_ variants
+
+        def run(iters):
+            return oracle.ref.mc_bench(cores, EPOCH, TAPS, 1023, iters, 8, False)
+    else:
+        kind = "port"
+        rng = np.random.default_rng(0)
+        iq = (rng.standard_normal(EPOCH * 8) + 1j * rng.standard_normal(EPOCH * 8)).astype(np.complex64)
+        code = oracle.port.gps_ca_code(1)
+
+        def run(iters):
+            params = np.tile(np.array([[0.4, 0.001, 0.3, 1023.0 / EPOCH]], np.float32), (iters * cores, 1))
+            idx_iq = np.tile(iq, 1)
+            t0 = time.perf_counter()
+            # items walk over 8 distinct epochs
+            oracle.port.multicorrelator_batch(1, cores, idx_iq, 0, code, SHIFTS, params, EPOCH)
+            return time.perf_counter() - t0
+    t = run(20)
+    iters = int(max(20, min(20000, 20 * budget_s / max(t, 1e-6))))
+    t = run(iters)
+    samples = cores * iters * EPOCH
+    return {"value": samples / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{cores} threads x {iters} epochs of {EPOCH} samples x {TAPS} taps, L=1023 "
+                      f"({samples / 1e6:.0f} M channel-samples, {t:.1f} s); "
+                      + ("reference Cpu_Multicorrelator_Real_Codes with volk_gnsssdr u_avx kernels "
+                         "(harness shaped like cpu_multicorrelator_real_codes_test.cc:41-62,135-169)"
+                         if kind == "reference" else "C port of the a_avx/u_avx arithmetic")}, t
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals, times = [], []
+    for k in range(args.warmup + args.steps):
+        cb, t = cpu_baseline(budget_s=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        if k >= args.warmup:
+            vals.append(cb["value"])
+            times.append(t)
+    cb["value"] = float(np.mean(vals))
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import gnss_sdr_b200.capi as capi   # raises if libb200gnss.so is missing: no fallback
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    import oracle  # only for PRN code tables of the synthetic input (test infrastructure, not timed)
+    codes = {p: oracle.port.gps_ca_code(p) for p in range(1, N_CH + 1)}
+    svs = svs_for_rank(rank)
+    n_iq = EPOCH * N_EPOCHS
+    iq_dev = synth_iq_device(torch, codes, svs, n_iq + 16, SEED + rank, dev)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = capi.Engine(local_rank, stream)
+    # band 0: attached device-resident IQ (value); band 1: ring fed from pinned host memory (e2e)
+    eng.iq_attach_dev(0, iq_dev.data_ptr(), n_iq + 16, 0)
+    cids = []
+    for sv in svs:
+        cid = eng.channel_create(0, TAPS)
+        eng.channel_set_code(cid, codes[sv["prn"]], SHIFTS)
+        cids.append(cid)
+    items = build_items(capi, svs, cids, 0)
+    n_items = items.size
+    items_dev = torch.from_numpy(items.view(np.uint8)).to(dev)
+    out_dev = torch.zeros((n_items, TAPS, 2), dtype=torch.float32, device=dev)
+    ch_samples_step = N_CH * EPOCH * N_EPOCHS
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        eng.trk_batch_dev(items_dev.data_ptr(), n_items, out_dev.data_ptr(), TAPS, 1)
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step_dev()
+        ev[k + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * ch_samples_step / (ms_per_step * 1e-3) / 1e6
+
+    # sanity: the prompt taps must show the signal (guards against timing a broken kernel)
+    taps = out_dev[:, :, 0].cpu().numpy() + 1j * out_dev[:, :, 1].cpu().numpy()
+    prompt_snr = float(np.mean(np.abs(taps[:, 1])) / np.sqrt(EPOCH * 2.0))
+
+    # ---- e2e: host buffers through the public C ABI, copies inside the timed region --------------
+    e2e = None
+    if not args.no_e2e:
+        host_iq = torch.empty((n_iq, 2), dtype=torch.float32, pin_memory=True)
+        host_iq.copy_(iq_dev[:n_iq])
+        torch.cuda.synchronize()
+        eng.iq_create(1, n_iq)
+        cids1 = []
+        for sv in svs:
+            cid = eng.channel_create(1, TAPS)
+            eng.channel_set_code(cid, codes[sv["prn"]], SHIFTS)
+            cids1.append(cid)
+        items1 = build_items(capi, svs, cids1, 0)
+        base_idx = items1["sample_index"].copy()
+
+        def step_e2e():
+            first = eng.iq_push_ptr(1, host_iq.data_ptr(), n_iq)     # H2D 200 MB from pinned host memory
+            items1["sample_index"] = base_idx + np.uint64(first)
+            return eng.trk_batch(items1, TAPS)                        # items H2D, launch, taps D2H
+
+        for _ in range(args.warmup):
+            res = step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step_e2e()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * ch_samples_step * args.steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_iq * 8 + items1.nbytes), "d2h_bytes_per_step": int(n_items * TAPS * 8),
+               "ms_per_step": dt / args.steps * 1e3,
+               "path": "b200_iq_push (pinned host -> device ring) + b200_trk_batch (items H2D, 1 launch, taps D2H)"}
+        # e2e result must agree with the device-resident run
+        e2e["max_rel_diff_vs_value_run"] = float(np.max(np.abs(res - taps)) / np.max(np.abs(taps)))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (only) kernel ----------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    launch_ms = float(np.mean(per_launch_ms))
+    achieved = ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "trk_correlate_kernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                "algorithmic_bytes_per_launch": ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE,
+                "launch_ms": launch_ms, "peak_source": peak_src,
+                "note": "algorithmic bytes = 8 B per channel-sample (SURVEY 8d); the 32 channels share one IQ stream, "
+                        "so DRAM traffic is ~1/32 of that and the kernel is issue-bound, see DESIGN.md"}
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        cb, _ = cpu_baseline()
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+            "stream_msps": value / N_CH, "prompt_over_noise": prompt_snr}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

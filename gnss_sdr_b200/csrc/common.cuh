@@ -1,0 +1,60 @@
+// Shared host/device declarations for libb200gnss.so (sm_100a only).
+#pragma once
+
+#include "../../include/b200gnss.h"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+namespace b200
+{
+// thread-local last-error text behind b200_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define B200_CUDA_TRY(expr)                                                                            \
+    do                                                                                                 \
+        {                                                                                              \
+            cudaError_t _e = (expr);                                                                   \
+            if (_e != cudaSuccess)                                                                     \
+                {                                                                                      \
+                    ::b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+                    return B200_ERR_CUDA;                                                              \
+                }                                                                                      \
+        }                                                                                              \
+    while (0)
+
+// One conditioned IQ stream resident in HBM.  Sample with absolute index i lives at
+// base[(i - first_index) & mask]; attach-mode (linear) bands use mask = ~0.
+struct BandDesc
+{
+    const float2* base;
+    unsigned long long mask;
+    unsigned long long first_index;
+};
+
+// One tracking channel registration: code table (device), its length, taps and shifts.
+struct ChanDesc
+{
+    const float* code;
+    int code_len;
+    int taps;
+    int band;
+    int high_dyn;
+    float shifts[B200_MAX_TAPS];
+};
+
+constexpr int kTrkThreads = 256;            // threads per CTA
+constexpr int kTrkTile = 2 * kTrkThreads;   // samples per CTA iteration (one LDG.128 per thread)
+constexpr int kTrkReseed = 16;              // tiles between exact phasor re-seeds
+constexpr int kTrkTablePad = 64;            // extra entries of the extended code table
+
+// Launchers (trk_kernels.cu).  All pointers are device-accessible.
+int launch_trk_batch(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands,
+    float2* out, int out_stride, int slices, float2* partial, unsigned int* counters,
+    int max_code_len, int taps_uniform, cudaStream_t stream);
+size_t trk_partial_elems(int n_items, int slices);
+
+}  // namespace b200

@@ -1,0 +1,638 @@
+// Host side of libb200gnss.so: engine, IQ band stores, channel registry and the tracking C ABI.
+// The shapes mirror the reference's correlator class
+// (src/algorithms/tracking/libs/cpu_multicorrelator_real_codes.{h,cc}); see include/b200gnss.h
+// for the per-function citations.
+
+#include "common.cuh"
+
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace b200
+{
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+constexpr int kMaxBands = 16;
+
+struct Band
+{
+    float2* dev{nullptr};      // owned ring (nullptr when attached)
+    const float2* base{nullptr};
+    unsigned long long mask{0};
+    unsigned long long first_index{0};
+    unsigned long long capacity{0};
+    unsigned long long write_index{0};  // absolute index of the next pushed sample
+    bool attached{false};
+    bool in_use{false};
+};
+
+struct Channel
+{
+    float* code_dev{nullptr};
+    int code_cap{0};
+    ChanDesc desc{};
+};
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_engine
+{
+    int device{0};
+    cudaStream_t stream{nullptr};
+    bool own_stream{false};
+    cudaStream_t copy_stream{nullptr};
+    cudaEvent_t copy_done{nullptr};
+    cudaEvent_t t0{nullptr}, t1{nullptr};
+    std::mutex mu;
+    Band bands[kMaxBands];
+    std::vector<Channel> chans;
+    // device mirrors
+    BandDesc* bands_dev{nullptr};
+    ChanDesc* chans_dev{nullptr};
+    int chans_dev_cap{0};
+    bool tables_dirty{true};
+    int max_code_len{0};
+    int taps_uniform{-1};
+    // batch staging
+    b200_trk_item* items_dev{nullptr};
+    b200_trk_item* items_pin{nullptr};
+    float2* out_dev{nullptr};
+    float2* out_pin{nullptr};
+    int batch_cap{0};
+    int out_cap{0};
+    float2* partial{nullptr};
+    unsigned int* counters{nullptr};
+    size_t partial_cap{0};
+    int counters_cap{0};
+    uint64_t launches{0};
+};
+
+namespace
+{
+int upload_tables(b200_engine* e)
+{
+    if (!e->tables_dirty) return B200_OK;
+    BandDesc bd[kMaxBands];
+    for (int i = 0; i < kMaxBands; i++)
+        {
+            bd[i].base = e->bands[i].base;
+            bd[i].mask = e->bands[i].mask;
+            bd[i].first_index = e->bands[i].first_index;
+        }
+    B200_CUDA_TRY(cudaMemcpyAsync(e->bands_dev, bd, sizeof(bd), cudaMemcpyHostToDevice, e->stream));
+    const int n = static_cast<int>(e->chans.size());
+    if (n > e->chans_dev_cap)
+        {
+            if (e->chans_dev) B200_CUDA_TRY(cudaFree(e->chans_dev));
+            e->chans_dev_cap = n + 64;
+            B200_CUDA_TRY(cudaMalloc(&e->chans_dev, sizeof(ChanDesc) * e->chans_dev_cap));
+        }
+    e->max_code_len = 0;
+    e->taps_uniform = -1;
+    if (n > 0)
+        {
+            std::vector<ChanDesc> cd(n);
+            for (int i = 0; i < n; i++)
+                {
+                    cd[i] = e->chans[i].desc;
+                    if (cd[i].code_len > e->max_code_len) e->max_code_len = cd[i].code_len;
+                    if (cd[i].code == nullptr) continue;
+                    if (e->taps_uniform == -1)
+                        e->taps_uniform = cd[i].taps;
+                    else if (e->taps_uniform != cd[i].taps)
+                        e->taps_uniform = 0;
+                }
+            // synchronous-safe: source is a temporary, so block until the copy has been staged
+            B200_CUDA_TRY(cudaMemcpyAsync(e->chans_dev, cd.data(), sizeof(ChanDesc) * n, cudaMemcpyHostToDevice, e->stream));
+            B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        }
+    if (e->taps_uniform < 0) e->taps_uniform = 0;
+    e->tables_dirty = false;
+    return B200_OK;
+}
+
+int ensure_partials(b200_engine* e, int n_items, int slices)
+{
+    if (slices <= 1) return B200_OK;
+    const size_t need = trk_partial_elems(n_items, slices);
+    if (need > e->partial_cap)
+        {
+            if (e->partial) B200_CUDA_TRY(cudaFree(e->partial));
+            e->partial_cap = need + need / 4;
+            B200_CUDA_TRY(cudaMalloc(&e->partial, sizeof(float2) * e->partial_cap));
+        }
+    if (n_items > e->counters_cap)
+        {
+            if (e->counters) B200_CUDA_TRY(cudaFree(e->counters));
+            e->counters_cap = n_items + n_items / 4 + 16;
+            B200_CUDA_TRY(cudaMalloc(&e->counters, sizeof(unsigned int) * e->counters_cap));
+            B200_CUDA_TRY(cudaMemsetAsync(e->counters, 0, sizeof(unsigned int) * e->counters_cap, e->stream));
+        }
+    return B200_OK;
+}
+
+unsigned long long next_pow2(unsigned long long v)
+{
+    unsigned long long p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+}  // namespace
+
+extern "C"
+{
+    int b200_version(void) { return 100; }
+    const char* b200_last_error(void) { return get_error(); }
+
+    int b200_device_count(int* count)
+    {
+        if (!count) return B200_ERR_ARG;
+        int n = 0;
+        cudaError_t err = cudaGetDeviceCount(&n);
+        if (err != cudaSuccess)
+            {
+                set_error("cudaGetDeviceCount: %s", cudaGetErrorString(err));
+                *count = 0;
+                return B200_ERR_NODEV;
+            }
+        *count = n;
+        return B200_OK;
+    }
+
+    int b200_engine_create(b200_engine** out, int device, void* stream)
+    {
+        if (!out) return B200_ERR_ARG;
+        *out = nullptr;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+            {
+                set_error("no CUDA device visible");
+                return B200_ERR_NODEV;
+            }
+        if (device < 0 || device >= n)
+            {
+                set_error("device %d out of range (have %d)", device, n);
+                return B200_ERR_ARG;
+            }
+        cudaDeviceProp prop{};
+        B200_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            {
+                set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+                return B200_ERR_NODEV;
+            }
+        B200_CUDA_TRY(cudaSetDevice(device));
+        b200_engine* e = new (std::nothrow) b200_engine();
+        if (!e) return B200_ERR_NOMEM;
+        e->device = device;
+        if (stream)
+            {
+                e->stream = static_cast<cudaStream_t>(stream);
+            }
+        else
+            {
+                B200_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+                e->own_stream = true;
+            }
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        B200_CUDA_TRY(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
+        B200_CUDA_TRY(cudaEventCreate(&e->t0));
+        B200_CUDA_TRY(cudaEventCreate(&e->t1));
+        B200_CUDA_TRY(cudaMalloc(&e->bands_dev, sizeof(BandDesc) * kMaxBands));
+        *out = e;
+        return B200_OK;
+    }
+
+    int b200_engine_destroy(b200_engine* e)
+    {
+        if (!e) return B200_ERR_ARG;
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->stream);
+        cudaStreamSynchronize(e->copy_stream);
+        for (auto& b : e->bands)
+            if (b.dev) cudaFree(b.dev);
+        for (auto& c : e->chans)
+            if (c.code_dev) cudaFree(c.code_dev);
+        if (e->bands_dev) cudaFree(e->bands_dev);
+        if (e->chans_dev) cudaFree(e->chans_dev);
+        if (e->items_dev) cudaFree(e->items_dev);
+        if (e->items_pin) cudaFreeHost(e->items_pin);
+        if (e->out_dev) cudaFree(e->out_dev);
+        if (e->out_pin) cudaFreeHost(e->out_pin);
+        if (e->partial) cudaFree(e->partial);
+        if (e->counters) cudaFree(e->counters);
+        cudaEventDestroy(e->copy_done);
+        cudaEventDestroy(e->t0);
+        cudaEventDestroy(e->t1);
+        cudaStreamDestroy(e->copy_stream);
+        if (e->own_stream) cudaStreamDestroy(e->stream);
+        delete e;
+        return B200_OK;
+    }
+
+    int b200_engine_sync(b200_engine* e)
+    {
+        if (!e) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        return B200_OK;
+    }
+
+    int b200_engine_timer_start(b200_engine* e)
+    {
+        if (!e) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaEventRecord(e->t0, e->stream));
+        return B200_OK;
+    }
+
+    int b200_engine_timer_stop_ms(b200_engine* e, float* ms)
+    {
+        if (!e || !ms) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaEventRecord(e->t1, e->stream));
+        B200_CUDA_TRY(cudaEventSynchronize(e->t1));
+        B200_CUDA_TRY(cudaEventElapsedTime(ms, e->t0, e->t1));
+        return B200_OK;
+    }
+
+    int b200_engine_launch_count(b200_engine* e, uint64_t* n)
+    {
+        if (!e || !n) return B200_ERR_ARG;
+        *n = e->launches;
+        return B200_OK;
+    }
+
+    // ---- bands -----------------------------------------------------------------------------
+    int b200_iq_create(b200_engine* e, int band, uint64_t capacity_samples)
+    {
+        if (!e || band < 0 || band >= kMaxBands || capacity_samples == 0) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> lk(e->mu);
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        Band& b = e->bands[band];
+        if (b.dev)
+            {
+                B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+                B200_CUDA_TRY(cudaFree(b.dev));
+                b.dev = nullptr;
+            }
+        const unsigned long long cap = next_pow2(capacity_samples);
+        cudaError_t err = cudaMalloc(&b.dev, cap * sizeof(float2));
+        if (err != cudaSuccess)
+            {
+                set_error("band %d: cudaMalloc(%llu samples): %s", band, cap, cudaGetErrorString(err));
+                return B200_ERR_NOMEM;
+            }
+        b.base = b.dev;
+        b.capacity = cap;
+        b.mask = cap - 1;
+        b.first_index = 0;
+        b.write_index = 0;
+        b.attached = false;
+        b.in_use = true;
+        e->tables_dirty = true;
+        return B200_OK;
+    }
+
+    int b200_iq_push(b200_engine* e, int band, const b200_cf32* host, uint64_t n, uint64_t* first_index)
+    {
+        if (!e || band < 0 || band >= kMaxBands || (!host && n)) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> lk(e->mu);
+        Band& b = e->bands[band];
+        if (!b.in_use || b.attached || !b.dev)
+            {
+                set_error("band %d is not an owned ring (call b200_iq_create)", band);
+                return B200_ERR_STATE;
+            }
+        if (n > b.capacity)
+            {
+                set_error("push of %llu samples exceeds ring capacity %llu", (unsigned long long)n, b.capacity);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        if (first_index) *first_index = b.write_index;
+        // copies run on the copy stream; later launches on the compute stream wait on copy_done.
+        // (Overwriting samples that an in-flight launch still reads is the caller's ring-sizing
+        // responsibility, exactly as with any circular sample buffer.)
+        const unsigned long long off = b.write_index & b.mask;
+        const unsigned long long first = (n < b.capacity - off) ? n : (b.capacity - off);
+        if (first) B200_CUDA_TRY(cudaMemcpyAsync(b.dev + off, host, first * sizeof(float2), cudaMemcpyHostToDevice, e->copy_stream));
+        if (n > first) B200_CUDA_TRY(cudaMemcpyAsync(b.dev, host + first, (n - first) * sizeof(float2), cudaMemcpyHostToDevice, e->copy_stream));
+        B200_CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
+        B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
+        b.write_index += n;
+        return B200_OK;
+    }
+
+    int b200_iq_attach_dev(b200_engine* e, int band, const b200_cf32* dev, uint64_t n_samples, uint64_t first_index)
+    {
+        if (!e || band < 0 || band >= kMaxBands || !dev) return B200_ERR_ARG;
+        if (reinterpret_cast<uintptr_t>(dev) & 15)
+            {
+                set_error("attached band must be 16-byte aligned");
+                return B200_ERR_ARG;
+            }
+        std::lock_guard<std::mutex> lk(e->mu);
+        Band& b = e->bands[band];
+        if (b.dev)
+            {
+                B200_CUDA_TRY(cudaSetDevice(e->device));
+                B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+                B200_CUDA_TRY(cudaFree(b.dev));
+                b.dev = nullptr;
+            }
+        b.base = reinterpret_cast<const float2*>(dev);
+        b.capacity = n_samples;
+        b.mask = ~0ULL;
+        b.first_index = first_index;
+        b.write_index = first_index + n_samples;
+        b.attached = true;
+        b.in_use = true;
+        e->tables_dirty = true;
+        return B200_OK;
+    }
+
+    // ---- channels ------------------------------------------------------------------------------
+    int b200_trk_channel_create(b200_engine* e, int band, int n_correlators, int* channel_id)
+    {
+        if (!e || !channel_id || band < 0 || band >= kMaxBands) return B200_ERR_ARG;
+        if (n_correlators < 1 || n_correlators > B200_MAX_TAPS)
+            {
+                set_error("n_correlators %d outside 1..%d", n_correlators, B200_MAX_TAPS);
+                return B200_ERR_RANGE;
+            }
+        std::lock_guard<std::mutex> lk(e->mu);
+        Channel c;
+        c.desc.band = band;
+        c.desc.taps = n_correlators;
+        c.desc.code = nullptr;
+        c.desc.code_len = 0;
+        c.desc.high_dyn = 0;
+        for (float& s : c.desc.shifts) s = 0.f;
+        e->chans.push_back(c);
+        *channel_id = static_cast<int>(e->chans.size()) - 1;
+        e->tables_dirty = true;
+        return B200_OK;
+    }
+
+    int b200_trk_channel_set_code(b200_engine* e, int channel_id, int code_length_chips, const float* local_code_in, const float* shifts_chips, int high_dynamics)
+    {
+        if (!e || !local_code_in || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (channel_id < 0 || channel_id >= static_cast<int>(e->chans.size())) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        Channel& c = e->chans[channel_id];
+        // a new table may be read by launches already queued: allocate fresh if it must grow
+        if (code_length_chips > c.code_cap)
+            {
+                B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+                if (c.code_dev) B200_CUDA_TRY(cudaFree(c.code_dev));
+                c.code_cap = code_length_chips;
+                B200_CUDA_TRY(cudaMalloc(&c.code_dev, sizeof(float) * c.code_cap));
+            }
+        B200_CUDA_TRY(cudaMemcpyAsync(c.code_dev, local_code_in, sizeof(float) * code_length_chips, cudaMemcpyHostToDevice, e->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(e->stream));  // caller's buffer may go away
+        c.desc.code = c.code_dev;
+        c.desc.code_len = code_length_chips;
+        c.desc.high_dyn = high_dynamics ? 1 : 0;
+        for (int t = 0; t < c.desc.taps; t++) c.desc.shifts[t] = shifts_chips[t];
+        e->tables_dirty = true;
+        return B200_OK;
+    }
+
+    int b200_trk_batch_dev(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices)
+    {
+        if (!e || n_items < 0 || (n_items && (!items_dev || !out_dev)) || out_stride < 1) return B200_ERR_ARG;
+        if (n_items == 0) return B200_OK;
+        std::lock_guard<std::mutex> lk(e->mu);
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        int rc = upload_tables(e);
+        if (rc) return rc;
+        if (slices < 1) slices = 1;
+        rc = ensure_partials(e, n_items, slices);
+        if (rc) return rc;
+        rc = launch_trk_batch(items_dev, n_items, e->chans_dev, e->bands_dev, reinterpret_cast<float2*>(out_dev), out_stride,
+            slices, e->partial, e->counters, e->max_code_len, e->taps_uniform, e->stream);
+        if (rc == B200_OK) e->launches++;
+        return rc;
+    }
+
+    int b200_trk_batch(b200_engine* e, const b200_trk_item* items_host, int n_items, b200_cf32* out_host, int out_stride)
+    {
+        if (!e || n_items < 0 || (n_items && (!items_host || !out_host)) || out_stride < 1) return B200_ERR_ARG;
+        if (n_items == 0) return B200_OK;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            B200_CUDA_TRY(cudaSetDevice(e->device));
+            for (int i = 0; i < n_items; i++)
+                {
+                    const int ch = items_host[i].channel;
+                    if (ch < 0 || ch >= static_cast<int>(e->chans.size()) || e->chans[ch].desc.code == nullptr)
+                        {
+                            set_error("item %d: channel %d has no code table", i, ch);
+                            return B200_ERR_STATE;
+                        }
+                    if (e->chans[ch].desc.taps > out_stride)
+                        {
+                            set_error("item %d: out_stride %d < taps %d", i, out_stride, e->chans[ch].desc.taps);
+                            return B200_ERR_ARG;
+                        }
+                }
+            if (n_items > e->batch_cap)
+                {
+                    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+                    if (e->items_dev) B200_CUDA_TRY(cudaFree(e->items_dev));
+                    if (e->items_pin) B200_CUDA_TRY(cudaFreeHost(e->items_pin));
+                    e->batch_cap = n_items + n_items / 2 + 64;
+                    B200_CUDA_TRY(cudaMalloc(&e->items_dev, sizeof(b200_trk_item) * e->batch_cap));
+                    B200_CUDA_TRY(cudaMallocHost(&e->items_pin, sizeof(b200_trk_item) * e->batch_cap));
+                }
+            const int out_elems = n_items * out_stride;
+            if (out_elems > e->out_cap)
+                {
+                    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+                    if (e->out_dev) B200_CUDA_TRY(cudaFree(e->out_dev));
+                    if (e->out_pin) B200_CUDA_TRY(cudaFreeHost(e->out_pin));
+                    e->out_cap = out_elems + out_elems / 2 + 64;
+                    B200_CUDA_TRY(cudaMalloc(&e->out_dev, sizeof(float2) * e->out_cap));
+                    B200_CUDA_TRY(cudaMallocHost(&e->out_pin, sizeof(float2) * e->out_cap));
+                }
+            std::memcpy(e->items_pin, items_host, sizeof(b200_trk_item) * n_items);
+            B200_CUDA_TRY(cudaMemcpyAsync(e->items_dev, e->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->stream));
+            B200_CUDA_TRY(cudaMemsetAsync(e->out_dev, 0, sizeof(float2) * out_elems, e->stream));
+        }
+        // few items: split epochs into slices so the whole chip works on them
+        int slices = 1;
+        if (n_items < 592) slices = (592 + n_items - 1) / n_items;
+        if (slices > 64) slices = 64;
+        int rc = b200_trk_batch_dev(e, e->items_dev, n_items, reinterpret_cast<b200_cf32*>(e->out_dev), out_stride, slices);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaMemcpyAsync(e->out_pin, e->out_dev, sizeof(float2) * n_items * out_stride, cudaMemcpyDeviceToHost, e->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        std::memcpy(out_host, e->out_pin, sizeof(float2) * n_items * out_stride);
+        return B200_OK;
+    }
+}
+
+// ---- single correlator object (Cpu_Multicorrelator_Real_Codes shape) ----------------------------
+struct b200_trk
+{
+    b200_engine* e{nullptr};
+    int max_len{0};
+    int taps{0};
+    int high_dyn{0};
+    cudaStream_t stream{nullptr};
+    float2* sig_dev{nullptr};
+    float* code_dev{nullptr};
+    int code_cap{0};
+    // host-mapped control block: the kernel reads the item and descriptors and writes the taps
+    // straight into pinned host memory (no D2H memcpy on the latency path)
+    struct Ctl
+    {
+        b200_trk_item item;
+        ChanDesc chan;
+        BandDesc band;
+        float2 out[B200_MAX_TAPS];
+    };
+    Ctl* ctl{nullptr};
+    float2* partial{nullptr};
+    unsigned int* counter{nullptr};
+    int slices_cap{0};
+    bool have_code{false};
+};
+
+extern "C"
+{
+    int b200_trk_create(b200_engine* e, b200_trk** out, int max_signal_length_samples, int n_correlators)
+    {
+        if (!e || !out || max_signal_length_samples < 1) return B200_ERR_ARG;
+        if (n_correlators < 1 || n_correlators > B200_MAX_TAPS)
+            {
+                set_error("n_correlators %d outside 1..%d", n_correlators, B200_MAX_TAPS);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        b200_trk* t = new (std::nothrow) b200_trk();
+        if (!t) return B200_ERR_NOMEM;
+        t->e = e;
+        t->max_len = max_signal_length_samples;
+        t->taps = n_correlators;
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+        B200_CUDA_TRY(cudaMalloc(&t->sig_dev, sizeof(float2) * (static_cast<size_t>(t->max_len) + 2)));
+        B200_CUDA_TRY(cudaHostAlloc(&t->ctl, sizeof(b200_trk::Ctl), cudaHostAllocMapped));
+        std::memset(t->ctl, 0, sizeof(b200_trk::Ctl));
+        t->slices_cap = 64;
+        B200_CUDA_TRY(cudaMalloc(&t->partial, sizeof(float2) * trk_partial_elems(1, t->slices_cap)));
+        B200_CUDA_TRY(cudaMalloc(&t->counter, sizeof(unsigned int)));
+        B200_CUDA_TRY(cudaMemsetAsync(t->counter, 0, sizeof(unsigned int), t->stream));
+        *out = t;
+        return B200_OK;
+    }
+
+    int b200_trk_set_high_dynamics_resampler(b200_trk* t, int use_high_dynamics_resampler)
+    {
+        if (!t) return B200_ERR_ARG;
+        t->high_dyn = use_high_dynamics_resampler ? 1 : 0;
+        return B200_OK;
+    }
+
+    int b200_trk_set_local_code_and_taps(b200_trk* t, int code_length_chips, const float* local_code_in, const float* shifts_chips)
+    {
+        if (!t || !local_code_in || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        if (code_length_chips > t->code_cap)
+            {
+                if (t->code_dev) B200_CUDA_TRY(cudaFree(t->code_dev));
+                t->code_cap = code_length_chips;
+                B200_CUDA_TRY(cudaMalloc(&t->code_dev, sizeof(float) * t->code_cap));
+            }
+        B200_CUDA_TRY(cudaMemcpyAsync(t->code_dev, local_code_in, sizeof(float) * code_length_chips, cudaMemcpyHostToDevice, t->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        ChanDesc& c = t->ctl->chan;
+        c.code = t->code_dev;
+        c.code_len = code_length_chips;
+        c.taps = t->taps;
+        c.band = 0;
+        for (int k = 0; k < t->taps; k++) c.shifts[k] = shifts_chips[k];
+        t->have_code = true;
+        return B200_OK;
+    }
+
+    int b200_trk_correlate(b200_trk* t, const b200_cf32* sig_in_host,
+        float rem_carrier_phase_in_rad, float phase_step_rad, float phase_rate_step_rad,
+        float rem_code_phase_chips, float code_phase_step_chips, float code_phase_rate_step_chips,
+        int signal_length_samples, b200_cf32* corr_out_host)
+    {
+        if (!t || !sig_in_host || !corr_out_host) return B200_ERR_ARG;
+        if (!t->have_code)
+            {
+                set_error("correlate before set_local_code_and_taps");
+                return B200_ERR_STATE;
+            }
+        if (signal_length_samples < 0 || signal_length_samples > t->max_len)
+            {
+                set_error("signal_length_samples %d outside 0..%d", signal_length_samples, t->max_len);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        const int n = signal_length_samples;
+        if (n > 0) B200_CUDA_TRY(cudaMemcpyAsync(t->sig_dev, sig_in_host, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
+        b200_trk::Ctl* c = t->ctl;
+        c->chan.high_dyn = t->high_dyn;
+        c->band.base = t->sig_dev;
+        c->band.mask = ~0ULL;
+        c->band.first_index = 0;
+        c->item.channel = 0;
+        c->item.n = n;
+        c->item.sample_index = 0;
+        c->item.rem_carrier_phase_rad = rem_carrier_phase_in_rad;
+        c->item.phase_step_rad = phase_step_rad;
+        c->item.phase_rate_step_rad = phase_rate_step_rad;
+        c->item.rem_code_phase_chips = rem_code_phase_chips;
+        c->item.code_phase_step_chips = code_phase_step_chips;
+        c->item.code_phase_rate_step_chips = code_phase_rate_step_chips;
+        int slices = (n + 4 * kTrkTile - 1) / (4 * kTrkTile);
+        if (slices < 1) slices = 1;
+        if (slices > t->slices_cap) slices = t->slices_cap;
+        int rc = launch_trk_batch(&c->item, 1, &c->chan, &c->band, c->out, B200_MAX_TAPS, slices, t->partial, t->counter,
+            c->chan.code_len, t->taps == 1 || t->taps == 3 || t->taps == 5 ? t->taps : 0, t->stream);
+        if (rc) return rc;
+        {
+            std::lock_guard<std::mutex> lk(t->e->mu);
+            t->e->launches++;
+        }
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        for (int k = 0; k < t->taps; k++)
+            {
+                corr_out_host[k].re = c->out[k].x;
+                corr_out_host[k].im = c->out[k].y;
+            }
+        return B200_OK;
+    }
+
+    int b200_trk_destroy(b200_trk* t)
+    {
+        if (!t) return B200_ERR_ARG;
+        cudaSetDevice(t->e->device);
+        cudaStreamSynchronize(t->stream);
+        if (t->sig_dev) cudaFree(t->sig_dev);
+        if (t->code_dev) cudaFree(t->code_dev);
+        if (t->ctl) cudaFreeHost(t->ctl);
+        if (t->partial) cudaFree(t->partial);
+        if (t->counter) cudaFree(t->counter);
+        cudaStreamDestroy(t->stream);
+        delete t;
+        return B200_OK;
+    }
+}

@@ -1,0 +1,511 @@
+// Multi-tap tracking correlator for sm_100a.
+//
+// One CTA per (work item, slice).  A work item is one (channel, epoch): N complex samples of the
+// band store, one code table, up to 8 taps.  The kernel fuses what the reference does in three
+// passes over memory (VG = src/algorithms/libs/volk_gnsssdr_module/volk_gnsssdr):
+//   a1  VG kernels/volk_gnsssdr/volk_gnsssdr_32f_xn_resampler_32f_xn.h:362-435  (code resampling,
+//       never materialised here: the chip index is computed per sample in registers with the
+//       SAME float32 operation order as the a_avx/u_avx kernel, so indices are bit-identical),
+//   a2  VG kernels/volk_gnsssdr/volk_gnsssdr_32fc_32f_rotator_dot_prod_32fc_xn.h:155-314 (carrier
+//       rotation + E/P/L dot products),
+//   a3  src/algorithms/tracking/libs/cpu_multicorrelator_real_codes.cc:103-127 (phase set-up).
+//
+// Data movement: each sample is read exactly once per channel with coalesced 16-byte loads
+// (LDG.128 = 2 samples per lane); the code table is staged once per CTA in shared memory as an
+// "extended" table that already contains the wrap-around, so the inner loop has no modulo.
+// Reductions: registers -> warp shuffles -> shared memory -> (optionally) a deterministic
+// cross-CTA combine when an epoch is split into slices for latency.
+//
+// Carrier: phase(n) = -(rem + n*step) is kept as a 64-bit fixed-point fraction of a turn, so
+// every re-seed is exact to 2^-32 turn regardless of n; between re-seeds (kTrkReseed tiles) the
+// phasor advances by a complex multiply.  No tensor cores: there is no dense contraction here.
+
+#include "common.cuh"
+
+namespace b200
+{
+namespace
+{
+// ---- float32 chip-index arithmetic, bit-compatible with the reference -------------------------
+// a_avx/u_avx association (resampler .h:387,393-396): floor(fl(fl(step*n) + fl(shift - rem)))
+__device__ __forceinline__ int chip_index_avx(float step, float nf, float aux2)
+{
+    return __float2int_rd(__fadd_rn(__fmul_rn(step, nf), aux2));
+}
+// generic association (resampler .h:73 and the AVX kernels' scalar tail :423-433):
+// floor(fl(fl(fl(step*n) + shift) - rem))
+__device__ __forceinline__ int chip_index_generic(float step, float nf, float shift, float rem)
+{
+    return __float2int_rd(__fsub_rn(__fadd_rn(__fmul_rn(step, nf), shift), rem));
+}
+// high-dynamics association (..._high_dynamics_resampler_32f_xn.h:77):
+// floor(fl(fl(fl(fl(step*n) + fl(rate*(float)(n*n))) + shift0) - rem)), n*n in uint32 (wraps)
+__device__ __forceinline__ int chip_index_hd(float step, float rate, unsigned int n, float shift0, float rem)
+{
+    const float nf = static_cast<float>(n);
+    const float n2 = static_cast<float>(n * n);
+    return __float2int_rd(__fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(step, nf), __fmul_rn(rate, n2)), shift0), rem));
+}
+
+__device__ __forceinline__ int mod_pos(int k, int L)
+{
+    int r = k % L;
+    return r < 0 ? r + L : r;
+}
+
+// exp(j*2*pi*T/2^64)
+__device__ __forceinline__ float2 phasor_from_turns(unsigned long long T)
+{
+    const int hi = static_cast<int>(T >> 32);
+    const float x = static_cast<float>(hi) * 4.656612873077393e-10f;  // half-turns in [-1,1)
+    float s, c;
+    sincospif(x, &s, &c);
+    return make_float2(c, s);
+}
+
+// radians -> 64-bit fixed-point turns (two's complement, wraps naturally)
+__device__ __forceinline__ unsigned long long turns_from_rad(double rad)
+{
+    double t = rad * 0.15915494309189535;  // 1/(2*pi)
+    t -= rint(t);
+    return static_cast<unsigned long long>(__double2ll_rn(t * 18446744073709551616.0));
+}
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+__device__ __forceinline__ float4 ldg_stream16(const float2* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float2 ldg_stream8(const float2* p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+struct ItemCtx
+{
+    const float2* base;
+    unsigned long long mask;
+    unsigned long long s0;  // offset of the epoch's first sample in the band
+    unsigned long long T0;  // -rem_carrier in turns
+    unsigned long long DT;  // -phase_step in turns
+    float step, rem;
+    int N, body;            // body = 8*(N/8): samples using the AVX association
+};
+
+// Code lookup policies -----------------------------------------------------------------------
+// FAST: extended table in smem covering [tbl_base, tbl_base+span): no modulo in the loop.
+struct LookupExt
+{
+    const float* tb;  // smem_table - tbl_base
+    __device__ __forceinline__ float operator()(int idx) const { return tb[idx]; }
+};
+// GENERAL: any index range (multi-period epochs, pathological parameters): integer modulo,
+// table in smem when it fits, else global.
+struct LookupMod
+{
+    const float* tbl;
+    int L;
+    __device__ __forceinline__ float operator()(int idx) const { return tbl[mod_pos(idx, L)]; }
+};
+
+template <int TAPS, class Lookup>
+__device__ __forceinline__ void accumulate_sample(float2 x, float2 z, float m, const float (&aux2)[TAPS],
+    const Lookup& lut, float2 (&acc)[TAPS])
+{
+    const float wr = fmaf(x.x, z.x, -x.y * z.y);
+    const float wi = fmaf(x.x, z.y, x.y * z.x);
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+        {
+            const int idx = __float2int_rd(__fadd_rn(m, aux2[t]));
+            const float c = lut(idx);
+            acc[t].x = fmaf(wr, c, acc[t].x);
+            acc[t].y = fmaf(wi, c, acc[t].y);
+        }
+}
+
+template <int TAPS, class Lookup>
+__device__ __forceinline__ void correlate_range(const ItemCtx& cx, const float (&shifts)[TAPS], const Lookup& lut,
+    int tile_begin, int tile_end, int head, bool do_remainder, int n_main_end, float2 (&acc)[TAPS])
+{
+    const int tid = threadIdx.x;
+    float aux2[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) aux2[t] = __fsub_rn(shifts[t], cx.rem);
+
+    // ---- main tiles: all samples < body, 16-byte aligned pairs -------------------------------
+    const float2 D = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile));
+    for (int tg = tile_begin; tg < tile_end; tg += kTrkReseed)
+        {
+            const int tg_end = min(tg + kTrkReseed, tile_end);
+            int n0 = head + tg * kTrkTile + 2 * tid;
+            float2 za = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0));
+            float2 zb = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0 + 1));
+            float nf = static_cast<float>(n0);
+#pragma unroll 4
+            for (int tile = tg; tile < tg_end; tile++)
+                {
+                    const float4 v = ldg_stream16(cx.base + ((cx.s0 + static_cast<unsigned long long>(n0)) & cx.mask));
+                    accumulate_sample<TAPS>(make_float2(v.x, v.y), za, __fmul_rn(cx.step, nf), aux2, lut, acc);
+                    accumulate_sample<TAPS>(make_float2(v.z, v.w), zb, __fmul_rn(cx.step, nf + 1.0f), aux2, lut, acc);
+                    za = cmulf(za, D);
+                    zb = cmulf(zb, D);
+                    n0 += kTrkTile;
+                    nf += static_cast<float>(kTrkTile);
+                }
+        }
+
+    // ---- remainder: optional head sample 0 and everything from n_main_end to N ------------------
+    if (do_remainder)
+        {
+            const int count = head + (cx.N - n_main_end);
+            for (int r = tid; r < count; r += kTrkThreads)
+                {
+                    const int n = (r < head) ? 0 : n_main_end + (r - head);
+                    const float2 x = ldg_stream8(cx.base + ((cx.s0 + static_cast<unsigned long long>(n)) & cx.mask));
+                    const float2 z = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n));
+                    const float wr = fmaf(x.x, z.x, -x.y * z.y);
+                    const float wi = fmaf(x.x, z.y, x.y * z.x);
+                    const float nf = static_cast<float>(n);
+#pragma unroll
+                    for (int t = 0; t < TAPS; t++)
+                        {
+                            const int idx = (n < cx.body) ? chip_index_avx(cx.step, nf, aux2[t])
+                                                          : chip_index_generic(cx.step, nf, shifts[t], cx.rem);
+                            const float c = lut(idx);
+                            acc[t].x = fmaf(wr, c, acc[t].x);
+                            acc[t].y = fmaf(wi, c, acc[t].y);
+                        }
+                }
+        }
+}
+
+// High-dynamics variant (a4): quadratic code phase on tap 0, other taps are circular
+// integer-sample shifts of tap 0's resampled sequence; carrier has a phase-rate term that lags
+// one sample (..._high_dynamic_rotator_dot_prod_32fc_xn.h:92-103).  Not the throughput path:
+// one sample per thread per step, exact phasor per sample.
+template <int TAPS, class Lookup>
+__device__ __forceinline__ void correlate_range_hd(const ItemCtx& cx, float rate, unsigned long long RT,
+    const float (&shifts)[TAPS], const Lookup& lut, int n_begin, int n_end, float2 (&acc)[TAPS])
+{
+    int shift_samples[TAPS];
+    shift_samples[0] = 0;
+    unsigned int ss = 0;
+#pragma unroll
+    for (int t = 1; t < TAPS; t++)
+        {
+            // (int)round((shifts[t]-shifts[t-1])/step) in double like C's round() on a float expr
+            ss += static_cast<unsigned int>(static_cast<int>(round(static_cast<double>(__fdiv_rn(__fsub_rn(shifts[t], shifts[t - 1]), cx.step)))));
+            shift_samples[t] = static_cast<int>(ss);
+        }
+    for (int n = n_begin + threadIdx.x; n < n_end; n += kTrkThreads)
+        {
+            const float2 x = ldg_stream8(cx.base + ((cx.s0 + static_cast<unsigned long long>(n)) & cx.mask));
+            // rate exponent: (n-1)^2 for n>=1 with the reference's uint32 wrap of k*k, as float
+            unsigned long long T = cx.T0 + cx.DT * static_cast<unsigned long long>(n);
+            if (n >= 1)
+                {
+                    const unsigned int k = static_cast<unsigned int>(n - 1);
+                    const float e = static_cast<float>(k * k);
+                    // RT is the per-unit rate in turns; e is an integer-valued float < 2^32
+                    T += RT * static_cast<unsigned long long>(e);
+                }
+            const float2 z = phasor_from_turns(T);
+            const float wr = fmaf(x.x, z.x, -x.y * z.y);
+            const float wi = fmaf(x.x, z.y, x.y * z.x);
+#pragma unroll
+            for (int t = 0; t < TAPS; t++)
+                {
+                    unsigned int m = static_cast<unsigned int>(n) + static_cast<unsigned int>(shift_samples[t]);
+                    if (m >= static_cast<unsigned int>(cx.N)) m -= static_cast<unsigned int>(cx.N);
+                    const int idx = chip_index_hd(cx.step, rate, m, shifts[0], cx.rem);
+                    const float c = lut(idx);
+                    acc[t].x = fmaf(wr, c, acc[t].x);
+                    acc[t].y = fmaf(wi, c, acc[t].y);
+                }
+        }
+}
+
+template <int TAPS>
+__device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const BandDesc& bd, float* smem_tbl,
+    int tbl_cap, float2* smem_red, int slice, int slices, float2 (&result)[TAPS])
+{
+    const int tid = threadIdx.x;
+    ItemCtx cx;
+    cx.base = bd.base;
+    cx.mask = bd.mask;
+    cx.s0 = it.sample_index - bd.first_index;
+    cx.N = it.n;
+    cx.body = (it.n / 8) * 8;
+    cx.step = it.code_phase_step_chips;
+    cx.rem = it.rem_code_phase_chips;
+    cx.T0 = turns_from_rad(-static_cast<double>(it.rem_carrier_phase_rad));
+    cx.DT = turns_from_rad(-static_cast<double>(it.phase_step_rad));
+    const int L = ch.code_len;
+
+    float shifts[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) shifts[t] = ch.shifts[t];
+
+    float2 acc[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) acc[t] = make_float2(0.f, 0.f);
+
+    if (ch.high_dyn)
+        {
+            // table of exactly L entries (smem if it fits), modulo lookup
+            const bool in_smem = L <= tbl_cap;
+            if (in_smem)
+                {
+                    for (int j = tid; j < L; j += kTrkThreads) smem_tbl[j] = ch.code[j];
+                }
+            __syncthreads();
+            LookupMod lut{in_smem ? smem_tbl : ch.code, L};
+            const unsigned long long RT = turns_from_rad(-static_cast<double>(it.phase_rate_step_rad));
+            const int per = (cx.N + slices - 1) / slices;
+            const int nb = min(cx.N, slice * per), ne = min(cx.N, nb + per);
+            correlate_range_hd<TAPS>(cx, it.code_phase_rate_step_chips, RT, shifts, lut, nb, ne, acc);
+        }
+    else
+        {
+            // index range over the epoch (monotone in n within each association)
+            long long lo = 0x7fffffff, hi = -0x7fffffff - 1LL;
+            const float nl_avx = static_cast<float>(max(cx.body - 1, 0));
+            const float n_last = static_cast<float>(max(cx.N - 1, 0));
+            const float n_body = static_cast<float>(cx.body);
+#pragma unroll
+            for (int t = 0; t < TAPS; t++)
+                {
+                    const float a2 = __fsub_rn(shifts[t], cx.rem);
+                    int v[4];
+                    v[0] = chip_index_avx(cx.step, 0.f, a2);
+                    v[1] = chip_index_avx(cx.step, nl_avx, a2);
+                    v[2] = chip_index_generic(cx.step, n_body, shifts[t], cx.rem);
+                    v[3] = chip_index_generic(cx.step, n_last, shifts[t], cx.rem);
+                    // association 0 also evaluated at n = 0 (epochs shorter than 8 samples)
+                    const int v4 = chip_index_generic(cx.step, 0.f, shifts[t], cx.rem);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        {
+                            lo = min(lo, static_cast<long long>(v[q]));
+                            hi = max(hi, static_cast<long long>(v[q]));
+                        }
+                    lo = min(lo, static_cast<long long>(v4));
+                    hi = max(hi, static_cast<long long>(v4));
+                }
+            const long long tbl_base = lo - 2;
+            const long long span = hi - lo + 5;
+
+            const int head = static_cast<int>(cx.s0 & 1ULL);
+            const int ntiles = (cx.body > head) ? (cx.body - head) / kTrkTile : 0;
+            const int n_main_end = head + ntiles * kTrkTile;
+            const int tb = static_cast<int>((static_cast<long long>(ntiles) * slice) / slices);
+            const int te = static_cast<int>((static_cast<long long>(ntiles) * (slice + 1)) / slices);
+            const bool rem_here = (slice == slices - 1);
+
+            if (span <= static_cast<long long>(tbl_cap))
+                {
+                    const int base_i = static_cast<int>(tbl_base);
+                    int r = mod_pos(base_i + tid, L);
+                    const int stride = kTrkThreads % L;
+                    for (int j = tid; j < static_cast<int>(span); j += kTrkThreads)
+                        {
+                            smem_tbl[j] = ch.code[r];
+                            r += stride;
+                            if (r >= L) r -= L;
+                        }
+                    __syncthreads();
+                    LookupExt lut{smem_tbl - base_i};
+                    correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                }
+            else
+                {
+                    const bool in_smem = L <= tbl_cap;
+                    if (in_smem)
+                        {
+                            for (int j = tid; j < L; j += kTrkThreads) smem_tbl[j] = ch.code[j];
+                        }
+                    __syncthreads();
+                    LookupMod lut{in_smem ? smem_tbl : ch.code, L};
+                    correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                }
+        }
+
+    // ---- CTA reduction: shuffles, then 8 warp partials through shared memory -------------------
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+        {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                {
+                    acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, o);
+                    acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, o);
+                }
+        }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0)
+        {
+#pragma unroll
+            for (int t = 0; t < TAPS; t++) smem_red[warp * B200_MAX_TAPS + t] = acc[t];
+        }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+        {
+            float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < kTrkThreads / 32; w++)
+                {
+                    const float2 p = smem_red[w * B200_MAX_TAPS + t];
+                    s.x += p.x;
+                    s.y += p.y;
+                }
+            result[t] = s;
+        }
+}
+
+template <int TAPS>
+__device__ __forceinline__ void run_item(const b200_trk_item& it, const ChanDesc& ch, const BandDesc& bd,
+    float* smem_tbl, int tbl_cap, float2* smem_red, int* smem_flag, int item_id, int slice, int slices,
+    float2* out, int out_stride, float2* partial, unsigned int* counters)
+{
+    float2 result[TAPS];
+    process_item<TAPS>(it, ch, bd, smem_tbl, tbl_cap, smem_red, slice, slices, result);
+    const int tid = threadIdx.x;
+    if (slices == 1)
+        {
+            if (tid < TAPS) out[static_cast<size_t>(item_id) * out_stride + tid] = result[tid];
+            return;
+        }
+    // deterministic cross-CTA combine: every slice publishes its partial; the last one to arrive
+    // adds them in slice order.
+    float2* my = partial + (static_cast<size_t>(item_id) * slices + slice) * B200_MAX_TAPS;
+    if (tid < TAPS) my[tid] = result[tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+        {
+            const unsigned int prev = atomicAdd(&counters[item_id], 1u);
+            *smem_flag = (prev == static_cast<unsigned int>(slices - 1));
+        }
+    __syncthreads();
+    if (*smem_flag)
+        {
+            __threadfence();
+            if (tid < TAPS)
+                {
+                    float2 s = make_float2(0.f, 0.f);
+                    const volatile float2* p = partial + static_cast<size_t>(item_id) * slices * B200_MAX_TAPS;
+                    for (int k = 0; k < slices; k++)
+                        {
+                            s.x += p[k * B200_MAX_TAPS + tid].x;
+                            s.y += p[k * B200_MAX_TAPS + tid].y;
+                        }
+                    out[static_cast<size_t>(item_id) * out_stride + tid] = s;
+                }
+            if (tid == 0) counters[item_id] = 0u;  // ready for the next launch
+        }
+}
+
+// TAPS_T > 0: every channel in the launch has exactly TAPS_T taps (specialised registers).
+// TAPS_T == 0: taps read per item.
+template <int TAPS_T>
+__global__ void __launch_bounds__(kTrkThreads) trk_correlate_kernel(const b200_trk_item* __restrict__ items, int n_items,
+    const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, float2* __restrict__ out, int out_stride,
+    int slices, float2* partial, unsigned int* counters, int tbl_cap)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* smem_tbl = smem;
+    float2* smem_red = reinterpret_cast<float2*>(smem + tbl_cap);
+    int* smem_flag = reinterpret_cast<int*>(smem_red + (kTrkThreads / 32) * B200_MAX_TAPS);
+
+    for (int w = blockIdx.x; w < n_items * slices; w += gridDim.x)
+        {
+            const int item_id = w / slices;
+            const int slice = w - item_id * slices;
+            const b200_trk_item it = items[item_id];
+            const ChanDesc& ch = chans[it.channel];
+            const BandDesc bd = bands[ch.band];
+            if (w != static_cast<int>(blockIdx.x)) __syncthreads();  // smem reuse across items
+            if (it.n <= 0)
+                {
+                    if (slice == 0 && threadIdx.x < ch.taps) out[static_cast<size_t>(item_id) * out_stride + threadIdx.x] = make_float2(0.f, 0.f);
+                    continue;
+                }
+            if (TAPS_T > 0)
+                {
+                    run_item<(TAPS_T > 0 ? TAPS_T : 1)>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters);
+                }
+            else
+                {
+                    switch (ch.taps)
+                        {
+                        case 1: run_item<1>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        case 2: run_item<2>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        case 3: run_item<3>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        case 4: run_item<4>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        case 5: run_item<5>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        case 6: run_item<6>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        case 7: run_item<7>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        default: run_item<8>(it, ch, bd, smem_tbl, tbl_cap, smem_red, smem_flag, item_id, slice, slices, out, out_stride, partial, counters); break;
+                        }
+                }
+        }
+}
+
+template <int T>
+int launch_one(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands, float2* out,
+    int out_stride, int slices, float2* partial, unsigned int* counters, int tbl_cap, size_t smem_bytes, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set)
+        {
+            B200_CUDA_TRY(cudaFuncSetAttribute(trk_correlate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+    const long long work = static_cast<long long>(n_items) * slices;
+    // plain grid for moderate sizes, grid-stride beyond (keeps blockIdx math in int)
+    const int grid = static_cast<int>(work < (1LL << 20) ? work : (1LL << 20));
+    trk_correlate_kernel<T><<<grid, kTrkThreads, smem_bytes, stream>>>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+}  // namespace
+
+size_t trk_partial_elems(int n_items, int slices)
+{
+    return static_cast<size_t>(n_items) * static_cast<size_t>(slices) * B200_MAX_TAPS;
+}
+
+int launch_trk_batch(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands,
+    float2* out, int out_stride, int slices, float2* partial, unsigned int* counters,
+    int max_code_len, int taps_uniform, cudaStream_t stream)
+{
+    if (n_items <= 0) return B200_OK;
+    if (slices < 1) slices = 1;
+    int tbl_cap = max_code_len + kTrkTablePad;
+    const int cap_limit = (200 * 1024 - 1024) / 4;
+    if (tbl_cap > cap_limit) tbl_cap = cap_limit;
+    tbl_cap = (tbl_cap + 3) & ~3;
+    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kTrkThreads / 32) * B200_MAX_TAPS * sizeof(float2) + 16;
+    switch (taps_uniform)
+        {
+        case 1: return launch_one<1>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
+        case 3: return launch_one<3>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
+        case 5: return launch_one<5>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
+        default: return launch_one<0>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
+        }
+}
+
+}  // namespace b200

@@ -1,0 +1,305 @@
+"""GPU parity tests for the tracking correlator, all through the C ABI (libb200gnss.so).
+
+Oracles: the reference's own Cpu_Multicorrelator_Real_Codes / volk_gnsssdr kernels
+(oracle.ref, prebuilt oracle/_ref/liboracle_ref.so) when present, else the pinned C port
+(oracle.port); plus the float64 truth.  Tolerances:
+  * integer-exact configurations: EXACT equality (this is what pins the chip indices);
+  * float data: |gpu - avx_oracle| / |avx_oracle| < 1e-3  (the reference's own SIMD-vs-generic
+    bound, VG lib/kernel_tests.h:41,87-89) and |gpu - f64 truth| < 1e-5 * |prompt|.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from gnss_synth import make_iq, trk_params_for  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import gnss_sdr_b200.capi as c
+    return c
+
+
+@pytest.fixture(scope="module")
+def engine(capi):
+    e = capi.Engine(0)
+    yield e
+    e.close()
+
+
+def int_oracle(x_int, code_int, idx):
+    """exact integer correlation given chip indices (taps x n)."""
+    return np.array([np.sum(x_int * code_int[idx[t]]) for t in range(idx.shape[0])], dtype=np.int64)
+
+
+SHAPES = [
+    # n, L, shifts, rem, step
+    (25000, 1023, [-0.5, 0.0, 0.5], 0.37, 1.023e6 * (1 + 3000 / 1575.42e6) / 25e6),
+    (25001, 1023, [-0.5, 0.0, 0.5], 0.93, 1.023e6 * (1 - 4500 / 1575.42e6) / 25e6),
+    (200000, 8184, [-1.2, -0.3, 0.0, 0.3, 1.2], 1.71, 2 * 1.023e6 / 50e6),
+    (4000, 1023, [-0.5, 0.0, 0.5], -0.25, 1.023e6 / 4e6),
+    (8111, 2046, [-0.1, 0.0, 0.1], -0.234, (2046 + 0.1) / 8111),
+    (511, 1023, [-0.5, 0.0, 0.5], 0.1, 1.9),
+    (512, 1023, [-0.5, 0.0, 0.5], 0.1, 1.9),
+    (513, 1023, [-0.5, 0.0, 0.5], 0.1, 1.9),
+    (1031, 1023, [0.0], 0.6, 0.99),
+    (7, 11, [-0.5, 0.0], 0.2, 1.9),
+    (1, 1023, [-0.5, 0.0, 0.5], 0.0, 0.04),
+    (100000, 1023, [-0.5, 0.0, 0.5], 0.37, 0.0409),        # 4 code periods: general (modulo) path
+    (6000, 1023, [-700.25, 0.0, 1500.5], 3.3, 0.7),         # far-apart taps: general path
+    (3000, 1023, [-0.5, -0.25, -0.1, 0.0, 0.1, 0.25, 0.5, 0.75], 0.3, 0.341),  # 8 taps
+    (3000, 1023, [-0.5, 0.5], 0.3, 0.341),
+    (3000, 1023, [-0.5, -0.2, 0.2, 0.5], 0.3, 0.341),
+]
+
+
+@pytest.mark.parametrize("n,L,shifts,rem,step", SHAPES)
+def test_single_correlator_integer_exact(capi, engine, oracle, n, L, shifts, rem, step):
+    """Small-integer samples and code values, zero carrier: every partial sum is an exactly
+    representable integer, so the GPU result must EQUAL the integer oracle built from the
+    AVX-association chip indices.  One wrong index changes the sum."""
+    rng = np.random.default_rng(n + L)
+    x_int = rng.integers(-7, 8, n)
+    x_int[x_int == 0] = 1
+    code_int = ((np.arange(L) * 7919) % 31) - 15
+    code_int[code_int == 0] = 16
+    _, idx = oracle.port.resampler(1, code_int.astype(np.float32), rem, step, shifts, n, return_idx=True)
+    want = int_oracle(x_int, code_int, idx)
+    mc = capi.Multicorrelator(engine, n, len(shifts))
+    mc.set_high_dynamics_resampler(False)
+    mc.set_local_code_and_taps(code_int.astype(np.float32), shifts)
+    got = mc.Carrier_wipeoff_multicorrelator_resampler(x_int.astype(np.complex64), 0.0, 0.0, 0.0, rem, step, 0.0)
+    mc.free()
+    assert np.array_equal(got.real.astype(np.int64), want)
+    assert np.all(got.imag == 0)
+
+
+@pytest.mark.parametrize("first,offset", [(0, 0), (0, 1), (0, 2), (0, 3), (0, 255), (0, 511), (0, 513),
+                                          (1000000, 0), (1000000, 1), (1000000, 2047), (5000, 7)])
+def test_batch_sample_offsets_integer_exact(capi, engine, oracle, first, offset):
+    """Epochs starting at odd/even absolute sample indices of a shared ring band (alignment
+    peel), including epochs that wrap around the end of the ring."""
+    n, L, shifts, rem, step = 5003, 1023, [-0.5, 0.0, 0.5], 0.37, 0.2051
+    rng = np.random.default_rng(first + offset)
+    total = 8192
+    x_int = rng.integers(-7, 8, total)
+    code_int = ((np.arange(L) * 7919) % 31) - 15
+    e = engine
+    band = 3
+    e.iq_create(band, total)
+    # advance the ring so absolute indices are large and the data wraps around the ring end
+    pad = np.zeros(total, np.complex64)
+    done = 0
+    while done < first:
+        k = min(total, first - done)
+        e.iq_push(band, pad[:k])
+        done += k
+    f0 = e.iq_push(band, x_int.astype(np.complex64))
+    assert f0 == first
+    cid = e.channel_create(band, 3)
+    e.channel_set_code(cid, code_int.astype(np.float32), shifts)
+    s_idx = first + offset
+    items = np.zeros(1, capi.TRK_ITEM_DTYPE)
+    items["channel"] = cid
+    items["n"] = n
+    items["sample_index"] = s_idx
+    items["rem_code_phase_chips"] = rem
+    items["code_phase_step_chips"] = step
+    got = e.trk_batch(items, 3)[0]
+    xs = x_int[offset: offset + n]
+    _, idx = oracle.port.resampler(1, code_int.astype(np.float32), rem, step, shifts, n, return_idx=True)
+    want = int_oracle(xs, code_int, idx)
+    assert np.array_equal(got.real.astype(np.int64), want)
+    assert np.all(got.imag == 0)
+
+
+def _ref_or_port_avx(oracle, iq, code, shifts, rem_carr, dphi, rem_code, step):
+    if oracle.ref is not None:
+        oracle.ref.select_arch("a_avx")
+        h = oracle.ref.mc_create(len(iq), len(shifts), high_dyn=False)
+        oracle.ref.mc_set_code(h, code, shifts)
+        out = oracle.ref.mc_correlate(h, iq, len(shifts), rem_carr, dphi, 0.0, rem_code, step, 0.0)
+        oracle.ref.mc_destroy(h)
+        return out
+    return oracle.port.multicorrelator(1, iq, code, shifts, rem_carr, dphi, rem_code, step)
+
+
+@pytest.mark.parametrize("fs,n,prn,doppler,shifts", [
+    (25e6, 25000, 7, 3217.0, [-0.5, 0.0, 0.5]),
+    (25e6, 25000, 19, -4711.0, [-0.5, 0.0, 0.5]),
+    (4e6, 4000, 1, 1680.0, [-0.5, 0.0, 0.5]),
+    (4e6, 8000, 3, -2500.0, [-0.25, 0.0, 0.25]),
+])
+def test_single_correlator_signal_parity(capi, engine, oracle, fs, n, prn, doppler, shifts):
+    code = oracle.port.gps_ca_code(prn)
+    sv = dict(prn=prn, doppler=doppler, code_phase_chips=417.3, cn0=45.0, phase0=0.9)
+    iq = make_iq({prn: code}, fs, n, [sv], seed=prn)
+    _, rem_carr, dphi, rem_code, step = trk_params_for(sv, fs, n, 1)
+    args = (float(rem_carr[0]), float(dphi[0]), float(rem_code[0]), float(step[0]))
+    want = _ref_or_port_avx(oracle, iq, code, shifts, *args)
+    truth = oracle.port.multicorrelator_f64(1, iq, code, shifts, *args)
+    mc = capi.Multicorrelator(engine, n, len(shifts))
+    mc.set_high_dynamics_resampler(False)
+    mc.set_local_code_and_taps(code, shifts)
+    got = mc.Carrier_wipeoff_multicorrelator_resampler(iq, args[0], args[1], 0.0, args[2], args[3], 0.0)
+    mc.free()
+    # the prompt must be a real peak for the test to mean anything
+    assert np.abs(truth[1]) > 5 * np.sqrt(n)
+    assert np.all(np.abs(got - want) / np.abs(want) < 1e-3)            # the reference's own bound
+    assert np.max(np.abs(got - truth)) / np.abs(truth[1]) < 1e-5         # vs float64 truth
+    # and we must be at least as close to the truth as the reference's SIMD path is
+    assert np.max(np.abs(got - truth)) <= np.max(np.abs(want - truth)) * 1.5 + 1e-6 * np.abs(truth[1])
+
+
+def test_galileo_e1_five_taps_parity(capi, engine, oracle):
+    """C3 shape: N=200000 @ 50 Msps, sinBOC(1,1) table of 8184 values, VE/E/P/L/VL."""
+    rng = np.random.default_rng(33)
+    primary = rng.choice([-1, 1], 4092)
+    code = oracle.port.sinboc11(primary)
+    fs, n = 50e6, 200000
+    shifts = np.array([-0.6, -0.15, 0.0, 0.15, 0.6], np.float32) * 2
+    sv = dict(prn=1, doppler=-1234.5, code_phase_chips=1000.25, cn0=42.0, phase0=2.1)
+    iq = make_iq({1: code}, fs, n, [sv], seed=33, chips_per_table_chip=2.0)
+    _, rem_carr, dphi, rem_code, step = trk_params_for(sv, fs, n, 1, table_chips_per_chip=2.0, L=8184)
+    args = (float(rem_carr[0]), float(dphi[0]), float(rem_code[0]), float(step[0]))
+    want = _ref_or_port_avx(oracle, iq, code, shifts, *args)
+    truth = oracle.port.multicorrelator_f64(1, iq, code, shifts, *args)
+    mc = capi.Multicorrelator(engine, n, 5)
+    mc.set_high_dynamics_resampler(False)
+    mc.set_local_code_and_taps(code, shifts)
+    got = mc.Carrier_wipeoff_multicorrelator_resampler(iq, args[0], args[1], 0.0, args[2], args[3], 0.0)
+    mc.free()
+    assert np.abs(truth[2]) > 5 * np.sqrt(n)
+    assert np.all(np.abs(got - want) / np.abs(want) < 1e-3)
+    assert np.max(np.abs(got - truth)) / np.abs(truth[2]) < 1e-5
+
+
+def test_batch_c2_slice_of_baseline_config(capi, engine, oracle):
+    """C2 (32 channels x 25 Msps) on a 40-epoch slice: batched launch == per-epoch oracle."""
+    fs, n, nch, nep = 25e6, 25000, 32, 40
+    rng = np.random.default_rng(2)
+    codes = {p: oracle.port.gps_ca_code(p) for p in range(1, nch + 1)}
+    svs = [dict(prn=p, doppler=float(rng.uniform(-5000, 5000)), code_phase_chips=float(rng.uniform(0, 1023)),
+                cn0=45.0, phase0=float(rng.uniform(0, 6.28))) for p in range(1, nch + 1)]
+    iq = make_iq(codes, fs, n * nep + 64, svs, seed=2)
+    e = engine
+    band = 1
+    e.iq_create(band, len(iq))
+    first = e.iq_push(band, iq)
+    shifts = [-0.5, 0.0, 0.5]
+    items = np.zeros(nch * nep, capi.TRK_ITEM_DTYPE)
+    cids = []
+    for sv in svs:
+        cid = e.channel_create(band, 3)
+        e.channel_set_code(cid, codes[sv["prn"]], shifts)
+        cids.append(cid)
+    params = []
+    for c, sv in enumerate(svs):
+        s, rc, dp, rcode, st = trk_params_for(sv, fs, n, nep)
+        for k in range(nep):
+            it = items[k * nch + c]   # epoch-major order: channels of one epoch are neighbours
+            it["channel"] = cids[c]
+            it["n"] = n
+            it["sample_index"] = first + int(s[k])
+            it["rem_carrier_phase_rad"] = rc[k]
+            it["phase_step_rad"] = dp[k]
+            it["rem_code_phase_chips"] = rcode[k]
+            it["code_phase_step_chips"] = st[k]
+    got = e.trk_batch(items, 3)
+    # oracle on a subset of items (every 7th) to keep the CPU side quick
+    worst_ref, worst_truth = 0.0, 0.0
+    for i in range(0, len(items), 7):
+        it = items[i]
+        sv = svs[i % nch]
+        seg = iq[int(it["sample_index"]) - first: int(it["sample_index"]) - first + n]
+        a = (float(it["rem_carrier_phase_rad"]), float(it["phase_step_rad"]), float(it["rem_code_phase_chips"]),
+             float(it["code_phase_step_chips"]))
+        want = _ref_or_port_avx(oracle, seg, codes[sv["prn"]], shifts, *a)
+        truth = oracle.port.multicorrelator_f64(1, seg, codes[sv["prn"]], shifts, *a)
+        worst_ref = max(worst_ref, float(np.max(np.abs(got[i] - want) / np.abs(want))))
+        worst_truth = max(worst_truth, float(np.max(np.abs(got[i] - truth)) / np.abs(truth[1])))
+        assert np.abs(truth[1]) > 3 * np.sqrt(n)
+    assert worst_ref < 1e-3
+    assert worst_truth < 1e-5
+
+
+def test_batch_slices_agree_and_are_deterministic(capi, engine, oracle):
+    """Splitting an epoch over 1..64 CTAs changes only the float summation order (tiny) and
+    repeated launches are bitwise identical (deterministic cross-CTA combine)."""
+    import torch
+    n, L = 25000, 1023
+    rng = np.random.default_rng(5)
+    iq = (rng.standard_normal(n + 8) + 1j * rng.standard_normal(n + 8)).astype(np.complex64)
+    code = oracle.port.gps_ca_code(5)
+    e = engine
+    band = 2
+    iq_t = torch.from_numpy(iq.view(np.float32)).cuda()
+    e.iq_attach_dev(band, iq_t.data_ptr(), n + 8, 0)
+    cid = e.channel_create(band, 3)
+    e.channel_set_code(cid, code, [-0.5, 0.0, 0.5])
+    items = np.zeros(1, capi.TRK_ITEM_DTYPE)
+    items["channel"] = cid
+    items["n"] = n
+    items["sample_index"] = 3
+    items["rem_carrier_phase_rad"] = 0.3
+    items["phase_step_rad"] = 1e-3
+    items["rem_code_phase_chips"] = 0.2
+    items["code_phase_step_chips"] = 0.04092
+    items_t = torch.from_numpy(items.view(np.uint8)).cuda()
+    outs = {}
+    for slices in (1, 2, 7, 16, 64):
+        reps = []
+        for _ in range(3):
+            out_t = torch.zeros(8, 2, dtype=torch.float32, device="cuda")
+            e.trk_batch_dev(items_t.data_ptr(), 1, out_t.data_ptr(), 8, slices)
+            e.sync()
+            reps.append(out_t.cpu().numpy().copy())
+        assert np.array_equal(reps[0], reps[1]) and np.array_equal(reps[0], reps[2])
+        outs[slices] = reps[0][:3, 0] + 1j * reps[0][:3, 1]
+    for s, v in outs.items():
+        assert np.max(np.abs(v - outs[1])) / np.max(np.abs(outs[1])) < 2e-5, s
+
+
+def test_mixed_tap_counts_in_one_batch(capi, engine, oracle):
+    """Galileo-style: a 5-tap pilot channel and a 1-tap data channel in the same launch
+    (dll_pll_veml_tracking.cc:1246-1256)."""
+    n, L = 6000, 2046
+    rng = np.random.default_rng(8)
+    x_int = rng.integers(-7, 8, n)
+    code_a = ((np.arange(L) * 7919) % 31) - 15
+    code_b = ((np.arange(L) * 104729) % 29) - 14
+    e = engine
+    band = 4
+    e.iq_create(band, 8192)
+    first = e.iq_push(band, x_int.astype(np.complex64))
+    sh5 = [-1.2, -0.3, 0.0, 0.3, 1.2]
+    ca = e.channel_create(band, 5)
+    cb = e.channel_create(band, 1)
+    e.channel_set_code(ca, code_a.astype(np.float32), sh5)
+    e.channel_set_code(cb, code_b.astype(np.float32), [0.0])
+    items = np.zeros(2, capi.TRK_ITEM_DTYPE)
+    items["channel"] = [ca, cb]
+    items["n"] = n
+    items["sample_index"] = first
+    items["rem_code_phase_chips"] = 0.41
+    items["code_phase_step_chips"] = 0.3411
+    got = e.trk_batch(items, 5)
+    _, ia = oracle.port.resampler(1, code_a.astype(np.float32), 0.41, 0.3411, sh5, n, return_idx=True)
+    _, ib = oracle.port.resampler(1, code_b.astype(np.float32), 0.41, 0.3411, [0.0], n, return_idx=True)
+    assert np.array_equal(got[0].real.astype(np.int64), int_oracle(x_int, code_a, ia))
+    assert np.array_equal(got[1, :1].real.astype(np.int64), int_oracle(x_int, code_b, ib))
+
+
+def test_error_paths(capi, engine):
+    with pytest.raises(capi.B200Error):
+        capi.Multicorrelator(engine, 1000, 9)         # too many taps
+    mc = capi.Multicorrelator(engine, 1000, 3)
+    with pytest.raises(capi.B200Error):               # correlate before set_local_code
+        mc.Carrier_wipeoff_multicorrelator_resampler(np.zeros(10, np.complex64), 0, 0, 0, 0, 0.1, 0)
+    mc.set_local_code_and_taps(np.ones(1023, np.float32), [-0.5, 0, 0.5])
+    with pytest.raises(capi.B200Error):               # longer than init() allowed
+        mc.Carrier_wipeoff_multicorrelator_resampler(np.zeros(2000, np.complex64), 0, 0, 0, 0, 0.1, 0)
+    out = mc.Carrier_wipeoff_multicorrelator_resampler(np.zeros(0, np.complex64), 0, 0, 0, 0, 0.1, 0, 0)
+    assert np.all(out == 0)
+    mc.free()
