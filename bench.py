@@ -107,7 +107,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -187,7 +187,7 @@ def cpu_baseline(budget_s=12.0):
             oracle.port.multicorrelator_batch(1, cores, idx_iq, 0, code, SHIFTS, params, EPOCH)
             return time.perf_counter() - t0
     t = run(20)
-    iters = int(max(20, min(20000, 20 * budget_s / max(t, 1e-6))))
+    iters = int(max(20, min(400000, 20 * budget_s / max(t, 1e-6))))
     t = run(iters)
     samples = cores * iters * EPOCH
     return {"value": samples / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
@@ -222,7 +222,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,7 +252,12 @@ def main():
     n_iq = EPOCH * N_EPOCHS
     iq_dev = synth_iq_device(torch, codes, svs, n_iq + 16, SEED + rank, dev)
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream is made current and handed to the engine, so that the
+    # torch.cuda.Event timings below are recorded on the very stream the kernels are launched on
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     eng = capi.Engine(local_rank, stream)
     # band 0: attached device-resident IQ (value); band 1: ring fed from pinned host memory (e2e)
     eng.iq_attach_dev(0, iq_dev.data_ptr(), n_iq + 16, 0)
@@ -290,10 +295,14 @@ def main():
         step_dev()
         ev[k + 1].record()
     barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    launches = eng.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launches = eng.launch_count() - l0
+    # cross-check with the library's own CUDA-event timer on the engine stream (one extra step)
+    eng.timer_start()
+    step_dev()
+    check_ms = eng.timer_stop_ms()
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -367,7 +376,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
-            "stream_msps": value / N_CH, "prompt_over_noise": prompt_snr}
+            "stream_msps": value / N_CH, "prompt_over_noise": prompt_snr, "engine_timer_check_ms": check_ms}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
