@@ -1,0 +1,267 @@
+// In-shared-memory mixed-radix complex FFT for sm_100a (no cuFFT).
+//
+// Sizes are whatever the receiver's sampling rate dictates (N = fs * T: 4000, 8000, 16000,
+// 25000 = 2^3*5^5 ...), so radices 2,3,4,5,7,8 are supported and the planner factors N into them.
+//
+// Layout trick that removes every permutation pass: the forward transform is decimation in
+// frequency (natural order in, digit-reversed order out), the inverse is decimation in time
+// running the same stages backwards (digit-reversed in, natural out).  The local-code spectrum
+// is stored in the same digit-reversed order, so the point-wise product between the two
+// transforms needs no reordering.  Every butterfly reads r elements and writes them back to the
+// same places: one buffer of N complex values (8N bytes, N <= kAcqMaxSmemPoints) and one
+// __syncthreads per stage.
+//
+// Transforms are unnormalised in both directions, like FFTW / gr::fft
+// (src/algorithms/libs/gnss_sdr_fft.h:26-62).
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace b200
+{
+constexpr int kAcqThreads = 512;
+constexpr int kAcqMaxStages = 16;
+constexpr int kAcqMaxSmemPoints = 27648;  // 216 KB of float2
+
+struct FftPlan
+{
+    int n;
+    int n_stages;
+    int radix[kAcqMaxStages];  // forward DIF order; product = n
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b)  // a * conj(b)
+{
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -j (forward rotation by -90 deg): (x, y) -> (y, -x)
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ float2 mul_pj(float2 a) { return make_float2(-a.y, a.x); }
+
+// ---- forward butterflies: y_p = sum_q x_q exp(-2 pi j p q / R), in place --------------------------
+template <int R>
+struct Bfly;
+
+template <>
+struct Bfly<2>
+{
+    static __device__ __forceinline__ void fwd(float2 (&v)[2])
+    {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <>
+struct Bfly<3>
+{
+    static __device__ __forceinline__ void fwd(float2 (&v)[3])
+    {
+        const float s = 0.86602540378443865f;
+        const float2 t = cadd(v[1], v[2]);
+        const float2 d = csub(v[1], v[2]);
+        const float2 a = make_float2(fmaf(-0.5f, t.x, v[0].x), fmaf(-0.5f, t.y, v[0].y));
+        const float2 b = make_float2(s * d.x, s * d.y);
+        v[0] = cadd(v[0], t);
+        v[1] = cadd(a, mul_mj(b));
+        v[2] = cadd(a, mul_pj(b));
+    }
+};
+
+template <>
+struct Bfly<4>
+{
+    static __device__ __forceinline__ void fwd(float2 (&v)[4])
+    {
+        const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        const float2 t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
+        v[0] = cadd(t0, t2);
+        v[2] = csub(t0, t2);
+        v[1] = cadd(t1, mul_mj(t3));
+        v[3] = cadd(t1, mul_pj(t3));
+    }
+};
+
+template <>
+struct Bfly<5>
+{
+    static __device__ __forceinline__ void fwd(float2 (&v)[5])
+    {
+        const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+        const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+        const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+        const float2 t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        const float2 a1 = make_float2(fmaf(c2, t2.x, fmaf(c1, t1.x, v[0].x)), fmaf(c2, t2.y, fmaf(c1, t1.y, v[0].y)));
+        const float2 a2 = make_float2(fmaf(c1, t2.x, fmaf(c2, t1.x, v[0].x)), fmaf(c1, t2.y, fmaf(c2, t1.y, v[0].y)));
+        const float2 b1 = make_float2(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y));
+        const float2 b2 = make_float2(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y));
+        v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
+        v[1] = cadd(a1, mul_mj(b1));
+        v[4] = cadd(a1, mul_pj(b1));
+        v[2] = cadd(a2, mul_mj(b2));
+        v[3] = cadd(a2, mul_pj(b2));
+    }
+};
+
+template <>
+struct Bfly<7>
+{
+    static __device__ __forceinline__ void fwd(float2 (&v)[7])
+    {
+        const float c1 = 0.62348980185873353f, c2 = -0.22252093395631440f, c3 = -0.90096886790241913f;
+        const float s1 = 0.78183148246802981f, s2 = 0.97492791218182361f, s3 = 0.43388373911755812f;
+        const float2 p1 = cadd(v[1], v[6]), p2 = cadd(v[2], v[5]), p3 = cadd(v[3], v[4]);
+        const float2 m1 = csub(v[1], v[6]), m2 = csub(v[2], v[5]), m3 = csub(v[3], v[4]);
+        const float2 x0 = v[0];
+        // a_k = x0 + sum_q cos(2 pi k q/7) p_q ; b_k = sum_q sin(2 pi k q/7) m_q ; y_k = a_k - j b_k
+        const float2 a1 = make_float2(x0.x + c1 * p1.x + c2 * p2.x + c3 * p3.x, x0.y + c1 * p1.y + c2 * p2.y + c3 * p3.y);
+        const float2 a2 = make_float2(x0.x + c2 * p1.x + c3 * p2.x + c1 * p3.x, x0.y + c2 * p1.y + c3 * p2.y + c1 * p3.y);
+        const float2 a3 = make_float2(x0.x + c3 * p1.x + c1 * p2.x + c2 * p3.x, x0.y + c3 * p1.y + c1 * p2.y + c2 * p3.y);
+        const float2 b1 = make_float2(s1 * m1.x + s2 * m2.x + s3 * m3.x, s1 * m1.y + s2 * m2.y + s3 * m3.y);
+        const float2 b2 = make_float2(s2 * m1.x - s3 * m2.x - s1 * m3.x, s2 * m1.y - s3 * m2.y - s1 * m3.y);
+        const float2 b3 = make_float2(s3 * m1.x - s1 * m2.x + s2 * m3.x, s3 * m1.y - s1 * m2.y + s2 * m3.y);
+        v[0] = make_float2(x0.x + p1.x + p2.x + p3.x, x0.y + p1.y + p2.y + p3.y);
+        v[1] = cadd(a1, mul_mj(b1));
+        v[6] = cadd(a1, mul_pj(b1));
+        v[2] = cadd(a2, mul_mj(b2));
+        v[5] = cadd(a2, mul_pj(b2));
+        v[3] = cadd(a3, mul_mj(b3));
+        v[4] = cadd(a3, mul_pj(b3));
+    }
+};
+
+template <>
+struct Bfly<8>
+{
+    static __device__ __forceinline__ void fwd(float2 (&v)[8])
+    {
+        const float h = 0.70710678118654752f;
+        // radix-2 step over (q, q+4), then two radix-4s on even/odd outputs
+        float2 e[4], o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            {
+                e[q] = cadd(v[q], v[q + 4]);
+                o[q] = csub(v[q], v[q + 4]);
+            }
+        // odd branch twiddles w8^q, q = 0..3
+        o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));   // * (1 - j)/sqrt2
+        o[2] = mul_mj(o[2]);
+        o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));  // * (-1 - j)/sqrt2
+        Bfly<4>::fwd(e);
+        Bfly<4>::fwd(o);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            {
+                v[2 * q] = e[q];
+                v[2 * q + 1] = o[q];
+            }
+    }
+};
+
+__device__ __forceinline__ float2 swap_ri(float2 a) { return make_float2(a.y, a.x); }
+
+// One DIF (forward) or DIT (inverse) stage over a buffer of n points in shared memory.
+// M = current block length, R | M, m = M / R.  tw = global table exp(-2 pi j k / n), k < n.
+template <int R, bool INV>
+__device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, const float2* __restrict__ tw)
+{
+    const int m = M / R;
+    const int tw_stride = n / M;
+    const int nb = n / R;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        {
+            const int b = i / m;
+            const int j = i - b * m;
+            float2* p = s + b * M + j;
+            float2 v[R];
+#pragma unroll
+            for (int q = 0; q < R; q++) v[q] = p[q * m];
+            if (INV)
+                {
+                    if (m > 1)
+                        {
+                            const float2 w1 = __ldg(tw + j * tw_stride);
+                            float2 w = w1;
+#pragma unroll
+                            for (int q = 1; q < R; q++)
+                                {
+                                    v[q] = cmul_conj(v[q], w);
+                                    if (q + 1 < R) w = cmul(w, w1);
+                                }
+                        }
+#pragma unroll
+                    for (int q = 0; q < R; q++) v[q] = swap_ri(v[q]);
+                    Bfly<R>::fwd(v);
+#pragma unroll
+                    for (int q = 0; q < R; q++) v[q] = swap_ri(v[q]);
+                }
+            else
+                {
+                    Bfly<R>::fwd(v);
+                    if (m > 1)
+                        {
+                            const float2 w1 = __ldg(tw + j * tw_stride);
+                            float2 w = w1;
+#pragma unroll
+                            for (int q = 1; q < R; q++)
+                                {
+                                    v[q] = cmul(v[q], w);
+                                    if (q + 1 < R) w = cmul(w, w1);
+                                }
+                        }
+                }
+#pragma unroll
+            for (int q = 0; q < R; q++) p[q * m] = v[q];
+        }
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, int M, const float2* tw)
+{
+    switch (radix)
+        {
+        case 2: fft_stage<2, INV>(s, n, M, tw); break;
+        case 3: fft_stage<3, INV>(s, n, M, tw); break;
+        case 4: fft_stage<4, INV>(s, n, M, tw); break;
+        case 5: fft_stage<5, INV>(s, n, M, tw); break;
+        case 7: fft_stage<7, INV>(s, n, M, tw); break;
+        default: fft_stage<8, INV>(s, n, M, tw); break;
+        }
+}
+
+// forward DIF over all stages: natural order in, digit-reversed out
+__device__ __forceinline__ void fft_forward_smem(float2* s, const FftPlan& pl, const float2* tw)
+{
+    int M = pl.n;
+    for (int st = 0; st < pl.n_stages; st++)
+        {
+            __syncthreads();
+            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, tw);
+            M /= pl.radix[st];
+        }
+    __syncthreads();
+}
+
+// inverse DIT over stages [n_stages-1 .. first_stage]: digit-reversed in, natural out when
+// first_stage == 0.  (first_stage == 1 leaves the last stage to a fused epilogue.)
+__device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, const float2* tw, int first_stage)
+{
+    int M = 1;
+    for (int st = pl.n_stages - 1; st >= first_stage; st--)
+        {
+            M *= pl.radix[st];
+            __syncthreads();
+            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, tw);
+        }
+    __syncthreads();
+}
+
+}  // namespace b200
