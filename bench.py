@@ -163,6 +163,107 @@ def ncu_traffic_bytes():
         return None
 
 
+# ---- acquisition sub-benchmark (BASELINE configs[3], SURVEY 8d "C4") -----------------------------------
+ACQ_FS = 25000000
+ACQ_N = 25000
+ACQ_PRNS = 32
+ACQ_DMAX, ACQ_DSTEP = 10125, 250     # 81 bins: -10125 ... +9875 Hz
+
+
+def acq_rows_bytes_flops():
+    import math
+    bins = int(math.ceil(2 * ACQ_DMAX / ACQ_DSTEP))
+    rows = ACQ_PRNS * bins
+    # 16N algorithmic bytes and N(16 + 10 log2 N) flops per (PRN, bin) row
+    return bins, rows, rows * 16 * ACQ_N, rows * ACQ_N * (16 + 10 * math.log2(ACQ_N))
+
+
+def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu):
+    import oracle
+    from gnss_synth import make_iq
+    bins, rows, abytes, aflops = acq_rows_bytes_flops()
+    rng = np.random.default_rng(4)
+    present = [2, 5, 9, 13, 17, 21, 26, 30]
+    codes = {p: oracle.port.gps_ca_code(p) for p in present}
+    svs = [dict(prn=p, doppler=float(rng.uniform(-9000, 9000)), code_phase_chips=float(rng.uniform(0, 1023)), cn0=45.0,
+                phase0=float(rng.uniform(0, 6.28))) for p in present]
+    iq = make_iq(codes, float(ACQ_FS), ACQ_N, svs, seed=4)
+    acq = capi.PcpsAcquisition(eng, fs_in=ACQ_FS, samples_per_ms=float(ACQ_N), samples_per_chip=24, doppler_max=ACQ_DMAX,
+                               doppler_step=ACQ_DSTEP, n_code_slots=ACQ_PRNS)
+    assert acq.conf.num_doppler_bins == bins
+    for p in range(1, ACQ_PRNS + 1):
+        acq.set_local_code(p - 1, oracle.port.gps_ca_code_complex_sampled(p, ACQ_FS))
+    slots = np.arange(ACQ_PRNS, dtype=np.uint32)
+    iq_dev = torch.from_numpy(iq.view(np.float32)).to(dev)
+    res_dev = torch.zeros(ACQ_PRNS * capi.ACQ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        acq.search_dev(iq_dev.data_ptr(), slots, res_dev.data_ptr())
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        acq.search_dev(iq_dev.data_ptr(), slots, res_dev.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = eng.launch_count() - l0
+    res = np.frombuffer(res_dev.cpu().numpy().tobytes(), capi.ACQ_RESULT_DTYPE)
+    from oracle.acq_np import compute_threshold
+    th = compute_threshold(0.001, ACQ_N, bins, 1)
+    detected = sorted(int(p) for p in range(1, ACQ_PRNS + 1) if res[p - 1]["test_statistics"] > th)
+    # e2e: host samples in, host results out, per sweep
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r2 = acq.search(iq, slots)
+    dt = (time.perf_counter() - t0) / steps
+    peak, peak_src = measured_peak_gbs()
+    out = {"metric": "acquisitions/s over Doppler grid", "unit": "acquisitions/s",
+           "config": {"workload": f"C4: GPS L1 C/A PCPS, {ACQ_PRNS} PRNs x {bins} Doppler bins x N={ACQ_N} (25 Msps, 1 ms), CFAR statistic, "
+                                  "forward FFTs shared by all PRNs"},
+           "value": ACQ_PRNS / (ms * 1e-3), "ms_per_sweep": ms, "rows_per_s": rows / (ms * 1e-3),
+           "e2e": {"value": ACQ_PRNS / dt, "unit": "acquisitions/s", "h2d_bytes_per_step": ACQ_N * 8,
+                   "d2h_bytes_per_step": ACQ_PRNS * capi.ACQ_RESULT_DTYPE.itemsize, "ms_per_sweep": dt * 1e3},
+           "gpu_launches_per_sweep": launches / steps,
+           "roofline": {"bound": "hbm", "kernel": "acq_corr_kernel", "achieved": abytes / (ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": abytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                        "algorithmic_bytes_per_sweep": abytes, "algorithmic_gflop_per_sweep": aflops / 1e9,
+                        "achieved_tflops": aflops / (ms * 1e-3) / 1e12, "peak_source": peak_src,
+                        "note": "16N bytes per (PRN,bin) row (SURVEY 8d); operands are L2-resident, the kernel is "
+                                "shared-memory/FP32 bound, see DESIGN.md"},
+           "detected_prns": detected, "present_prns": present,
+           "e2e_matches_dev": bool(np.array_equal(r2["index_time"], res["index_time"]))}
+    if with_cpu:
+        out["cpu_baseline"] = cpu_baseline_acq(iq)
+    acq.close()
+    return out
+
+
+def cpu_baseline_acq(iq=None, n_prn=2):
+    """numpy restatement of pcps_acquisition (pocketfft float32, all cores via scipy.fft workers); FFTW/GNU Radio
+    are not installable here, so kind is "port"."""
+    import oracle
+    from oracle.acq_np import AcqConf, PcpsAcquisitionOracle
+    from gnss_synth import make_iq
+    cores = os.cpu_count() or 1
+    if iq is None:
+        code = oracle.port.gps_ca_code(2)
+        iq = make_iq({2: code}, float(ACQ_FS), ACQ_N, [dict(prn=2, doppler=1234.0, code_phase_chips=100.0, cn0=45.0)], seed=4)
+    conf = AcqConf(fs_in=ACQ_FS, samples_per_ms=float(ACQ_N), samples_per_code=float(ACQ_N), samples_per_chip=24,
+                   doppler_max=ACQ_DMAX, doppler_step=ACQ_DSTEP, pfa=0.001)
+    o = PcpsAcquisitionOracle(conf, workers=cores)
+    o.set_local_code(oracle.port.gps_ca_code_complex_sampled(2, ACQ_FS))
+    o.acquisition_core(iq)   # warm-up (plans, caches)
+    t0 = time.perf_counter()
+    for _ in range(n_prn):
+        o.num_noncoherent_integrations_counter = 0
+        o.acquisition_core(iq)
+    dt = time.perf_counter() - t0
+    return {"value": n_prn / dt, "unit": "acquisitions/s", "cores": cores, "kind": "port",
+            "sample": f"{n_prn} PRN searches x {conf.num_doppler_bins} bins x N={ACQ_N}; numpy restatement of pcps_acquisition.cc "
+                      f"with scipy.fft (pocketfft, float32, workers={cores})"}
+
+
 # ---- CPU baseline (the reference's own SIMD path, timed like its own harness) --------------------
 def cpu_baseline(budget_s=12.0):
     import oracle
@@ -227,6 +328,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-acq", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -353,6 +455,13 @@ def main():
         # e2e result must agree with the device-resident run
         e2e["max_rel_diff_vs_value_run"] = float(np.max(np.abs(res - taps)) / np.max(np.abs(taps)))
 
+    acq = None
+    if not args.no_acq and rank == 0:
+        try:
+            acq = bench_acq(torch, capi, eng, dev, max(5, min(args.steps, 50)), 3, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as ex:  # the headline metric must still be reported
+            acq = {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -376,7 +485,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
-            "stream_msps": value / N_CH, "prompt_over_noise": prompt_snr, "engine_timer_check_ms": check_ms}
+            "stream_msps": value / N_CH, "prompt_over_noise": prompt_snr, "engine_timer_check_ms": check_ms,
+            "acq": acq}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -65,6 +65,38 @@ _SIGS = {
     "b200_trk_batch": ([_vp, _vp, C.c_int, _vp, C.c_int], C.c_int),
     "b200_trk_batch_dev": ([_vp, _vp, C.c_int, _vp, C.c_int, C.c_int], C.c_int),
 }
+
+
+class AcqConf(C.Structure):
+    _fields_ = [("fft_size", C.c_uint32), ("effective_fft_size", C.c_uint32), ("consumed_samples", C.c_uint32),
+                ("num_doppler_bins", C.c_uint32), ("doppler_max", C.c_int32), ("doppler_step", C.c_int32),
+                ("fs_in", C.c_int64), ("samples_per_chip", C.c_uint32), ("code_layout", C.c_uint32),
+                ("bit_transition_flag", C.c_int32), ("use_cfar", C.c_int32), ("max_dwells", C.c_uint32),
+                ("n_code_slots", C.c_uint32), ("keep_grid", C.c_int32)]
+
+
+class AcqResult(C.Structure):
+    _fields_ = [("index_time", C.c_uint32), ("index_doppler", C.c_uint32), ("doppler", C.c_int32),
+                ("test_statistics", C.c_float), ("grid_maximum", C.c_float), ("input_power", C.c_float),
+                ("second_peak", C.c_float)]
+
+
+ACQ_RESULT_DTYPE = np.dtype([("index_time", "<u4"), ("index_doppler", "<u4"), ("doppler", "<i4"),
+                             ("test_statistics", "<f4"), ("grid_maximum", "<f4"), ("input_power", "<f4"),
+                             ("second_peak", "<f4")])
+assert ACQ_RESULT_DTYPE.itemsize == C.sizeof(AcqResult) == 28
+
+_SIGS.update({
+    "b200_acq_create": ([_vp, C.POINTER(AcqConf), C.POINTER(_vp)], C.c_int),
+    "b200_acq_set_local_code": ([_vp, C.c_uint32, _vp], C.c_int),
+    "b200_acq_set_doppler_center": ([_vp, C.c_int32, C.c_int32], C.c_int),
+    "b200_acq_search": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
+    "b200_acq_search_dev": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
+    "b200_acq_read_grid": ([_vp, C.c_uint32, _vp], C.c_int),
+    "b200_acq_read_wipeoffs": ([_vp, _vp], C.c_int),
+    "b200_acq_destroy": ([_vp], C.c_int),
+})
+
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
@@ -202,5 +234,74 @@ class Multicorrelator:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class PcpsAcquisition:
+    """b200_acq handle: the arithmetic of one pcps_acquisition block (or of a multi-PRN sweep).
+
+    Construction mirrors pcps_acquisition's constructor (pcps_acquisition.cc:100-193): sizes are
+    derived from the Acq_Conf fields exactly as there."""
+
+    def __init__(self, engine: Engine, *, fs_in: int, samples_per_ms: float, samples_per_chip: int, doppler_max: int,
+                 doppler_step: int, sampled_ms: int = 1, ms_per_code: int = 1, bit_transition_flag: bool = False,
+                 use_CFAR_algorithm_flag: bool = True, max_dwells: int = 1, n_code_slots: int = 1,
+                 keep_grid: bool = False):
+        import math
+        consumed = int(sampled_ms * samples_per_ms * (2.0 if bit_transition_flag else 1.0))
+        fft_size = consumed if sampled_ms == ms_per_code else consumed * 2
+        eff = fft_size // 2 if bit_transition_flag else fft_size
+        bins = int(math.ceil(float(2 * doppler_max) / float(doppler_step)))
+        layout = 1 if bit_transition_flag else (0 if sampled_ms == ms_per_code else 2)
+        self.conf = AcqConf(fft_size, eff, consumed, bins, doppler_max, doppler_step, int(fs_in), samples_per_chip,
+                            layout, int(bit_transition_flag), int(use_CFAR_algorithm_flag), max_dwells, n_code_slots,
+                            int(keep_grid))
+        h = _vp()
+        _chk(lib.b200_acq_create(engine.h, C.byref(self.conf), C.byref(h)), "b200_acq_create")
+        self.h = h
+        self.engine = engine
+
+    def set_local_code(self, slot: int, code):
+        code = np.ascontiguousarray(code, np.complex64)
+        need = self.conf.fft_size // 2 if self.conf.code_layout == 1 else self.conf.consumed_samples
+        assert code.size >= need, (code.size, need)
+        _chk(lib.b200_acq_set_local_code(self.h, slot, code.ctypes.data), "b200_acq_set_local_code")
+
+    def set_doppler_center(self, center: int, bias: int = 0):
+        _chk(lib.b200_acq_set_doppler_center(self.h, center, bias), "b200_acq_set_doppler_center")
+
+    def search(self, iq, slots, dwell_counter: int = 1) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, np.complex64)
+        assert iq.size >= self.conf.consumed_samples
+        slots = np.ascontiguousarray(slots, np.uint32)
+        res = np.zeros(slots.size, ACQ_RESULT_DTYPE)
+        _chk(lib.b200_acq_search(self.h, iq.ctypes.data, slots.ctypes.data, slots.size, dwell_counter, res.ctypes.data),
+             "b200_acq_search")
+        return res
+
+    def search_dev(self, in_dev_ptr: int, slots, results_dev_ptr: int, dwell_counter: int = 1):
+        slots = np.ascontiguousarray(slots, np.uint32)
+        _chk(lib.b200_acq_search_dev(self.h, in_dev_ptr, slots.ctypes.data, slots.size, dwell_counter, results_dev_ptr),
+             "b200_acq_search_dev")
+
+    def read_grid(self, slot: int) -> np.ndarray:
+        g = np.empty((self.conf.num_doppler_bins, self.conf.effective_fft_size), np.float32)
+        _chk(lib.b200_acq_read_grid(self.h, slot, g.ctypes.data), "b200_acq_read_grid")
+        return g
+
+    def read_wipeoffs(self) -> np.ndarray:
+        w = np.empty((self.conf.num_doppler_bins, self.conf.fft_size), np.complex64)
+        _chk(lib.b200_acq_read_wipeoffs(self.h, w.ctypes.data), "b200_acq_read_wipeoffs")
+        return w
+
+    def close(self):
+        if self.h:
+            lib.b200_acq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass

@@ -1,0 +1,279 @@
+// Host side of the acquisition C ABI (include/b200gnss.h, b200_acq_*): owns what one
+// pcps_acquisition block owns (src/algorithms/acquisition/gnuradio_blocks/pcps_acquisition.h:
+// FFT plans, d_grid_doppler_wipeoffs, d_fft_codes, d_magnitude_grid) as device buffers.
+
+#include "acq_fft.cuh"
+#include "engine.cuh"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace b200
+{
+struct AcqRowStat
+{
+    float max;
+    unsigned int argmax;
+    float sum;
+    float pad;
+};
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_acq
+{
+    b200_engine* e{nullptr};
+    b200_acq_conf c{};
+    FftPlan plan{};
+    cudaStream_t stream{nullptr};
+    bool own_stream{false};
+    int doppler_center{0};
+    int doppler_bias{0};
+    float2* tw{nullptr};
+    float2* wipe{nullptr};     // bins x n
+    float2* X{nullptr};        // bins x n   forward spectra (digit-reversed)
+    float2* codes{nullptr};    // slots x n  conj(FFT(code)) (digit-reversed)
+    float2* in_dev{nullptr};   // consumed
+    float2* code_stage{nullptr};
+    float* grid{nullptr};      // slots x bins x ne (optional)
+    AcqRowStat* rowstat{nullptr};
+    int* slot_list{nullptr};
+    void* best{nullptr};
+    float* second_peak{nullptr};
+    b200_acq_result* results_dev{nullptr};
+    b200_acq_result* results_pin{nullptr};
+    int* slot_pin{nullptr};
+    std::vector<char> slot_set;
+};
+
+namespace
+{
+int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32_t n_slots, uint32_t dwell_counter,
+    b200_acq_result* results_dev)
+{
+    const b200_acq_conf& c = a->c;
+    if (n_slots == 0) return B200_OK;
+    if (n_slots > c.n_code_slots || !slots) return B200_ERR_ARG;
+    if (dwell_counter < 1) dwell_counter = 1;
+    if (dwell_counter > 1 && !a->grid)
+        {
+            set_error("dwell_counter %u needs the magnitude grid (create with max_dwells > 1 or keep_grid)", dwell_counter);
+            return B200_ERR_STATE;
+        }
+    for (uint32_t i = 0; i < n_slots; i++)
+        {
+            if (slots[i] >= c.n_code_slots || !a->slot_set[slots[i]])
+                {
+                    set_error("slot %u has no local code", slots[i]);
+                    return B200_ERR_STATE;
+                }
+            a->slot_pin[i] = static_cast<int>(slots[i]);
+        }
+    cudaStream_t st = a->stream;
+    B200_CUDA_TRY(cudaMemcpyAsync(a->slot_list, a->slot_pin, sizeof(int) * n_slots, cudaMemcpyHostToDevice, st));
+    const int n = static_cast<int>(c.fft_size);
+    const int bins = static_cast<int>(c.num_doppler_bins);
+    const int ne = static_cast<int>(c.effective_fft_size);
+    const int off = c.bit_transition_flag ? ne : 0;
+    int rc = acq_launch_fwd(in_dev, static_cast<int>(c.consumed_samples), a->wipe, a->X, bins, a->plan, a->tw, st);
+    if (rc) return rc;
+    rc = acq_launch_corr(a->X, a->codes, a->slot_list, static_cast<int>(n_slots), bins, a->plan, a->tw, off, ne, a->rowstat, a->grid,
+        dwell_counter > 1 ? 1 : 0, 0, nullptr, 0, nullptr, st);
+    if (rc) return rc;
+    rc = acq_launch_stats(a->rowstat, static_cast<int>(n_slots), bins, ne, c.doppler_max, a->doppler_center, c.doppler_step,
+        dwell_counter, c.use_cfar, a->best, results_dev, st);
+    if (rc) return rc;
+    uint64_t launched = 3;
+    if (!c.use_cfar)
+        {
+            rc = acq_launch_corr(a->X, a->codes, a->slot_list, static_cast<int>(n_slots), bins, a->plan, a->tw, off, ne, a->rowstat,
+                a->grid, 0, 1, a->best, static_cast<int>(c.samples_per_chip), a->second_peak, st);
+            if (rc) return rc;
+            rc = acq_launch_finish_second_peak(a->second_peak, static_cast<int>(n_slots), results_dev, st);
+            if (rc) return rc;
+            launched += 2;
+        }
+    {
+        std::lock_guard<std::mutex> lk(a->e->mu);
+        a->e->launches += launched;
+    }
+    (void)n;
+    return B200_OK;
+}
+}  // namespace
+
+extern "C"
+{
+    int b200_acq_create(b200_engine* e, const b200_acq_conf* conf, b200_acq** out)
+    {
+        if (!e || !conf || !out) return B200_ERR_ARG;
+        *out = nullptr;
+        const b200_acq_conf& c = *conf;
+        if (c.fft_size < 2 || c.effective_fft_size < 1 || c.effective_fft_size > c.fft_size || c.consumed_samples < 1 ||
+            c.consumed_samples > c.fft_size || c.num_doppler_bins < 1 || c.n_code_slots < 1 || c.code_layout > 2 || c.fs_in <= 0)
+            {
+                set_error("b200_acq_create: inconsistent configuration");
+                return B200_ERR_ARG;
+            }
+        if (c.bit_transition_flag && 2 * c.effective_fft_size > c.fft_size) return B200_ERR_ARG;
+        FftPlan pl{};
+        int rc = acq_plan_make(static_cast<int>(c.fft_size), &pl);
+        if (rc)
+            {
+                set_error("fft_size %u unsupported: must be <= %d and factor into 2,3,5,7", c.fft_size, kAcqMaxSmemPoints);
+                return rc;
+            }
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        b200_acq* a = new (std::nothrow) b200_acq();
+        if (!a) return B200_ERR_NOMEM;
+        a->e = e;
+        a->c = c;
+        a->plan = pl;
+        a->slot_set.assign(c.n_code_slots, 0);
+        const size_t n = c.fft_size, bins = c.num_doppler_bins, slots = c.n_code_slots, ne = c.effective_fft_size;
+        if (e->own_stream)
+            {
+                // one private stream per acquisition object: blocks of different channels overlap
+                B200_CUDA_TRY(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+                a->own_stream = true;
+            }
+        else
+            {
+                a->stream = e->stream;  // caller-owned stream (e.g. for event timing on that stream)
+            }
+        B200_CUDA_TRY(cudaMalloc(&a->tw, sizeof(float2) * n));
+        B200_CUDA_TRY(cudaMalloc(&a->wipe, sizeof(float2) * n * bins));
+        B200_CUDA_TRY(cudaMalloc(&a->X, sizeof(float2) * n * bins));
+        B200_CUDA_TRY(cudaMalloc(&a->codes, sizeof(float2) * n * slots));
+        B200_CUDA_TRY(cudaMalloc(&a->in_dev, sizeof(float2) * n));
+        B200_CUDA_TRY(cudaMalloc(&a->code_stage, sizeof(float2) * n));
+        B200_CUDA_TRY(cudaMalloc(&a->rowstat, sizeof(AcqRowStat) * bins * slots));
+        B200_CUDA_TRY(cudaMalloc(&a->slot_list, sizeof(int) * slots));
+        B200_CUDA_TRY(cudaMalloc(&a->best, 8 * slots));
+        B200_CUDA_TRY(cudaMalloc(&a->second_peak, sizeof(float) * slots));
+        B200_CUDA_TRY(cudaMalloc(&a->results_dev, sizeof(b200_acq_result) * slots));
+        B200_CUDA_TRY(cudaMallocHost(&a->results_pin, sizeof(b200_acq_result) * slots));
+        B200_CUDA_TRY(cudaMallocHost(&a->slot_pin, sizeof(int) * slots));
+        if (c.max_dwells > 1 || c.keep_grid)
+            {
+                cudaError_t err = cudaMalloc(&a->grid, sizeof(float) * ne * bins * slots);
+                if (err != cudaSuccess)
+                    {
+                        set_error("magnitude grid (%zu bytes): %s", sizeof(float) * ne * bins * slots, cudaGetErrorString(err));
+                        b200_acq_destroy(a);
+                        return B200_ERR_NOMEM;
+                    }
+                B200_CUDA_TRY(cudaMemsetAsync(a->grid, 0, sizeof(float) * ne * bins * slots, a->stream));
+            }
+        rc = acq_launch_twiddles(a->tw, static_cast<int>(n), a->stream);
+        if (rc) return rc;
+        rc = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, a->stream);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        *out = a;
+        return B200_OK;
+    }
+
+    int b200_acq_set_local_code(b200_acq* a, uint32_t slot, const b200_cf32* code_host)
+    {
+        if (!a || !code_host || slot >= a->c.n_code_slots) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        const b200_acq_conf& c = a->c;
+        const size_t need = (c.code_layout == 1) ? c.fft_size / 2 : c.consumed_samples;
+        B200_CUDA_TRY(cudaMemcpyAsync(a->code_stage, code_host, sizeof(float2) * need, cudaMemcpyHostToDevice, a->stream));
+        int rc = acq_launch_code_fft(a->code_stage, static_cast<int>(c.consumed_samples), static_cast<int>(c.code_layout),
+            a->codes + static_cast<size_t>(slot) * c.fft_size, a->plan, a->tw, a->stream);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        a->slot_set[slot] = 1;
+        return B200_OK;
+    }
+
+    int b200_acq_set_doppler_center(b200_acq* a, int32_t doppler_center, int32_t doppler_bias)
+    {
+        if (!a) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        a->doppler_center = doppler_center;
+        a->doppler_bias = doppler_bias;
+        const b200_acq_conf& c = a->c;
+        int rc = acq_launch_wipeoff(a->wipe, static_cast<int>(c.fft_size), static_cast<int>(c.num_doppler_bins), c.doppler_max,
+            doppler_center, c.doppler_step, doppler_bias, c.fs_in, a->stream);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return B200_OK;
+    }
+
+    int b200_acq_search(b200_acq* a, const b200_cf32* in_host, const uint32_t* slots, uint32_t n_slots,
+        uint32_t dwell_counter, b200_acq_result* results_host)
+    {
+        if (!a || !in_host || !results_host) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_CUDA_TRY(cudaMemcpyAsync(a->in_dev, in_host, sizeof(float2) * a->c.consumed_samples, cudaMemcpyHostToDevice, a->stream));
+        int rc = search_impl(a, a->in_dev, slots, n_slots, dwell_counter, a->results_dev);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaMemcpyAsync(a->results_pin, a->results_dev, sizeof(b200_acq_result) * n_slots, cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        std::memcpy(results_host, a->results_pin, sizeof(b200_acq_result) * n_slots);
+        return B200_OK;
+    }
+
+    int b200_acq_search_dev(b200_acq* a, const b200_cf32* in_dev, const uint32_t* slots_host, uint32_t n_slots,
+        uint32_t dwell_counter, b200_acq_result* results_dev)
+    {
+        if (!a || !in_dev || !results_dev) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        // slot_pin is reused by every call: wait for the previous call's H2D of it
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return search_impl(a, reinterpret_cast<const float2*>(in_dev), slots_host, n_slots, dwell_counter, results_dev);
+    }
+
+    int b200_acq_read_grid(b200_acq* a, uint32_t slot, float* grid_host)
+    {
+        if (!a || !grid_host || slot >= a->c.n_code_slots) return B200_ERR_ARG;
+        if (!a->grid)
+            {
+                set_error("no magnitude grid: create with keep_grid or max_dwells > 1");
+                return B200_ERR_STATE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        const size_t row = static_cast<size_t>(a->c.num_doppler_bins) * a->c.effective_fft_size;
+        B200_CUDA_TRY(cudaMemcpyAsync(grid_host, a->grid + row * slot, sizeof(float) * row, cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return B200_OK;
+    }
+
+    int b200_acq_read_wipeoffs(b200_acq* a, b200_cf32* wipe_host)
+    {
+        if (!a || !wipe_host) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_CUDA_TRY(cudaMemcpyAsync(wipe_host, a->wipe, sizeof(float2) * a->c.fft_size * a->c.num_doppler_bins, cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return B200_OK;
+    }
+
+    int b200_acq_destroy(b200_acq* a)
+    {
+        if (!a) return B200_ERR_ARG;
+        cudaSetDevice(a->e->device);
+        if (a->stream) cudaStreamSynchronize(a->stream);
+        cudaFree(a->tw);
+        cudaFree(a->wipe);
+        cudaFree(a->X);
+        cudaFree(a->codes);
+        cudaFree(a->in_dev);
+        cudaFree(a->code_stage);
+        cudaFree(a->grid);
+        cudaFree(a->rowstat);
+        cudaFree(a->slot_list);
+        cudaFree(a->best);
+        cudaFree(a->second_peak);
+        cudaFree(a->results_dev);
+        if (a->results_pin) cudaFreeHost(a->results_pin);
+        if (a->slot_pin) cudaFreeHost(a->slot_pin);
+        if (a->stream && a->own_stream) cudaStreamDestroy(a->stream);
+        delete a;
+        return B200_OK;
+    }
+}

@@ -168,10 +168,19 @@ struct Bfly<8>
 
 __device__ __forceinline__ float2 swap_ri(float2 a) { return make_float2(a.y, a.x); }
 
+// Where a stage puts its outputs.  StoreSink writes them back in place (the normal case); the
+// acquisition kernels pass a sink that consumes the natural-order outputs of the LAST inverse
+// stage directly (|.|^2, max, sum) so the correlation row is never written anywhere.
+struct StoreSink
+{
+    __device__ __forceinline__ void operator()(float2* p, int /*pos*/, float2 v) const { *p = v; }
+};
+
 // One DIF (forward) or DIT (inverse) stage over a buffer of n points in shared memory.
 // M = current block length, R | M, m = M / R.  tw = global table exp(-2 pi j k / n), k < n.
-template <int R, bool INV>
-__device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, const float2* __restrict__ tw)
+// sink(ptr, position, value) receives each output; position = index in the buffer.
+template <int R, bool INV, class Sink>
+__device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, const float2* __restrict__ tw, Sink& sink)
 {
     const int m = M / R;
     const int tw_stride = n / M;
@@ -180,7 +189,8 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
         {
             const int b = i / m;
             const int j = i - b * m;
-            float2* p = s + b * M + j;
+            const int pos0 = b * M + j;
+            float2* p = s + pos0;
             float2 v[R];
 #pragma unroll
             for (int q = 0; q < R; q++) v[q] = p[q * m];
@@ -219,49 +229,53 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
                         }
                 }
 #pragma unroll
-            for (int q = 0; q < R; q++) p[q * m] = v[q];
+            for (int q = 0; q < R; q++) sink(p + q * m, pos0 + q * m, v[q]);
         }
 }
 
-template <bool INV>
-__device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, int M, const float2* tw)
+template <bool INV, class Sink>
+__device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, int M, const float2* tw, Sink& sink)
 {
     switch (radix)
         {
-        case 2: fft_stage<2, INV>(s, n, M, tw); break;
-        case 3: fft_stage<3, INV>(s, n, M, tw); break;
-        case 4: fft_stage<4, INV>(s, n, M, tw); break;
-        case 5: fft_stage<5, INV>(s, n, M, tw); break;
-        case 7: fft_stage<7, INV>(s, n, M, tw); break;
-        default: fft_stage<8, INV>(s, n, M, tw); break;
+        case 2: fft_stage<2, INV>(s, n, M, tw, sink); break;
+        case 3: fft_stage<3, INV>(s, n, M, tw, sink); break;
+        case 4: fft_stage<4, INV>(s, n, M, tw, sink); break;
+        case 5: fft_stage<5, INV>(s, n, M, tw, sink); break;
+        case 7: fft_stage<7, INV>(s, n, M, tw, sink); break;
+        default: fft_stage<8, INV>(s, n, M, tw, sink); break;
         }
 }
 
 // forward DIF over all stages: natural order in, digit-reversed out
 __device__ __forceinline__ void fft_forward_smem(float2* s, const FftPlan& pl, const float2* tw)
 {
+    StoreSink st_sink;
     int M = pl.n;
     for (int st = 0; st < pl.n_stages; st++)
         {
             __syncthreads();
-            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, tw);
+            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, tw, st_sink);
             M /= pl.radix[st];
         }
     __syncthreads();
 }
 
-// inverse DIT over stages [n_stages-1 .. first_stage]: digit-reversed in, natural out when
-// first_stage == 0.  (first_stage == 1 leaves the last stage to a fused epilogue.)
-__device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, const float2* tw, int first_stage)
+// inverse DIT over stages n_stages-1 .. 1 in place, then stage 0 (block length n, natural-order
+// outputs) through `last`: digit-reversed in, natural out.
+template <class Sink>
+__device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, const float2* tw, Sink& last)
 {
+    StoreSink st_sink;
     int M = 1;
-    for (int st = pl.n_stages - 1; st >= first_stage; st--)
+    for (int st = pl.n_stages - 1; st >= 1; st--)
         {
             M *= pl.radix[st];
             __syncthreads();
-            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, tw);
+            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, tw, st_sink);
         }
     __syncthreads();
+    fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, tw, last);
 }
 
 }  // namespace b200

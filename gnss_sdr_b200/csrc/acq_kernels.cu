@@ -1,0 +1,528 @@
+// PCPS acquisition grid search for sm_100a.  Reference: src/algorithms/acquisition/
+// gnuradio_blocks/pcps_acquisition.cc (doppler_grid :522-560, statistics :409-519,
+// set_local_code :218-251, wipe-off grid :275-291).
+//
+// Kernels (all FFT work in shared memory, acq_fft.cuh; no cuFFT):
+//   acq_wipeoff_kernel   Doppler wipe-off carriers, bit-compatible with the AVX2 variant of
+//                        volk_gnsssdr_s32f_sincos_32fc (what runs on an x86-64 host).
+//   acq_code_fft_kernel  set_local_code: FFT of the (padded) local code, conjugated, stored in
+//                        digit-reversed order.
+//   acq_fwd_kernel       one CTA per Doppler bin: x = in * wipe[d]; X_d = FFT(x), stored
+//                        digit-reversed.  Computed ONCE per bin and shared by every PRN searched
+//                        on the same samples (the reference recomputes it per channel).
+//   acq_corr_kernel      one CTA per (PRN, bin) row: Y = X_d . conj(FFT(code)); y = IFFT(Y); the
+//                        last inverse stage feeds |y|^2 straight into (max, first arg-max, sum)
+//                        so the N-point row never leaves the SM (optionally accumulated into the
+//                        magnitude grid for non-coherent dwells / dumps).
+//   acq_stats_kernel     per PRN: arg-max over bins (strict '>' in ascending bin order) and the
+//                        CFAR statistic, or hands the winning row to acq_corr_kernel in
+//                        "second peak" mode.
+#include "acq_fft.cuh"
+#include "common.cuh"
+
+namespace b200
+{
+struct AcqRowStat
+{
+    float max;
+    unsigned int argmax;
+    float sum;
+    float pad;
+};
+
+namespace
+{
+// ---- wipe-off carrier, reference float32 semantics --------------------------------------------
+// One lane of VG kernels/volk_gnsssdr/volk_gnsssdr_s32f_sincos_32fc.h:448-633 (Cephes-style
+// polynomial); every operation separately rounded, in the upstream order.
+__device__ __forceinline__ float2 cephes_sincos(float p)
+{
+    const float FOPI = 1.27323954473516f;
+    const float DP1 = -0.78515625f, DP2 = -2.4187564849853515625e-4f, DP3 = -3.77489497744594108e-8f;
+    const float cc0 = 2.443315711809948E-005f, cc1 = -1.388731625493765E-003f, cc2 = 4.166664568298827E-002f;
+    const float sc0 = -1.9515295891E-4f, sc1 = 8.3321608736E-3f, sc2 = -1.6666654611E-1f;
+    float x = fabsf(p);
+    unsigned int sign_bit_sin = __float_as_uint(p) & 0x80000000u;
+    float y = __fmul_rn(x, FOPI);
+    int emm2 = __float2int_rz(y);
+    emm2 = (emm2 + 1) & ~1;
+    y = __int2float_rn(emm2);
+    int emm4 = emm2;
+    const unsigned int swap_sign_bit_sin = (static_cast<unsigned int>(emm2 & 4)) << 29;
+    const bool poly_sel = (emm2 & 2) == 0;
+    const float xmm1 = __fmul_rn(y, DP1), xmm2 = __fmul_rn(y, DP2), xmm3 = __fmul_rn(y, DP3);
+    x = __fadd_rn(x, xmm1);
+    x = __fadd_rn(x, xmm2);
+    x = __fadd_rn(x, xmm3);
+    emm4 = emm4 - 2;
+    const unsigned int sign_bit_cos = (static_cast<unsigned int>((~emm4) & 4)) << 29;
+    sign_bit_sin ^= swap_sign_bit_sin;
+    const float z = __fmul_rn(x, x);
+    y = cc0;
+    y = __fmul_rn(y, z);
+    y = __fadd_rn(y, cc1);
+    y = __fmul_rn(y, z);
+    y = __fadd_rn(y, cc2);
+    y = __fmul_rn(y, z);
+    y = __fmul_rn(y, z);
+    const float tmp = __fmul_rn(z, 0.5f);
+    y = __fsub_rn(y, tmp);
+    y = __fadd_rn(y, 1.0f);
+    float y2 = sc0;
+    y2 = __fmul_rn(y2, z);
+    y2 = __fadd_rn(y2, sc1);
+    y2 = __fmul_rn(y2, z);
+    y2 = __fadd_rn(y2, sc2);
+    y2 = __fmul_rn(y2, z);
+    y2 = __fmul_rn(y2, x);
+    y2 = __fadd_rn(y2, x);
+    // select: sine takes y2 where poly_sel, else y; cosine the other one
+    const float sm = poly_sel ? y2 : y;
+    const float cm = poly_sel ? y : y2;
+    const float s = __uint_as_float(__float_as_uint(sm) ^ sign_bit_sin);
+    const float c = __uint_as_float(__float_as_uint(cm) ^ sign_bit_cos);
+    return make_float2(c, s);
+}
+
+// grid: bins blocks of 32 threads; lanes 0..7 carry the eight float32 phase accumulators of the
+// AVX2 kernel (p_l = phase + l*inc, advanced by fl(8*inc) per iteration); lane 0 does the tail.
+__global__ void acq_wipeoff_kernel(float2* __restrict__ wipe, int n, int bins, int doppler_max, int doppler_center,
+    int doppler_step, int doppler_bias, long long fs_in)
+{
+    const int d = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (d >= bins || lane >= 8) return;
+    // pcps_acquisition.cc:288-289 and :277-278
+    const int doppler = -doppler_max + doppler_center + doppler_step * d;
+    const float freq = static_cast<float>(doppler_bias + doppler);
+    const float phase_step_rad = __fdiv_rn(__fmul_rn(static_cast<float>(6.283185307179586), freq), static_cast<float>(fs_in));
+    const float inc = -phase_step_rad;
+    const int iters = n / 8;
+    float p = (lane == 0) ? 0.0f : __fadd_rn(0.0f, __fmul_rn(static_cast<float>(lane), inc));
+    if (lane == 1) p = __fadd_rn(0.0f, inc);
+    const float inc8 = __fmul_rn(8.0f, inc);
+    float2* row = wipe + static_cast<size_t>(d) * n;
+    for (int it = 0; it < iters; it++)
+        {
+            row[8 * it + lane] = cephes_sincos(p);
+            p = __fadd_rn(p, inc8);
+        }
+    if (lane == 0)
+        {
+            // scalar tail (n % 8 samples): cosf/sinf of the float-accumulated phase (:616-620);
+            // CUDA's sinf/cosf are not glibc's, so these <8 samples are within 1 ulp, not bit-exact.
+            float ph = __fadd_rn(0.0f, __fmul_rn(inc, static_cast<float>(static_cast<unsigned int>(iters * 8))));
+            for (int i = iters * 8; i < n; i++)
+                {
+                    row[i] = make_float2(cosf(ph), sinf(ph));
+                    ph = __fadd_rn(ph, inc);
+                }
+        }
+}
+
+// ---- set_local_code ------------------------------------------------------------------------------
+// layout 0: code[0..consumed) at the front (sampled_ms == ms_per_code)          (:238-241)
+// layout 1: bit_transition_flag: zeros in the first half, code[0..n/2) in the second (:230-235)
+// layout 2: zero-padded front: code[0..consumed) at [n-consumed, n)               (:243-246)
+__global__ void __launch_bounds__(kAcqThreads, 1) acq_code_fft_kernel(const float2* __restrict__ code, int consumed, int layout,
+    float2* __restrict__ out, FftPlan pl, const float2* __restrict__ tw)
+{
+    extern __shared__ __align__(16) float2 s[];
+    const int n = pl.n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            float2 v = make_float2(0.f, 0.f);
+            if (layout == 0)
+                {
+                    if (i < consumed) v = code[i];
+                }
+            else if (layout == 1)
+                {
+                    const int off = n / 2;
+                    if (i >= off) v = code[i - off];
+                }
+            else
+                {
+                    const int off = n - consumed;
+                    if (i >= off) v = code[i - off];
+                }
+            s[i] = v;
+        }
+    fft_forward_smem(s, pl, tw);
+    // volk_32fc_conjugate_32fc (:250)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = make_float2(s[i].x, -s[i].y);
+}
+
+// ---- forward: wipe-off + FFT, one CTA per Doppler bin ------------------------------------------------
+__global__ void __launch_bounds__(kAcqThreads, 1) acq_fwd_kernel(const float2* __restrict__ in, int consumed,
+    const float2* __restrict__ wipe, float2* __restrict__ X, FftPlan pl, const float2* __restrict__ tw)
+{
+    extern __shared__ __align__(16) float2 s[];
+    const int n = pl.n;
+    const int d = blockIdx.x;
+    const float2* w = wipe + static_cast<size_t>(d) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            // acquisition_core zero-pads beyond consumed samples (:657-664); volk_32fc_x2_multiply_32fc (:531)
+            float2 v = make_float2(0.f, 0.f);
+            if (i < consumed)
+                {
+                    const float2 a = in[i];
+                    const float2 b = w[i];
+                    v.x = __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+                    v.y = __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
+                }
+            s[i] = v;
+        }
+    fft_forward_smem(s, pl, tw);
+    float2* o = X + static_cast<size_t>(d) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = s[i];
+}
+
+// ---- correlation rows ---------------------------------------------------------------------------------
+struct RowSink
+{
+    // natural-order outputs of the last inverse stage -> |y|^2 -> running statistics
+    int off;        // first output index that counts (bit_transition: effective_fft_size, else 0)
+    int ne;         // effective_fft_size
+    int ex1, ex2;   // excluded window [ex1, ex2) with wrap-around; ex1 < 0 disables
+    float* grid;    // optional magnitude row (ne floats): store or accumulate
+    int accumulate;
+    float best;
+    unsigned int best_t;
+    float sum;
+    __device__ __forceinline__ void operator()(float2* /*p*/, int pos, float2 v)
+    {
+        const int t = pos - off;
+        if (t < 0 || t >= ne) return;
+        // volk_32fc_magnitude_squared_32f (:547/:551)
+        float mag = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
+        if (grid)
+            {
+                if (accumulate) mag = __fadd_rn(grid[t], mag);  // volk_32f_x2_add_32f (:552)
+                grid[t] = mag;
+            }
+        if (ex1 >= 0)
+            {
+                const bool excluded = (ex1 <= ex2) ? (t >= ex1 && t < ex2) : (t >= ex1 || t < ex2);
+                if (excluded) mag = 0.0f;  // the reference zeroes the window before its second arg-max (:499-509)
+            }
+        sum += mag;
+        if (mag > best || (mag == best && static_cast<unsigned int>(t) < best_t))
+            {
+                best = mag;
+                best_t = static_cast<unsigned int>(t);
+            }
+    }
+};
+
+struct AcqBest
+{
+    unsigned int index_time;
+    unsigned int index_doppler;
+};
+
+// mode 0: grid = n_slots * bins rows; row r -> slot_list[r / bins], bin r % bins; writes rowstat.
+// mode 1: grid = n_slots; row = the winning (bin, index_time) in best[]; excluded window of
+//         +-samples_per_chip around the peak; writes second_peak[slot].
+__global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* __restrict__ X, const float2* __restrict__ codes,
+    const int* __restrict__ slot_list, int bins, FftPlan pl, const float2* __restrict__ tw, int off, int ne,
+    AcqRowStat* __restrict__ rowstat, float* __restrict__ grid, int accumulate, int mode,
+    const AcqBest* __restrict__ best, int samples_per_chip, float* __restrict__ second_peak)
+{
+    extern __shared__ __align__(16) float2 s[];
+    __shared__ float red_v[kAcqThreads / 32];
+    __shared__ unsigned int red_i[kAcqThreads / 32];
+    __shared__ float red_s[kAcqThreads / 32];
+    const int n = pl.n;
+    int slot_pos, bin;
+    RowSink sink;
+    sink.off = off;
+    sink.ne = ne;
+    sink.ex1 = -1;
+    sink.ex2 = -1;
+    sink.grid = nullptr;
+    sink.accumulate = accumulate;
+    if (mode == 0)
+        {
+            slot_pos = blockIdx.x / bins;
+            bin = blockIdx.x - slot_pos * bins;
+        }
+    else
+        {
+            slot_pos = blockIdx.x;
+            bin = static_cast<int>(best[slot_pos].index_doppler);
+            // pcps_acquisition.cc:485-497
+            int e1 = static_cast<int>(best[slot_pos].index_time) - samples_per_chip;
+            int e2 = static_cast<int>(best[slot_pos].index_time) + samples_per_chip;
+            if (e1 < 0)
+                e1 = ne + e1;
+            else if (e2 >= ne)
+                e2 = e2 - ne;
+            sink.ex1 = e1;
+            sink.ex2 = e2;
+        }
+    const int slot = slot_list[slot_pos];
+    if (grid != nullptr)
+        {
+            sink.grid = grid + (static_cast<size_t>(slot) * bins + bin) * ne;
+            if (mode == 1)
+                {
+                    // second-peak pass over an already accumulated grid row: read it, do not touch it
+                    sink.grid = nullptr;
+                }
+        }
+    sink.best = -1.0f;
+    sink.best_t = 0xffffffffu;
+    sink.sum = 0.0f;
+
+    if (mode == 1 && grid != nullptr)
+        {
+            // dwell-accumulated grids: statistics come from the stored row, not from a recomputation
+            const float* g = grid + (static_cast<size_t>(slot) * bins + bin) * ne;
+            for (int t = threadIdx.x; t < ne; t += blockDim.x)
+                {
+                    const bool excluded = (sink.ex1 <= sink.ex2) ? (t >= sink.ex1 && t < sink.ex2) : (t >= sink.ex1 || t < sink.ex2);
+                    const float mag = excluded ? 0.0f : g[t];
+                    if (mag > sink.best || (mag == sink.best && static_cast<unsigned int>(t) < sink.best_t))
+                        {
+                            sink.best = mag;
+                            sink.best_t = static_cast<unsigned int>(t);
+                        }
+                }
+        }
+    else
+        {
+            const float2* x = X + static_cast<size_t>(bin) * n;
+            const float2* c = codes + static_cast<size_t>(slot) * n;
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+                {
+                    // volk_32fc_x2_multiply_32fc (:538)
+                    const float2 a = x[i];
+                    const float2 b = __ldg(c + i);
+                    s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+                }
+            fft_inverse_smem(s, pl, tw, sink);
+        }
+
+    // CTA reduction with "first maximum" tie-break
+    float bv = sink.best;
+    unsigned int bi = sink.best_t;
+    float sm = sink.sum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const unsigned int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            if (ov > bv || (ov == bv && oi < bi))
+                {
+                    bv = ov;
+                    bi = oi;
+                }
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        {
+            red_v[warp] = bv;
+            red_i[warp] = bi;
+            red_s[warp] = sm;
+        }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        {
+            for (int w = 1; w < kAcqThreads / 32; w++)
+                {
+                    if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi))
+                        {
+                            bv = red_v[w];
+                            bi = red_i[w];
+                        }
+                    sm += red_s[w];
+                }
+            if (mode == 0)
+                {
+                    AcqRowStat r;
+                    r.max = bv;
+                    r.argmax = bi;
+                    r.sum = sm;
+                    r.pad = 0.f;
+                    rowstat[static_cast<size_t>(slot_pos) * bins + bin] = r;
+                }
+            else
+                {
+                    second_peak[slot_pos] = bv;
+                }
+        }
+}
+
+// ---- statistics ---------------------------------------------------------------------------------------
+// one thread per searched PRN (bins <= a few hundred): pcps_acquisition.cc:417-449 / :464-482
+__global__ void acq_stats_kernel(const AcqRowStat* __restrict__ rowstat, int n_slots, int bins, int ne, int doppler_max,
+    int doppler_center, int doppler_step, unsigned int dwell_counter, int use_cfar, AcqBest* __restrict__ best,
+    b200_acq_result* __restrict__ results)
+{
+    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sp >= n_slots) return;
+    const AcqRowStat* rs = rowstat + static_cast<size_t>(sp) * bins;
+    float grid_maximum = 0.0f;
+    unsigned int index_doppler = 0, index_time = 0;
+    for (int i = 0; i < bins; i++)
+        {
+            if (rs[i].max > grid_maximum)
+                {
+                    grid_maximum = rs[i].max;
+                    index_doppler = static_cast<unsigned int>(i);
+                    index_time = rs[i].argmax;
+                }
+        }
+    b200_acq_result r;
+    r.index_time = index_time;
+    r.index_doppler = index_doppler;
+    r.doppler = -doppler_max + doppler_center + doppler_step * static_cast<int>(index_doppler);
+    r.grid_maximum = grid_maximum;
+    r.test_statistics = 0.0f;
+    r.input_power = 0.0f;
+    r.second_peak = 0.0f;
+    if (use_cfar)
+        {
+            const unsigned int index_opp = (index_doppler + static_cast<unsigned int>(bins) / 2u) % static_cast<unsigned int>(bins);
+            // static_cast<float>(accumulate(...) / N_eff / 2.0 / counter)   (:431)
+            const float a = __fdiv_rn(rs[index_opp].sum, static_cast<float>(static_cast<unsigned int>(ne)));
+            const double ip = static_cast<double>(a) / 2.0 / static_cast<double>(dwell_counter);
+            const float input_power = static_cast<float>(ip);
+            r.input_power = input_power;
+            r.test_statistics = (input_power < 1.1920929e-07f) ? 0.0f : __fdiv_rn(grid_maximum, input_power);
+        }
+    best[sp].index_time = index_time;
+    best[sp].index_doppler = index_doppler;
+    results[sp] = r;
+}
+
+__global__ void acq_finish_second_peak_kernel(const float* __restrict__ second_peak, int n_slots, b200_acq_result* __restrict__ results)
+{
+    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sp >= n_slots) return;
+    const float sec = second_peak[sp];
+    results[sp].second_peak = sec;
+    results[sp].test_statistics = __fdiv_rn(results[sp].grid_maximum, sec);  // (:517)
+}
+
+// twiddle table exp(-2 pi j k / n) in double, rounded once
+__global__ void acq_twiddle_kernel(float2* __restrict__ tw, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s, c;
+    sincospi(-2.0 * static_cast<double>(k) / static_cast<double>(n), &s, &c);
+    tw[k] = make_float2(static_cast<float>(c), static_cast<float>(s));
+}
+
+bool g_attr_done = false;
+int set_attrs()
+{
+    if (g_attr_done) return B200_OK;
+    const int bytes = kAcqMaxSmemPoints * static_cast<int>(sizeof(float2));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_code_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_attr_done = true;
+    return B200_OK;
+}
+}  // namespace
+
+// ---- launchers (called from acq_engine.cu) --------------------------------------------------------------
+int acq_plan_make(int n, FftPlan* pl)
+{
+    if (n < 2 || n > kAcqMaxSmemPoints) return B200_ERR_RANGE;
+    int rem = n;
+    int cnt[8] = {0};
+    const int primes[4] = {7, 5, 3, 2};
+    for (int p : primes)
+        while (rem % p == 0)
+            {
+                cnt[p]++;
+                rem /= p;
+            }
+    if (rem != 1) return B200_ERR_RANGE;  // unsupported prime factor
+    pl->n = n;
+    int k = 0;
+    for (int i = 0; i < cnt[7]; i++) pl->radix[k++] = 7;
+    for (int i = 0; i < cnt[5]; i++) pl->radix[k++] = 5;
+    for (int i = 0; i < cnt[3]; i++) pl->radix[k++] = 3;
+    int twos = cnt[2];
+    while (twos >= 3)
+        {
+            pl->radix[k++] = 8;
+            twos -= 3;
+        }
+    if (twos == 2) pl->radix[k++] = 4;
+    if (twos == 1) pl->radix[k++] = 2;
+    if (k > kAcqMaxStages) return B200_ERR_RANGE;
+    pl->n_stages = k;
+    return B200_OK;
+}
+
+int acq_launch_twiddles(float2* tw, int n, cudaStream_t st)
+{
+    acq_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(tw, n);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_wipeoff(float2* wipe, int n, int bins, int doppler_max, int doppler_center, int doppler_step,
+    int doppler_bias, long long fs_in, cudaStream_t st)
+{
+    acq_wipeoff_kernel<<<bins, 32, 0, st>>>(wipe, n, bins, doppler_max, doppler_center, doppler_step, doppler_bias, fs_in);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_code_fft(const float2* code, int consumed, int layout, float2* out, const FftPlan& pl, const float2* tw, cudaStream_t st)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    acq_code_fft_kernel<<<1, kAcqThreads, pl.n * sizeof(float2), st>>>(code, consumed, layout, out, pl, tw);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_fwd(const float2* in, int consumed, const float2* wipe, float2* X, int bins, const FftPlan& pl, const float2* tw, cudaStream_t st)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    acq_fwd_kernel<<<bins, kAcqThreads, pl.n * sizeof(float2), st>>>(in, consumed, wipe, X, pl, tw);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_corr(const float2* X, const float2* codes, const int* slot_list, int n_slots, int bins, const FftPlan& pl,
+    const float2* tw, int off, int ne, AcqRowStat* rowstat, float* grid, int accumulate, int mode, const void* best,
+    int samples_per_chip, float* second_peak, cudaStream_t st)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    const int grid_dim = (mode == 0) ? n_slots * bins : n_slots;
+    acq_corr_kernel<<<grid_dim, kAcqThreads, pl.n * sizeof(float2), st>>>(X, codes, slot_list, bins, pl, tw, off, ne, rowstat,
+        grid, accumulate, mode, static_cast<const AcqBest*>(best), samples_per_chip, second_peak);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_stats(const AcqRowStat* rowstat, int n_slots, int bins, int ne, int doppler_max, int doppler_center,
+    int doppler_step, unsigned int dwell_counter, int use_cfar, void* best, b200_acq_result* results, cudaStream_t st)
+{
+    acq_stats_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(rowstat, n_slots, bins, ne, doppler_max, doppler_center, doppler_step,
+        dwell_counter, use_cfar, static_cast<AcqBest*>(best), results);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_finish_second_peak(const float* second_peak, int n_slots, b200_acq_result* results, cudaStream_t st)
+{
+    acq_finish_second_peak_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(second_peak, n_slots, results);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -23,61 +23,11 @@ void set_error(const char* fmt, ...)
 }
 const char* get_error() { return g_err; }
 
-constexpr int kMaxBands = 16;
-
-struct Band
-{
-    float2* dev{nullptr};      // owned ring (nullptr when attached)
-    const float2* base{nullptr};
-    unsigned long long mask{0};
-    unsigned long long first_index{0};
-    unsigned long long capacity{0};
-    unsigned long long write_index{0};  // absolute index of the next pushed sample
-    bool attached{false};
-    bool in_use{false};
-};
-
-struct Channel
-{
-    float* code_dev{nullptr};
-    int code_cap{0};
-    ChanDesc desc{};
-};
 }  // namespace b200
 
-using namespace b200;
+#include "engine.cuh"
 
-struct b200_engine
-{
-    int device{0};
-    cudaStream_t stream{nullptr};
-    bool own_stream{false};
-    cudaStream_t copy_stream{nullptr};
-    cudaEvent_t copy_done{nullptr};
-    cudaEvent_t t0{nullptr}, t1{nullptr};
-    std::mutex mu;
-    Band bands[kMaxBands];
-    std::vector<Channel> chans;
-    // device mirrors
-    BandDesc* bands_dev{nullptr};
-    ChanDesc* chans_dev{nullptr};
-    int chans_dev_cap{0};
-    bool tables_dirty{true};
-    int max_code_len{0};
-    int taps_uniform{-1};
-    // batch staging
-    b200_trk_item* items_dev{nullptr};
-    b200_trk_item* items_pin{nullptr};
-    float2* out_dev{nullptr};
-    float2* out_pin{nullptr};
-    int batch_cap{0};
-    int out_cap{0};
-    float2* partial{nullptr};
-    unsigned int* counters{nullptr};
-    size_t partial_cap{0};
-    int counters_cap{0};
-    uint64_t launches{0};
-};
+using namespace b200;
 
 namespace
 {

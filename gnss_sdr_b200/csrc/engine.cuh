@@ -1,0 +1,64 @@
+// Host-side engine state shared by engine.cu (tracking) and acq_engine.cu (acquisition).
+#pragma once
+
+#include "common.cuh"
+
+#include <mutex>
+#include <vector>
+
+namespace b200
+{
+constexpr int kMaxBands = 16;
+
+struct Band
+{
+    float2* dev{nullptr};      // owned ring (nullptr when attached)
+    const float2* base{nullptr};
+    unsigned long long mask{0};
+    unsigned long long first_index{0};
+    unsigned long long capacity{0};
+    unsigned long long write_index{0};  // absolute index of the next pushed sample
+    bool attached{false};
+    bool in_use{false};
+};
+
+struct Channel
+{
+    float* code_dev{nullptr};
+    int code_cap{0};
+    ChanDesc desc{};
+};
+}  // namespace b200
+
+struct b200_engine
+{
+    int device{0};
+    cudaStream_t stream{nullptr};
+    bool own_stream{false};
+    cudaStream_t copy_stream{nullptr};
+    cudaEvent_t copy_done{nullptr};
+    cudaEvent_t t0{nullptr}, t1{nullptr};
+    std::mutex mu;
+    b200::Band bands[b200::kMaxBands];
+    std::vector<b200::Channel> chans;
+    // device mirrors
+    b200::BandDesc* bands_dev{nullptr};
+    b200::ChanDesc* chans_dev{nullptr};
+    int chans_dev_cap{0};
+    bool tables_dirty{true};
+    int max_code_len{0};
+    int taps_uniform{-1};
+    // batch staging
+    b200_trk_item* items_dev{nullptr};
+    b200_trk_item* items_pin{nullptr};
+    float2* out_dev{nullptr};
+    float2* out_pin{nullptr};
+    int batch_cap{0};
+    int out_cap{0};
+    float2* partial{nullptr};
+    unsigned int* counters{nullptr};
+    size_t partial_cap{0};
+    int counters_cap{0};
+    uint64_t launches{0};
+};
+

@@ -130,6 +130,63 @@ extern "C"
     /* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
     int b200_engine_launch_count(b200_engine* e, uint64_t* n);
 
+    /* ---- acquisition: PCPS grid search, 1:1 with the arithmetic of pcps_acquisition ------------- */
+    /* src/algorithms/acquisition/gnuradio_blocks/pcps_acquisition.{h,cc}.  One b200_acq holds what one
+     * pcps_acquisition block holds (FFT plan, Doppler wipe-off grid, local-code spectra, magnitude
+     * grid) for up to n_code_slots PRNs, so that a cold-start sweep can search many PRNs on the
+     * same samples while computing the wiped-off forward FFTs once. */
+    typedef struct b200_acq_conf
+    {
+        uint32_t fft_size;            /* d_fft_size            (pcps_acquisition.cc:110) */
+        uint32_t effective_fft_size;  /* d_effective_fft_size  (:111) */
+        uint32_t consumed_samples;    /* d_consumed_samples    (:109) */
+        uint32_t num_doppler_bins;    /* d_num_doppler_bins = ceil(2*doppler_max/doppler_step) (:112) */
+        int32_t doppler_max;          /* Acq_Conf::doppler_max   */
+        int32_t doppler_step;         /* Acq_Conf::doppler_step  */
+        int64_t fs_in;                /* Acq_Conf::fs_in (or resampled_fs) used by update_local_carrier (:277) */
+        uint32_t samples_per_chip;    /* Acq_Conf::samples_per_chip (second-peak exclusion window, :485) */
+        uint32_t code_layout;         /* set_local_code placement: 0 front (:238-241), 1 bit-transition (:230-235), 2 zero-padded front (:243-246) */
+        int32_t bit_transition_flag;  /* magnitudes taken from ifft_out + effective_fft_size (:544) */
+        int32_t use_cfar;             /* d_use_CFAR_algorithm_flag: max/input-power (:409-449) else first/second peak (:452-519) */
+        uint32_t max_dwells;          /* >1 allocates the magnitude grid so dwells can accumulate (:545-553) */
+        uint32_t n_code_slots;        /* local-code spectra kept resident (PRNs searched per call <= this) */
+        int32_t keep_grid;            /* 1: always materialise d_magnitude_grid (dump / mag()) */
+    } b200_acq_conf;
+
+    typedef struct b200_acq_result
+    {
+        uint32_t index_time;     /* AcquisitionResult::index_time (first maximum of the winning bin) */
+        uint32_t index_doppler;  /* winning Doppler bin */
+        int32_t doppler;         /* AcquisitionResult::doppler = -doppler_max + center + step*index_doppler (:432,:476) */
+        float test_statistics;   /* AcquisitionResult::test_statistics */
+        float grid_maximum;      /* peak |y|^2 */
+        float input_power;       /* d_input_power (CFAR) */
+        float second_peak;       /* secondPeak (non-CFAR) */
+    } b200_acq_result;
+
+    /* pcps_acquisition::pcps_acquisition(conf)  (:100-193): plan, buffers, wipe-off grid for center 0 */
+    int b200_acq_create(b200_engine* e, const b200_acq_conf* conf, b200_acq** out);
+    /* set_local_code(code)  (:218-251): code_host holds consumed_samples (layout 0/2) or fft_size/2
+     * (layout 1) complex samples; stores conj(FFT(padded code)) in slot `slot`. */
+    int b200_acq_set_local_code(b200_acq* a, uint32_t slot, const b200_cf32* code_host);
+    /* set_doppler_center / is_fdma bias + update_grid_doppler_wipeoffs  (:254-291) */
+    int b200_acq_set_doppler_center(b200_acq* a, int32_t doppler_center, int32_t doppler_bias);
+    /* acquisition_core's arithmetic (:648-683): doppler_grid + compute_statistics for n_slots PRNs on
+     * the same consumed_samples input.  dwell_counter = d_num_noncoherent_integrations_counter AFTER
+     * its increment (1 for the first dwell; >1 accumulates into the magnitude grid).
+     * results[i] belongs to slots[i].  Synchronous (input H2D, kernels, results D2H). */
+    int b200_acq_search(b200_acq* a, const b200_cf32* in_host, const uint32_t* slots, uint32_t n_slots,
+        uint32_t dwell_counter, b200_acq_result* results_host);
+    /* same with the input already on the device and results left on the device (asynchronous) */
+    int b200_acq_search_dev(b200_acq* a, const b200_cf32* in_dev, const uint32_t* slots_host, uint32_t n_slots,
+        uint32_t dwell_counter, b200_acq_result* results_dev);
+    /* d_magnitude_grid of one slot (bins x effective_fft_size floats); needs keep_grid or max_dwells>1.
+     * Replaces the grid copy in doppler_grid (:555-558) / dump_results (:354-406). */
+    int b200_acq_read_grid(b200_acq* a, uint32_t slot, float* grid_host);
+    /* the wipe-off grid (bins x fft_size complex), for parity tests against volk_gnsssdr_s32f_sincos_32fc */
+    int b200_acq_read_wipeoffs(b200_acq* a, b200_cf32* wipe_host);
+    int b200_acq_destroy(b200_acq* a);
+
 #ifdef __cplusplus
 }
 #endif
