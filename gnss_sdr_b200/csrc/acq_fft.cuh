@@ -19,7 +19,7 @@
 
 namespace b200
 {
-constexpr int kAcqThreads = 512;
+constexpr int kAcqThreads = 1024;
 constexpr int kAcqMaxStages = 16;
 constexpr int kAcqMaxSmemPoints = 27648;  // 216 KB of float2
 
@@ -27,8 +27,14 @@ struct FftPlan
 {
     int n;
     int n_stages;
-    int radix[kAcqMaxStages];  // forward DIF order; product = n
+    int radix[kAcqMaxStages];          // forward DIF order; product = n
+    unsigned int mdiv[kAcqMaxStages];  // floor(2^32 / m) + 1 for the stage's m = M / radix (exact i / m for i < 2^16)
 };
+
+__device__ __forceinline__ int fast_div(int i, int m, unsigned int magic)
+{
+    return (m == 1) ? i : static_cast<int>(__umulhi(static_cast<unsigned int>(i), magic));
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
@@ -180,14 +186,15 @@ struct StoreSink
 // M = current block length, R | M, m = M / R.  tw = global table exp(-2 pi j k / n), k < n.
 // sink(ptr, position, value) receives each output; position = index in the buffer.
 template <int R, bool INV, class Sink>
-__device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, const float2* __restrict__ tw, Sink& sink)
+__device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, unsigned int magic, const float2* __restrict__ tw, Sink& sink)
 {
     const int m = M / R;
     const int tw_stride = n / M;
     const int nb = n / R;
+#pragma unroll 2
     for (int i = threadIdx.x; i < nb; i += blockDim.x)
         {
-            const int b = i / m;
+            const int b = fast_div(i, m, magic);
             const int j = i - b * m;
             const int pos0 = b * M + j;
             float2* p = s + pos0;
@@ -234,16 +241,16 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
 }
 
 template <bool INV, class Sink>
-__device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, int M, const float2* tw, Sink& sink)
+__device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, int M, unsigned int magic, const float2* tw, Sink& sink)
 {
     switch (radix)
         {
-        case 2: fft_stage<2, INV>(s, n, M, tw, sink); break;
-        case 3: fft_stage<3, INV>(s, n, M, tw, sink); break;
-        case 4: fft_stage<4, INV>(s, n, M, tw, sink); break;
-        case 5: fft_stage<5, INV>(s, n, M, tw, sink); break;
-        case 7: fft_stage<7, INV>(s, n, M, tw, sink); break;
-        default: fft_stage<8, INV>(s, n, M, tw, sink); break;
+        case 2: fft_stage<2, INV>(s, n, M, magic, tw, sink); break;
+        case 3: fft_stage<3, INV>(s, n, M, magic, tw, sink); break;
+        case 4: fft_stage<4, INV>(s, n, M, magic, tw, sink); break;
+        case 5: fft_stage<5, INV>(s, n, M, magic, tw, sink); break;
+        case 7: fft_stage<7, INV>(s, n, M, magic, tw, sink); break;
+        default: fft_stage<8, INV>(s, n, M, magic, tw, sink); break;
         }
 }
 
@@ -255,7 +262,7 @@ __device__ __forceinline__ void fft_forward_smem(float2* s, const FftPlan& pl, c
     for (int st = 0; st < pl.n_stages; st++)
         {
             __syncthreads();
-            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, tw, st_sink);
+            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw, st_sink);
             M /= pl.radix[st];
         }
     __syncthreads();
@@ -272,10 +279,10 @@ __device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, c
         {
             M *= pl.radix[st];
             __syncthreads();
-            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, tw, st_sink);
+            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw, st_sink);
         }
     __syncthreads();
-    fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, tw, last);
+    fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw, last);
 }
 
 }  // namespace b200

@@ -447,9 +447,9 @@ int acq_plan_make(int n, FftPlan* pl)
     if (rem != 1) return B200_ERR_RANGE;  // unsupported prime factor
     pl->n = n;
     int k = 0;
-    for (int i = 0; i < cnt[7]; i++) pl->radix[k++] = 7;
-    for (int i = 0; i < cnt[5]; i++) pl->radix[k++] = 5;
-    for (int i = 0; i < cnt[3]; i++) pl->radix[k++] = 3;
+    // Powers of two first (large sub-block stride m, conflict-free stride-1 accesses), odd radices
+    // last: in the final stages consecutive threads are R*m apart and an ODD stride spreads over
+    // all shared-memory banks, while an even one would serialise.
     int twos = cnt[2];
     while (twos >= 3)
         {
@@ -458,8 +458,18 @@ int acq_plan_make(int n, FftPlan* pl)
         }
     if (twos == 2) pl->radix[k++] = 4;
     if (twos == 1) pl->radix[k++] = 2;
+    for (int i = 0; i < cnt[3]; i++) pl->radix[k++] = 3;
+    for (int i = 0; i < cnt[7]; i++) pl->radix[k++] = 7;
+    for (int i = 0; i < cnt[5]; i++) pl->radix[k++] = 5;
     if (k > kAcqMaxStages) return B200_ERR_RANGE;
     pl->n_stages = k;
+    int M = n;
+    for (int st = 0; st < k; st++)
+        {
+            const int m = M / pl->radix[st];
+            pl->mdiv[st] = (m <= 1) ? 0u : static_cast<unsigned int>((1ULL << 32) / static_cast<unsigned long long>(m)) + 1u;
+            M = m;
+        }
     return B200_OK;
 }
 
