@@ -92,6 +92,50 @@ __device__ __forceinline__ float2 ldg_stream8(const float2* p)
     return v;
 }
 
+
+// ---- packed f32x2 arithmetic (Blackwell FADD2/FMUL2/FFMA2), explicit .rn/.rm in PTX so that
+// ptxas can never contract a separately rounded mul+add of the chip-index arithmetic into an FMA.
+typedef unsigned long long f2x;  // two packed floats: .x in the low word, .y in the high word
+__device__ __forceinline__ f2x pk(float lo, float hi)
+{
+    f2x r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk(f2x v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void unpk_u(f2x v, unsigned int& lo, unsigned int& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f2x mul2_rn(f2x a, f2x b)
+{
+    f2x r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2x add2_rn(f2x a, f2x b)
+{
+    f2x r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2x add2_rm(f2x a, f2x b)
+{
+    f2x r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2x fma2_rn(f2x a, f2x b, f2x c)
+{
+    f2x r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f2x neg2(f2x a) { return a ^ 0x8000000080000000ULL; }
+__device__ __forceinline__ float lds_f32(unsigned int addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 struct ItemCtx
 {
     const float2* base;
@@ -188,6 +232,103 @@ __device__ __forceinline__ void correlate_range(const ItemCtx& cx, const float (
                             acc[t].y = fmaf(wi, c, acc[t].y);
                         }
                 }
+        }
+}
+
+
+// ---- main tiles, FAST path: packed arithmetic on sample pairs, no modulo, no F2I -------------------
+// Lane .x of every packed value belongs to sample n0, lane .y to sample n0+1 (one LDG.128).
+// floor() uses the 1.5*2^23 trick: fl_rm(aux + 12582912.f) has floor(aux) in its low mantissa bits
+// (exact for |aux| < 2^22, guaranteed by the caller's range check), so the table address is one LEA:
+//   addr = (bits << 2) + tbl_off,  tbl_off = smem(table) - 4*(tbl_base + 0x4B400000)  (mod 2^32).
+// NOTE: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit rounding
+// modifiers and --fmad=false, which would change chip indices; the products step*n therefore use
+// the scalar __fmul_rn (never contracted) and only the additions are packed.
+template <int TAPS, bool WRAPS>
+__device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const float (&shifts)[TAPS], unsigned int tbl_off,
+    int tile_begin, int tile_end, int head, float2 (&acc)[TAPS])
+{
+    const int tid = threadIdx.x;
+    float2 aux2[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+        {
+            const float a = __fsub_rn(shifts[t], cx.rem);
+            aux2[t] = make_float2(a, a);
+        }
+    float2 are[TAPS], aim[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) are[t] = aim[t] = make_float2(0.f, 0.f);
+
+    const float2 magic2 = make_float2(12582912.0f, 12582912.0f);
+    const float2 D = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile));
+    const float2 Dr2 = make_float2(D.x, D.x), Di2 = make_float2(D.y, D.y);
+    // group-to-group phasor step: kTrkReseed tiles
+    const float2 G = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile * kTrkReseed));
+    const float2 Gr2 = make_float2(G.x, G.x), Gi2 = make_float2(G.y, G.y);
+
+    int n0 = head + tile_begin * kTrkTile + 2 * tid;
+    float2 zr2, zi2;   // phasors of the two samples at the start of the current group
+    {
+        const float2 za = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0));
+        const float2 zb = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0 + 1));
+        zr2 = make_float2(za.x, zb.x);
+        zi2 = make_float2(za.y, zb.y);
+    }
+    float nfa = static_cast<float>(n0), nfb = static_cast<float>(n0 + 1);
+    const float2* ptr = cx.base + ((cx.s0 + static_cast<unsigned long long>(n0)) & cx.mask);
+
+    for (int tg = tile_begin; tg < tile_end; tg += kTrkReseed)
+        {
+            const int tg_end = min(tg + kTrkReseed, tile_end);
+            float2 zr = zr2, zi = zi2;   // running phasors inside the group
+#pragma unroll 4
+            for (int tile = tg; tile < tg_end; tile++)
+                {
+                    float4 v;
+                    if (WRAPS)
+                        v = ldg_stream16(cx.base + ((cx.s0 + static_cast<unsigned long long>(n0)) & cx.mask));
+                    else
+                        v = ldg_stream16(ptr);
+                    // w = x * z, scalar: the LDG.128 delivers (re,im,re,im), so packed operands would
+                    // need 8 register moves per tile; scalar results land directly in register pairs
+                    float2 wr2, wi2;
+                    wr2.x = fmaf(v.x, zr.x, -v.y * zi.x);
+                    wi2.x = fmaf(v.x, zi.x, v.y * zr.x);
+                    wr2.y = fmaf(v.z, zr.y, -v.w * zi.y);
+                    wi2.y = fmaf(v.z, zi.y, v.w * zr.y);
+                    const float2 m2 = make_float2(__fmul_rn(cx.step, nfa), __fmul_rn(cx.step, nfb));
+#pragma unroll
+                    for (int t = 0; t < TAPS; t++)
+                        {
+                            const float2 tt = __fadd2_rd(__fadd2_rn(m2, aux2[t]), magic2);
+                            const float ca = lds_f32((__float_as_uint(tt.x) << 2) + tbl_off);
+                            const float cb = lds_f32((__float_as_uint(tt.y) << 2) + tbl_off);
+                            const float2 c2 = make_float2(ca, cb);
+                            are[t] = __ffma2_rn(wr2, c2, are[t]);
+                            aim[t] = __ffma2_rn(wi2, c2, aim[t]);
+                        }
+                    // z *= D
+                    const float2 t1 = __fmul2_rn(zi, Di2);
+                    const float2 nzr = __ffma2_rn(zr, Dr2, make_float2(-t1.x, -t1.y));
+                    zi = __ffma2_rn(zr, Di2, __fmul2_rn(zi, Dr2));
+                    zr = nzr;
+                    nfa += static_cast<float>(kTrkTile);
+                    nfb += static_cast<float>(kTrkTile);
+                    n0 += kTrkTile;
+                    ptr += kTrkTile;
+                }
+            // group seed advances by G (few steps per epoch: error stays ~1e-7 per step)
+            const float2 t2 = __fmul2_rn(zi2, Gi2);
+            const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
+            zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
+            zr2 = ngr;
+        }
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+        {
+            acc[t].x += are[t].x + are[t].y;
+            acc[t].y += aim[t].x + aim[t].y;
         }
 }
 
@@ -327,7 +468,28 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
                         }
                     __syncthreads();
                     LookupExt lut{smem_tbl - base_i};
-                    correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                    if (lo > -4000000LL && hi < 4000000LL)
+                        {
+                            // computed inside an asm so the optimiser cannot split the constant back out of
+                            // the per-lookup LEA
+                            unsigned int tbl_off;
+                            asm("sub.u32 %0, %1, %2;"
+                                : "=r"(tbl_off)
+                                : "r"(static_cast<unsigned int>(__cvta_generic_to_shared(smem_tbl))),
+                                  "r"(4u * (static_cast<unsigned int>(base_i) + 0x4B400000u)));
+                            // ring wrap inside the epoch? (uniform per item)
+                            const bool wraps = ((cx.s0 & cx.mask) + static_cast<unsigned long long>(cx.N)) > cx.mask;
+                            if (wraps)
+                                correlate_tiles_fast<TAPS, true>(cx, shifts, tbl_off, tb, te, head, acc);
+                            else
+                                correlate_tiles_fast<TAPS, false>(cx, shifts, tbl_off, tb, te, head, acc);
+                            // remainder samples only (no main tiles) through the scalar path
+                            correlate_range<TAPS>(cx, shifts, lut, 0, 0, head, rem_here, n_main_end, acc);
+                        }
+                    else
+                        {
+                            correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                        }
                 }
             else
                 {
