@@ -1,0 +1,154 @@
+// Parity test of the C++ host mirror classes against the reference's own class, written the way
+// the reference's engine test is (tests/unit-tests/signal-processing-blocks/tracking/
+// cpu_multicorrelator_real_codes_test.cc:65-180: same sizes 2048/4096/8192, 3 taps at +-0.5 chip,
+// PRN-like code, uniform-random IQ, concurrent correlator objects on std::threads) -- except that
+// it CHECKS the E/P/L values instead of only timing them.
+//
+// Build (tests/test_host_mirror.py does this):
+//   g++ -std=c++17 tests/host/test_host_mirror.cc gnss_sdr_b200/host/*.cc -Iinclude -Ignss_sdr_b200/host
+//       -Lgnss_sdr_b200 -lb200gnss [-DHAVE_REF oracle/_ref/liboracle_ref.so] -lpthread
+#include "b200_multicorrelator_real_codes.h"
+#include "b200_pcps_acquisition_core.h"
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <random>
+#include <thread>
+#include <vector>
+
+#ifdef HAVE_REF
+extern "C"
+{
+    void* ref_mc_create(int max_len, int taps, int high_dyn);
+    int ref_mc_set_code(void* h, const float* code, int code_len, const float* shifts);
+    int ref_mc_correlate(void* h, const float* in_iq, float rem_carr_rad, float phase_step_rad, float phase_rate_step_rad,
+        float rem_code_chips, float code_step_chips, float code_rate_step_chips, int n, float* out_taps);
+    void ref_mc_destroy(void* h);
+    int ref_select_arch(const char* arch);
+}
+#endif
+
+static int g_fail = 0;
+#define CHECK(cond, ...)                      \
+    do                                        \
+        {                                     \
+            if (!(cond))                      \
+                {                             \
+                    std::printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+                    std::printf(__VA_ARGS__); \
+                    std::printf("\n");        \
+                    g_fail++;                 \
+                }                             \
+        }                                     \
+    while (0)
+
+static void correlator_worker(int tid, int n, int iters, const std::vector<float>* code, const std::vector<std::complex<float>>* in,
+    std::vector<std::complex<float>>* out)
+{
+    B200_Multicorrelator_Real_Codes mc;
+    float shifts[3] = {-0.5F, 0.0F, 0.5F};
+    if (!mc.init(8192, 3))
+        {
+            std::printf("init failed: %s\n", mc.last_error());
+            g_fail++;
+            return;
+        }
+    mc.set_high_dynamics_resampler(false);
+    mc.set_local_code_and_taps(static_cast<int>(code->size()), code->data(), shifts);
+    mc.set_input_output_vectors(out->data() + 3 * tid, in->data());
+    for (int k = 0; k < iters; k++)
+        {
+            // cpu_multicorrelator_real_codes_test.cc:129-133 parameters
+            if (!mc.Carrier_wipeoff_multicorrelator_resampler(0.0F, 0.1F, 0.0F, 0.4F, 0.3F, 0.0F, n)) g_fail++;
+        }
+    mc.free();
+}
+
+int main()
+{
+    std::mt19937 rng(7);
+    std::uniform_real_distribution<float> ud(0.0F, 1.0F);
+    std::vector<float> code(1023);
+    for (auto& c : code) c = (rng() & 1U) ? 1.0F : -1.0F;
+    std::vector<std::complex<float>> in(2 * 8192);
+    for (auto& v : in) v = std::complex<float>(ud(rng), ud(rng));
+
+    const int sizes[3] = {2048, 4096, 8192};
+    for (int n : sizes)
+        {
+            const int threads = 6;
+            std::vector<std::complex<float>> out(3 * threads);
+            std::vector<std::thread> pool;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int t = 0; t < threads; t++) pool.emplace_back(correlator_worker, t, n, 50, &code, &in, &out);
+            for (auto& t : pool) t.join();
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            std::printf("B200 multicorrelator (real codes): %d concurrent correlators, length=%d : %.3e [s] per call\n", threads, n, dt / 50);
+            for (int t = 1; t < threads; t++)
+                for (int k = 0; k < 3; k++) CHECK(out[3 * t + k] == out[k], "thread %d tap %d differs", t, k);
+#ifdef HAVE_REF
+            ref_select_arch("a_avx");
+            void* h = ref_mc_create(8192, 3, 0);
+            float shifts[3] = {-0.5F, 0.0F, 0.5F};
+            ref_mc_set_code(h, code.data(), 1023, shifts);
+            std::complex<float> want[3];
+            ref_mc_correlate(h, reinterpret_cast<const float*>(in.data()), 0.0F, 0.1F, 0.0F, 0.4F, 0.3F, 0.0F, n, reinterpret_cast<float*>(want));
+            ref_mc_destroy(h);
+            for (int k = 0; k < 3; k++)
+                {
+                    const float rel = std::abs(out[k] - want[k]) / std::abs(want[k]);
+                    CHECK(rel < 1e-3F, "n=%d tap %d: got (%g,%g) want (%g,%g) rel %g", n, k, out[k].real(), out[k].imag(), want[k].real(), want[k].imag(), rel);
+                }
+#endif
+        }
+
+    // ---- acquisition core: PRN-like code delayed by 524 samples and shifted by +1680 Hz -----------
+    {
+        b200::Acq_Conf_Core conf;
+        conf.fs_in = 4000000;
+        conf.samples_per_ms = 4000.0F;
+        conf.samples_per_code = 4000.0F;
+        conf.samples_per_chip = 3;
+        conf.doppler_max = 5000;
+        conf.doppler_step = 250;
+        conf.pfa = 0.001F;
+        b200::Pcps_Acquisition_Core acq(conf);
+        CHECK(acq.ok(), "acquisition core not created");
+        CHECK(acq.d_fft_size == 4000 && acq.d_num_doppler_bins == 40, "sizes");
+        // closed form check of the threshold: P(2, th/2) = (1-pfa)^(1/nbins)
+        const double x = acq.get_threshold() / 2.0;
+        const double q = (1.0 + x) * std::exp(-x);
+        CHECK(std::fabs(q / (-std::expm1(std::log1p(-0.001) / 160000.0)) - 1.0) < 1e-5, "threshold %g", acq.get_threshold());
+        std::vector<std::complex<float>> sampled(4000);
+        for (int i = 0; i < 4000; i++) sampled[i] = std::complex<float>(0.0F, code[static_cast<size_t>(i * 1023.0 / 4000.0)]);
+        std::vector<std::complex<float>> sig(4000);
+        std::normal_distribution<float> nd(0.0F, 1.0F);
+        for (int i = 0; i < 4000; i++)
+            {
+                const double ph = 2.0 * M_PI * 1680.0 * i / 4e6;
+                const std::complex<float> c = sampled[(i + 4000 - 524) % 4000];
+                sig[i] = 0.2F * c * std::complex<float>(static_cast<float>(std::cos(ph)), static_cast<float>(std::sin(ph))) + std::complex<float>(nd(rng), nd(rng));
+            }
+        b200::Acq_Synchro syn;
+        acq.set_gnss_synchro(&syn);
+        acq.set_local_code(sampled.data());
+        acq.init();
+        acq.set_active(true);
+        b200::AcquisitionResult res;
+        const int ev = acq.acquisition_core(sig.data(), 123456, &res);
+        std::printf("acquisition: event %d, delay %.0f samples, doppler %.0f Hz, stat %.1f (threshold %.1f)\n", ev, syn.Acq_delay_samples,
+            syn.Acq_doppler_hz, res.test_statistics, acq.get_threshold());
+        // the reference test's tolerances (gps_l1_ca_pcps_acquisition_test.cc:357-364)
+        CHECK(ev == 1, "expected a positive acquisition");
+        CHECK(std::fabs(syn.Acq_delay_samples - 524.0) <= 2.0, "delay %g", syn.Acq_delay_samples);
+        CHECK(std::fabs(syn.Acq_doppler_hz - 1680.0) <= 666.0, "doppler %g", syn.Acq_doppler_hz);
+        CHECK(syn.Acq_samplestamp_samples == 123456, "sample stamp");
+        // noise only -> negative acquisition (event 2)
+        for (auto& v : sig) v = std::complex<float>(nd(rng), nd(rng));
+        acq.init();
+        CHECK(acq.acquisition_core(sig.data(), 1, &res) == 2, "noise must not be acquired (stat %g)", res.test_statistics);
+    }
+    std::printf(g_fail ? "HOST_MIRROR_FAILED (%d)\n" : "HOST_MIRROR_OK\n", g_fail);
+    return g_fail ? 1 : 0;
+}
