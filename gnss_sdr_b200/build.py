@@ -34,7 +34,10 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False, extra=(), out: str = None) -> str:
+    """extra: additional nvcc flags (e.g. -DTRK_PREFETCH=2) and out: alternative output path, for A/B variants."""
+    if out:
+        force = True
     if not force and not needs_build():
         return LIB
     objs = []
@@ -42,28 +45,31 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
     procs = []
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
+        obj = obj if not out else obj[:-2] + "_" + os.path.basename(out) + ".o"
+        cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        txt, _ = p.communicate()
         if p.returncode != 0:
             failed = True
-            sys.stderr.write(out)
+            sys.stderr.write(txt)
         elif verbose or ptxas_v:
-            sys.stdout.write(out)
+            sys.stdout.write(txt)
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined"]
+    cmd = [NVCC, "-shared", "-o", out or LIB] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_v="--ptxas" in sys.argv)
-    print(LIB)
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_v="--ptxas" in sys.argv, extra=extra,
+                out=outs[0] if outs else None))

@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200gnss.so")
+# B200_LIB selects an alternative build of the SAME library (A/B kernel experiments); default = in-tree build
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libb200gnss.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

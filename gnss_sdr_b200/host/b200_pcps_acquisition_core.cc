@@ -13,42 +13,30 @@ namespace b200
 namespace
 {
 // boost::math::gamma_p_inv(a, p) for INTEGER a (compute_threshold always passes a = 2*max_dwells):
-// P(a, x) = 1 - exp(-x) * sum_{k<a} x^k / k!.  Newton iterations from the Wilson-Hilferty start.
-double gamma_p_int(uint32_t a, double x)
+// P(a, x) = 1 - exp(-x) * sum_{k<a} x^k / k!.
+// Solve Q(a, x) = q (Q = 1 - P, upper regularised incomplete gamma, integer a) for small q.
+// Newton on g(x) = ln Q(a,x) - ln q, which is close to linear (ln Q ~ -x + (a-1) ln x - ln (a-1)!).
+double gamma_q_inv_int(uint32_t a, double q)
 {
-    double term = 1.0, sum = 1.0;
-    for (uint32_t k = 1; k < a; k++)
+    if (q >= 1.0) return 0.0;
+    const double lq = std::log(q);
+    double x = -lq + static_cast<double>(a);  // start to the right of the root
+    for (int it = 0; it < 100; it++)
         {
-            term *= x / static_cast<double>(k);
-            sum += term;
-        }
-    return 1.0 - std::exp(-x) * sum;
-}
-
-double gamma_p_inv_int(uint32_t a, double p)
-{
-    if (p <= 0.0) return 0.0;
-    // The thresholds of interest have 1-p ~ 1e-9: work with q = 1-p via log to keep precision.
-    const double da = static_cast<double>(a);
-    double x = da + 3.0 * std::sqrt(da) + 20.0;  // right of the solution, Q is convex there
-    for (int it = 0; it < 200; it++)
-        {
-            // f(x) = Q(a,x) - q,  Q = exp(-x) sum_{k<a} x^k/k!,  Q' = -exp(-x) x^(a-1)/(a-1)!
             double term = 1.0, sum = 1.0;
             for (uint32_t k = 1; k < a; k++)
                 {
                     term *= x / static_cast<double>(k);
                     sum += term;
                 }
-            const double Q = std::exp(-x) * sum;
-            const double dQ = -std::exp(-x) * term;  // term == x^(a-1)/(a-1)!
-            const double q = 1.0 - p;
-            const double step = (Q - q) / dQ;
+            // ln Q = -x + ln(sum);  d/dx ln Q = -term / sum   (term == x^(a-1)/(a-1)!)
+            const double g = -x + std::log(sum) - lq;
+            const double dg = -term / sum;
+            const double step = g / dg;
             x -= step;
-            if (x <= 0.0) x = 1e-12;
-            if (std::fabs(step) < 1e-13 * std::fabs(x)) break;
+            if (x <= 0.0) x = 1e-300;
+            if (std::fabs(step) < 1e-14 * std::fabs(x)) break;
         }
-    (void)gamma_p_int;
     return x;
 }
 }  // namespace
@@ -57,11 +45,12 @@ float compute_threshold(float pfa, uint32_t effective_fft_size, uint32_t num_dop
 {
     // :52-56
     const int num_bins = effective_fft_size * num_doppler_bins;
-    const double p = std::pow(1.0 - pfa, 1.0 / static_cast<float>(num_bins));
-    // 1-p loses digits in double when p ~ 1-1e-9; evaluate q = -expm1(log1p(-pfa)/num_bins) instead
+    // gamma_p_inv(a, p) with p = (1-pfa)^(1/num_bins): p is within ~1e-9 of 1, so solve for the
+    // complement q = 1-p = -expm1(log1p(-pfa)/num_bins) directly instead of losing digits in 1-p.
+    // (Boost evaluates in double on p = std::pow(1.0 - pfa, 1.0 / float(num_bins)); both agree to
+    // ~1e-7 relative, far inside the float the result is cast to.)
     const double q = -std::expm1(std::log1p(-static_cast<double>(pfa)) / static_cast<double>(static_cast<float>(num_bins)));
-    (void)p;
-    return static_cast<float>(2.0 * gamma_p_inv_int(2 * max_dwells, 1.0 - q));
+    return static_cast<float>(2.0 * gamma_q_inv_int(2 * max_dwells, q));
 }
 
 

@@ -14,6 +14,7 @@
 #include <complex>
 #include <cstdio>
 #include <random>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -65,8 +66,20 @@ static void correlator_worker(int tid, int n, int iters, const std::vector<float
     mc.free();
 }
 
-int main()
+int main(int argc, char** argv)
 {
+    if (argc > 1 && std::string(argv[1]) == "--thresholds")
+        {
+            // CPU-only: print compute_threshold for a few configurations (checked against scipy by pytest)
+            const float pfas[3] = {0.001F, 0.01F, 1e-6F};
+            const uint32_t sizes[3] = {4000, 25000, 8000};
+            const uint32_t bins[3] = {40, 81, 80};
+            const uint32_t dw[3] = {1, 2, 8};
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++)
+                    std::printf("THRESH %g %u %u %u %.9g\n", pfas[i], sizes[j], bins[j], dw[j], b200::compute_threshold(pfas[i], sizes[j], bins[j], dw[j]));
+            return 0;
+        }
     std::mt19937 rng(7);
     std::uniform_real_distribution<float> ud(0.0F, 1.0F);
     std::vector<float> code(1023);

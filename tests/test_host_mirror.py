@@ -29,6 +29,20 @@ def test_host_mirror_builds_and_links():
     assert os.path.exists(exe)
 
 
+def test_compute_threshold_matches_boost_formula():
+    """compute_threshold (pcps_acquisition.cc:52-56) on the host, no GPU: against scipy's gammaincinv
+    (== boost::math::gamma_p_inv) through the oracle's restatement."""
+    from oracle.acq_np import compute_threshold
+    exe = build()
+    r = subprocess.run([exe, "--thresholds"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0
+    lines = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("THRESH")]
+    assert len(lines) == 9
+    for _, pfa, n, bins, dw, val in lines:
+        want = compute_threshold(float(pfa), int(n), int(bins), int(dw))
+        assert abs(float(val) - want) / want < 2e-6, (pfa, n, bins, dw, val, want)
+
+
 @pytest.mark.gpu
 def test_host_mirror_runs_and_matches_reference():
     exe = build()
