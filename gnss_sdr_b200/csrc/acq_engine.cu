@@ -167,7 +167,7 @@ extern "C"
                     }
                 B200_CUDA_TRY(cudaMemsetAsync(a->grid, 0, sizeof(float) * ne * bins * slots, a->stream));
             }
-        rc = acq_launch_twiddles(a->tw, static_cast<int>(n), a->stream);
+        rc = acq_launch_twiddles(a->tw, a->plan, a->stream);
         if (rc) return rc;
         rc = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, a->stream);
         if (rc) return rc;

@@ -29,6 +29,7 @@ struct FftPlan
     int n_stages;
     int radix[kAcqMaxStages];          // forward DIF order; product = n
     unsigned int mdiv[kAcqMaxStages];  // floor(2^32 / m) + 1 for the stage's m = M / radix (exact i / m for i < 2^16)
+    int tw_off[kAcqMaxStages];         // start of the stage's compact twiddle table: exp(-2 pi j k / M), k < m
 };
 
 __device__ __forceinline__ int fast_div(int i, int m, unsigned int magic)
@@ -183,13 +184,13 @@ struct StoreSink
 };
 
 // One DIF (forward) or DIT (inverse) stage over a buffer of n points in shared memory.
-// M = current block length, R | M, m = M / R.  tw = global table exp(-2 pi j k / n), k < n.
+// M = current block length, R | M, m = M / R.  tw = this stage's compact table exp(-2 pi j k / M), k < m
+// (contiguous, so a warp's twiddle loads are coalesced and the small late-stage tables stay in L1).
 // sink(ptr, position, value) receives each output; position = index in the buffer.
 template <int R, bool INV, class Sink>
 __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, unsigned int magic, const float2* __restrict__ tw, Sink& sink)
 {
     const int m = M / R;
-    const int tw_stride = n / M;
     const int nb = n / R;
 #pragma unroll 2
     for (int i = threadIdx.x; i < nb; i += blockDim.x)
@@ -205,7 +206,7 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
                 {
                     if (m > 1)
                         {
-                            const float2 w1 = __ldg(tw + j * tw_stride);
+                            const float2 w1 = __ldg(tw + j);
                             float2 w = w1;
 #pragma unroll
                             for (int q = 1; q < R; q++)
@@ -225,7 +226,7 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
                     Bfly<R>::fwd(v);
                     if (m > 1)
                         {
-                            const float2 w1 = __ldg(tw + j * tw_stride);
+                            const float2 w1 = __ldg(tw + j);
                             float2 w = w1;
 #pragma unroll
                             for (int q = 1; q < R; q++)
@@ -262,7 +263,7 @@ __device__ __forceinline__ void fft_forward_smem(float2* s, const FftPlan& pl, c
     for (int st = 0; st < pl.n_stages; st++)
         {
             __syncthreads();
-            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw, st_sink);
+            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
             M /= pl.radix[st];
         }
     __syncthreads();
@@ -279,10 +280,10 @@ __device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, c
         {
             M *= pl.radix[st];
             __syncthreads();
-            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw, st_sink);
+            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
         }
     __syncthreads();
-    fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw, last);
+    fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw + pl.tw_off[0], last);
 }
 
 }  // namespace b200

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_fwd_kernel(const float2* _
     const int n = pl.n;
     const int d = blockIdx.x;
     const float2* w = wipe + static_cast<size_t>(d) * n;
+#pragma unroll 4
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         {
             // acquisition_core zero-pads beyond consumed samples (:657-664); volk_32fc_x2_multiply_32fc (:531)
@@ -295,10 +296,11 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* 
         {
             const float2* x = X + static_cast<size_t>(bin) * n;
             const float2* c = codes + static_cast<size_t>(slot) * n;
+#pragma unroll 4
             for (int i = threadIdx.x; i < n; i += blockDim.x)
                 {
                     // volk_32fc_x2_multiply_32fc (:538)
-                    const float2 a = x[i];
+                    const float2 a = __ldg(x + i);
                     const float2 b = __ldg(c + i);
                     s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
                 }
@@ -408,14 +410,21 @@ __global__ void acq_finish_second_peak_kernel(const float* __restrict__ second_p
     results[sp].test_statistics = __fdiv_rn(results[sp].grid_maximum, sec);  // (:517)
 }
 
-// twiddle table exp(-2 pi j k / n) in double, rounded once
-__global__ void acq_twiddle_kernel(float2* __restrict__ tw, int n)
+// per-stage compact twiddle tables exp(-2 pi j k / M_stage), k < m_stage, in double, rounded once
+__global__ void acq_twiddle_kernel(float2* __restrict__ tw, FftPlan pl)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    double s, c;
-    sincospi(-2.0 * static_cast<double>(k) / static_cast<double>(n), &s, &c);
-    tw[k] = make_float2(static_cast<float>(c), static_cast<float>(s));
+    int M = pl.n;
+    for (int st = 0; st < pl.n_stages; st++)
+        {
+            const int m = M / pl.radix[st];
+            for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x)
+                {
+                    double s, c;
+                    sincospi(-2.0 * static_cast<double>(k) / static_cast<double>(M), &s, &c);
+                    tw[pl.tw_off[st] + k] = make_float2(static_cast<float>(c), static_cast<float>(s));
+                }
+            M = m;
+        }
 }
 
 bool g_attr_done = false;
@@ -464,18 +473,21 @@ int acq_plan_make(int n, FftPlan* pl)
     if (k > kAcqMaxStages) return B200_ERR_RANGE;
     pl->n_stages = k;
     int M = n;
+    int off = 0;
     for (int st = 0; st < k; st++)
         {
             const int m = M / pl->radix[st];
             pl->mdiv[st] = (m <= 1) ? 0u : static_cast<unsigned int>((1ULL << 32) / static_cast<unsigned long long>(m)) + 1u;
+            pl->tw_off[st] = off;
+            off += m;   // sum of m over the stages < n
             M = m;
         }
     return B200_OK;
 }
 
-int acq_launch_twiddles(float2* tw, int n, cudaStream_t st)
+int acq_launch_twiddles(float2* tw, const FftPlan& pl, cudaStream_t st)
 {
-    acq_twiddle_kernel<<<(n + 255) / 256, 256, 0, st>>>(tw, n);
+    acq_twiddle_kernel<<<32, 256, 0, st>>>(tw, pl);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }

@@ -65,7 +65,7 @@ namespace b200
 struct FftPlan;
 struct AcqRowStat;
 int acq_plan_make(int n, FftPlan* pl);
-int acq_launch_twiddles(float2* tw, int n, cudaStream_t st);
+int acq_launch_twiddles(float2* tw, const FftPlan& pl, cudaStream_t st);
 int acq_launch_wipeoff(float2* wipe, int n, int bins, int doppler_max, int doppler_center, int doppler_step,
     int doppler_bias, long long fs_in, cudaStream_t st);
 int acq_launch_code_fft(const float2* code, int consumed, int layout, float2* out, const FftPlan& pl, const float2* tw, cudaStream_t st);

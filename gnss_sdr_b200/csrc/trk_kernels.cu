@@ -136,13 +136,6 @@ __device__ __forceinline__ float lds_f32(unsigned int addr)
     return v;
 }
 
-// per-item constants shared by the CTA (written by warp 0)
-struct ItemSetup
-{
-    float2 D, G, inc1;
-    int lo, hi;
-};
-
 struct ItemCtx
 {
     const float2* base;
@@ -253,7 +246,7 @@ __device__ __forceinline__ void correlate_range(const ItemCtx& cx, const float (
 // the scalar __fmul_rn (never contracted) and only the additions are packed.
 template <int TAPS, bool WRAPS>
 __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const float (&shifts)[TAPS], unsigned int tbl_off,
-    int tile_begin, int tile_end, int head, int npairs, float2 D, float2 G, float2 inc1, float2 (&acc)[TAPS])
+    int tile_begin, int tile_end, int head, float2 (&acc)[TAPS])
 {
     const int tid = threadIdx.x;
     float2 aux2[TAPS];
@@ -268,86 +261,27 @@ __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const fl
     for (int t = 0; t < TAPS; t++) are[t] = aim[t] = make_float2(0.f, 0.f);
 
     const float2 magic2 = make_float2(12582912.0f, 12582912.0f);
+    const float2 D = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile));
     const float2 Dr2 = make_float2(D.x, D.x), Di2 = make_float2(D.y, D.y);
+    // group-to-group phasor step: kTrkReseed tiles
+    const float2 G = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile * kTrkReseed));
     const float2 Gr2 = make_float2(G.x, G.x), Gi2 = make_float2(G.y, G.y);
 
     int n0 = head + tile_begin * kTrkTile + 2 * tid;
     float2 zr2, zi2;   // phasors of the two samples at the start of the current group
     {
         const float2 za = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0));
-        const float2 zb = cmulf(za, inc1);
+        const float2 zb = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0 + 1));
         zr2 = make_float2(za.x, zb.x);
         zi2 = make_float2(za.y, zb.y);
     }
     float nfa = static_cast<float>(n0), nfb = static_cast<float>(n0 + 1);
     const float2* ptr = cx.base + ((cx.s0 + static_cast<unsigned long long>(n0)) & cx.mask);
-    // tiles [tile_begin, full_end) are complete; a last partial tile is processed with invalid
-    // pairs zeroed (their chip index is evaluated at n = 0/1, always inside the table)
-    const int full_end = min(tile_end, npairs / kTrkThreads);
 
-    auto tile_body = [&](const float4 v, const float2 zr, const float2 zi, const float fa, const float fb) {
-        // w = x * z, scalar: the LDG.128 delivers (re,im,re,im), so packed operands would need
-        // 8 register moves per tile; scalar results land directly in register pairs
-        float2 wr2, wi2;
-        wr2.x = fmaf(v.x, zr.x, -v.y * zi.x);
-        wi2.x = fmaf(v.x, zi.x, v.y * zr.x);
-        wr2.y = fmaf(v.z, zr.y, -v.w * zi.y);
-        wi2.y = fmaf(v.z, zi.y, v.w * zr.y);
-        const float2 m2 = make_float2(__fmul_rn(cx.step, fa), __fmul_rn(cx.step, fb));
-#pragma unroll
-        for (int t = 0; t < TAPS; t++)
-            {
-                const float2 tt = __fadd2_rd(__fadd2_rn(m2, aux2[t]), magic2);
-                const float ca = lds_f32((__float_as_uint(tt.x) << 2) + tbl_off);
-                const float cb = lds_f32((__float_as_uint(tt.y) << 2) + tbl_off);
-                const float2 c2 = make_float2(ca, cb);
-                are[t] = __ffma2_rn(wr2, c2, are[t]);
-                aim[t] = __ffma2_rn(wi2, c2, aim[t]);
-            }
-    };
-
-#ifndef TRK_PREFETCH
-#define TRK_PREFETCH 0
-#endif
-#if TRK_PREFETCH > 0
-    // explicit register prefetch: TRK_PREFETCH tiles of IQ are always in flight per thread
-    float4 vbuf[TRK_PREFETCH];
-#pragma unroll
-    for (int u = 0; u < TRK_PREFETCH; u++)
+    for (int tg = tile_begin; tg < tile_end; tg += kTrkReseed)
         {
-            vbuf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tile_begin + u < full_end)
-                vbuf[u] = ldg_stream16(cx.base + ((cx.s0 + static_cast<unsigned long long>(n0 + u * kTrkTile)) & cx.mask));
-        }
-#endif
-    int tg = tile_begin;
-    for (; tg < full_end; tg += kTrkReseed)
-        {
-            const int tg_end = min(tg + kTrkReseed, full_end);
+            const int tg_end = min(tg + kTrkReseed, tile_end);
             float2 zr = zr2, zi = zi2;   // running phasors inside the group
-#if TRK_PREFETCH > 0
-            for (int tile = tg; tile < tg_end; tile += TRK_PREFETCH)
-                {
-#pragma unroll
-                    for (int u = 0; u < TRK_PREFETCH; u++)
-                        {
-                            if (tile + u < tg_end)
-                                {
-                                    const float4 v = vbuf[u];
-                                    if (tile + u + TRK_PREFETCH < full_end)
-                                        vbuf[u] = ldg_stream16(cx.base + ((cx.s0 + static_cast<unsigned long long>(n0 + TRK_PREFETCH * kTrkTile)) & cx.mask));
-                                    tile_body(v, zr, zi, nfa, nfb);
-                                    const float2 t1 = __fmul2_rn(zi, Di2);
-                                    const float2 nzr = __ffma2_rn(zr, Dr2, make_float2(-t1.x, -t1.y));
-                                    zi = __ffma2_rn(zr, Di2, __fmul2_rn(zi, Dr2));
-                                    zr = nzr;
-                                    nfa += static_cast<float>(kTrkTile);
-                                    nfb += static_cast<float>(kTrkTile);
-                                    n0 += kTrkTile;
-                                }
-                        }
-                }
-#else
 #pragma unroll 4
             for (int tile = tg; tile < tg_end; tile++)
                 {
@@ -356,7 +290,24 @@ __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const fl
                         v = ldg_stream16(cx.base + ((cx.s0 + static_cast<unsigned long long>(n0)) & cx.mask));
                     else
                         v = ldg_stream16(ptr);
-                    tile_body(v, zr, zi, nfa, nfb);
+                    // w = x * z, scalar: the LDG.128 delivers (re,im,re,im), so packed operands would
+                    // need 8 register moves per tile; scalar results land directly in register pairs
+                    float2 wr2, wi2;
+                    wr2.x = fmaf(v.x, zr.x, -v.y * zi.x);
+                    wi2.x = fmaf(v.x, zi.x, v.y * zr.x);
+                    wr2.y = fmaf(v.z, zr.y, -v.w * zi.y);
+                    wi2.y = fmaf(v.z, zi.y, v.w * zr.y);
+                    const float2 m2 = make_float2(__fmul_rn(cx.step, nfa), __fmul_rn(cx.step, nfb));
+#pragma unroll
+                    for (int t = 0; t < TAPS; t++)
+                        {
+                            const float2 tt = __fadd2_rd(__fadd2_rn(m2, aux2[t]), magic2);
+                            const float ca = lds_f32((__float_as_uint(tt.x) << 2) + tbl_off);
+                            const float cb = lds_f32((__float_as_uint(tt.y) << 2) + tbl_off);
+                            const float2 c2 = make_float2(ca, cb);
+                            are[t] = __ffma2_rn(wr2, c2, are[t]);
+                            aim[t] = __ffma2_rn(wi2, c2, aim[t]);
+                        }
                     // z *= D
                     const float2 t1 = __fmul2_rn(zi, Di2);
                     const float2 nzr = __ffma2_rn(zr, Dr2, make_float2(-t1.x, -t1.y));
@@ -367,29 +318,11 @@ __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const fl
                     n0 += kTrkTile;
                     ptr += kTrkTile;
                 }
-#endif
-            if (tg_end - tg == kTrkReseed)
-                {
-                    // group seed advances by G (few steps per epoch: error stays ~1e-7 per step)
-                    const float2 t2 = __fmul2_rn(zi2, Gi2);
-                    const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
-                    zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
-                    zr2 = ngr;
-                }
-            else
-                {
-                    zr2 = zr;   // partial group: carry the running phasor on
-                    zi2 = zi;
-                }
-        }
-    if (full_end < tile_end)
-        {
-            // the single partial tile (only the slice that owns it gets here)
-            const int pair = full_end * kTrkThreads + tid;
-            const bool valid = pair < npairs;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) v = ldg_stream16(cx.base + ((cx.s0 + static_cast<unsigned long long>(n0)) & cx.mask));
-            tile_body(v, zr2, zi2, valid ? nfa : 0.0f, valid ? nfb : 1.0f);
+            // group seed advances by G (few steps per epoch: error stays ~1e-7 per step)
+            const float2 t2 = __fmul2_rn(zi2, Gi2);
+            const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
+            zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
+            zr2 = ngr;
         }
 #pragma unroll
     for (int t = 0; t < TAPS; t++)
@@ -447,7 +380,7 @@ __device__ __forceinline__ void correlate_range_hd(const ItemCtx& cx, float rate
 
 template <int TAPS>
 __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const BandDesc& bd, float* smem_tbl,
-    int tbl_cap, float2* smem_red, ItemSetup* smem_setup, int slice, int slices, float2 (&result)[TAPS])
+    int tbl_cap, float2* smem_red, int slice, int slices, float2 (&result)[TAPS])
 {
     const int tid = threadIdx.x;
     ItemCtx cx;
@@ -487,55 +420,42 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
         }
     else
         {
-            // ---- per-item constants ---------------------------------------------------------------------
-            // Chip-index range of the epoch: the index is monotone in n within each association, so the
-            // epoch ends bound it (every thread evaluates it: ~60 instructions, no barrier needed).
-            const int head = static_cast<int>(cx.s0 & 1ULL);
+            // index range over the epoch (monotone in n within each association)
             long long lo = 0x7fffffff, hi = -0x7fffffff - 1LL;
-            {
-                const float nl_avx = static_cast<float>(max(cx.body - 1, 0));
-                const float n_last = static_cast<float>(max(cx.N - 1, 0));
-                const float n_body = static_cast<float>(cx.body);
+            const float nl_avx = static_cast<float>(max(cx.body - 1, 0));
+            const float n_last = static_cast<float>(max(cx.N - 1, 0));
+            const float n_body = static_cast<float>(cx.body);
 #pragma unroll
-                for (int t = 0; t < TAPS; t++)
-                    {
-                        const float a2 = __fsub_rn(shifts[t], cx.rem);
-                        int v[6];
-                        v[0] = chip_index_avx(cx.step, 0.f, a2);
-                        v[1] = chip_index_avx(cx.step, nl_avx, a2);
-                        v[2] = chip_index_generic(cx.step, n_body, shifts[t], cx.rem);
-                        v[3] = chip_index_generic(cx.step, n_last, shifts[t], cx.rem);
-                        v[4] = chip_index_generic(cx.step, 0.f, shifts[t], cx.rem);  // epochs shorter than 8 samples
-                        v[5] = chip_index_avx(cx.step, 1.f, a2);                     // masked pairs of the tail tile
-#pragma unroll
-                        for (int q = 0; q < 6; q++)
-                            {
-                                lo = min(lo, static_cast<long long>(v[q]));
-                                hi = max(hi, static_cast<long long>(v[q]));
-                            }
-                    }
-            }
-            // The three phasor constants (tile step D, group step G, one-sample step inc1) cost a
-            // sincospi each: lanes 16..18 of warp 0 compute one each in a single non-divergent pass
-            // and publish them before the barrier that follows the table fill.
-            if (tid >= 16 && tid < 19)
+            for (int t = 0; t < TAPS; t++)
                 {
-                    const unsigned long long mult = (tid == 16) ? static_cast<unsigned long long>(kTrkTile)
-                                                                : (tid == 17 ? static_cast<unsigned long long>(kTrkTile * kTrkReseed) : 1ULL);
-                    const float2 ph = phasor_from_turns(cx.DT * mult);
-                    float2* dst = (tid == 16) ? &smem_setup->D : (tid == 17 ? &smem_setup->G : &smem_setup->inc1);
-                    *dst = ph;
+                    const float a2 = __fsub_rn(shifts[t], cx.rem);
+                    int v[4];
+                    v[0] = chip_index_avx(cx.step, 0.f, a2);
+                    v[1] = chip_index_avx(cx.step, nl_avx, a2);
+                    v[2] = chip_index_generic(cx.step, n_body, shifts[t], cx.rem);
+                    v[3] = chip_index_generic(cx.step, n_last, shifts[t], cx.rem);
+                    // association 0 also evaluated at n = 0 (epochs shorter than 8 samples)
+                    const int v4 = chip_index_generic(cx.step, 0.f, shifts[t], cx.rem);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        {
+                            lo = min(lo, static_cast<long long>(v[q]));
+                            hi = max(hi, static_cast<long long>(v[q]));
+                        }
+                    lo = min(lo, static_cast<long long>(v4));
+                    hi = max(hi, static_cast<long long>(v4));
                 }
             const long long tbl_base = lo - 2;
             const long long span = hi - lo + 5;
-            const bool fits = span <= static_cast<long long>(tbl_cap);
-            const bool fast = fits && lo > -4000000LL && hi < 4000000LL;
 
-            // sample pairs (n, n+1) with both samples below `body`, starting at an even band offset
-            const int npairs = (cx.body > head) ? (cx.body - head) / 2 : 0;
+            const int head = static_cast<int>(cx.s0 & 1ULL);
+            const int ntiles = (cx.body > head) ? (cx.body - head) / kTrkTile : 0;
+            const int n_main_end = head + ntiles * kTrkTile;
+            const int tb = static_cast<int>((static_cast<long long>(ntiles) * slice) / slices);
+            const int te = static_cast<int>((static_cast<long long>(ntiles) * (slice + 1)) / slices);
             const bool rem_here = (slice == slices - 1);
 
-            if (fits)
+            if (span <= static_cast<long long>(tbl_cap))
                 {
                     const int base_i = static_cast<int>(tbl_base);
                     int r = mod_pos(base_i + tid, L);
@@ -546,54 +466,41 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
                             r += stride;
                             if (r >= L) r -= L;
                         }
-                }
-            else if (L <= tbl_cap)
-                {
-                    for (int j = tid; j < L; j += kTrkThreads) smem_tbl[j] = ch.code[j];
-                }
-            __syncthreads();
-
-            if (fast)
-                {
-                    const int base_i = static_cast<int>(tbl_base);
-                    const int ntiles = (npairs + kTrkThreads - 1) / kTrkThreads;   // last one may be partial
-                    const int tb = static_cast<int>((static_cast<long long>(ntiles) * slice) / slices);
-                    const int te = static_cast<int>((static_cast<long long>(ntiles) * (slice + 1)) / slices);
-                    const int n_main_end = head + 2 * npairs;
-                    // computed inside an asm so the optimiser cannot split the constant back out of
-                    // the per-lookup LEA
-                    unsigned int tbl_off;
-                    asm("sub.u32 %0, %1, %2;"
-                        : "=r"(tbl_off)
-                        : "r"(static_cast<unsigned int>(__cvta_generic_to_shared(smem_tbl))),
-                          "r"(4u * (static_cast<unsigned int>(base_i) + 0x4B400000u)));
-                    const float2 D = smem_setup->D, G = smem_setup->G, inc1 = smem_setup->inc1;
-                    // ring wrap inside the epoch? (uniform per item)
-                    const bool wraps = ((cx.s0 & cx.mask) + static_cast<unsigned long long>(cx.N)) > cx.mask;
-                    if (wraps)
-                        correlate_tiles_fast<TAPS, true>(cx, shifts, tbl_off, tb, te, head, npairs, D, G, inc1, acc);
-                    else
-                        correlate_tiles_fast<TAPS, false>(cx, shifts, tbl_off, tb, te, head, npairs, D, G, inc1, acc);
-                    // the few samples outside the pair grid (head sample, n >= 8*(N/8) tail)
+                    __syncthreads();
                     LookupExt lut{smem_tbl - base_i};
-                    correlate_range<TAPS>(cx, shifts, lut, 0, 0, head, rem_here, n_main_end, acc);
+                    if (lo > -4000000LL && hi < 4000000LL)
+                        {
+                            // computed inside an asm so the optimiser cannot split the constant back out of
+                            // the per-lookup LEA
+                            unsigned int tbl_off;
+                            asm("sub.u32 %0, %1, %2;"
+                                : "=r"(tbl_off)
+                                : "r"(static_cast<unsigned int>(__cvta_generic_to_shared(smem_tbl))),
+                                  "r"(4u * (static_cast<unsigned int>(base_i) + 0x4B400000u)));
+                            // ring wrap inside the epoch? (uniform per item)
+                            const bool wraps = ((cx.s0 & cx.mask) + static_cast<unsigned long long>(cx.N)) > cx.mask;
+                            if (wraps)
+                                correlate_tiles_fast<TAPS, true>(cx, shifts, tbl_off, tb, te, head, acc);
+                            else
+                                correlate_tiles_fast<TAPS, false>(cx, shifts, tbl_off, tb, te, head, acc);
+                            // remainder samples only (no main tiles) through the scalar path
+                            correlate_range<TAPS>(cx, shifts, lut, 0, 0, head, rem_here, n_main_end, acc);
+                        }
+                    else
+                        {
+                            correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                        }
                 }
             else
                 {
-                    const int ntiles = npairs / kTrkThreads;   // full tiles only on the scalar paths
-                    const int tb = static_cast<int>((static_cast<long long>(ntiles) * slice) / slices);
-                    const int te = static_cast<int>((static_cast<long long>(ntiles) * (slice + 1)) / slices);
-                    const int n_main_end = head + ntiles * kTrkTile;
-                    if (fits)
+                    const bool in_smem = L <= tbl_cap;
+                    if (in_smem)
                         {
-                            LookupExt lut{smem_tbl - static_cast<int>(tbl_base)};
-                            correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                            for (int j = tid; j < L; j += kTrkThreads) smem_tbl[j] = ch.code[j];
                         }
-                    else
-                        {
-                            LookupMod lut{(L <= tbl_cap) ? smem_tbl : ch.code, L};
-                            correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
-                        }
+                    __syncthreads();
+                    LookupMod lut{in_smem ? smem_tbl : ch.code, L};
+                    correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
                 }
         }
 
@@ -636,7 +543,7 @@ __device__ __forceinline__ void run_item(const b200_trk_item& it, const ChanDesc
     float2* out, int out_stride, float2* partial, unsigned int* counters)
 {
     float2 result[TAPS];
-    process_item<TAPS>(it, ch, bd, smem_tbl, tbl_cap, smem_red, reinterpret_cast<ItemSetup*>(smem_flag + 2), slice, slices, result);
+    process_item<TAPS>(it, ch, bd, smem_tbl, tbl_cap, smem_red, slice, slices, result);
     const int tid = threadIdx.x;
     if (slices == 1)
         {
@@ -675,11 +582,8 @@ __device__ __forceinline__ void run_item(const b200_trk_item& it, const ChanDesc
 
 // TAPS_T > 0: every channel in the launch has exactly TAPS_T taps (specialised registers).
 // TAPS_T == 0: taps read per item.
-#ifndef TRK_MINB
-#define TRK_MINB 4
-#endif
 template <int TAPS_T>
-__global__ void __launch_bounds__(kTrkThreads, (TAPS_T == 1 || TAPS_T == 3) ? TRK_MINB : (TAPS_T == 5 ? 3 : 2)) trk_correlate_kernel(const b200_trk_item* __restrict__ items, int n_items,
+__global__ void __launch_bounds__(kTrkThreads) trk_correlate_kernel(const b200_trk_item* __restrict__ items, int n_items,
     const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, float2* __restrict__ out, int out_stride,
     int slices, float2* partial, unsigned int* counters, int tbl_cap)
 {
@@ -756,7 +660,7 @@ int launch_trk_batch(const b200_trk_item* items, int n_items, const ChanDesc* ch
     const int cap_limit = (200 * 1024 - 1024) / 4;
     if (tbl_cap > cap_limit) tbl_cap = cap_limit;
     tbl_cap = (tbl_cap + 3) & ~3;
-    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kTrkThreads / 32) * B200_MAX_TAPS * sizeof(float2) + 16 + 64;
+    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kTrkThreads / 32) * B200_MAX_TAPS * sizeof(float2) + 16;
     switch (taps_uniform)
         {
         case 1: return launch_one<1>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
