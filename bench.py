@@ -178,7 +178,7 @@ def acq_rows_bytes_flops():
     return bins, rows, rows * 16 * ACQ_N, rows * ACQ_N * (16 + 10 * math.log2(ACQ_N))
 
 
-def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu):
+def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0, world=1):
     import oracle
     from gnss_synth import make_iq
     bins, rows, abytes, aflops = acq_rows_bytes_flops()
@@ -193,22 +193,51 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu):
     assert acq.conf.num_doppler_bins == bins
     for p in range(1, ACQ_PRNS + 1):
         acq.set_local_code(p - 1, oracle.port.gps_ca_code_complex_sampled(p, ACQ_FS))
-    slots = np.arange(ACQ_PRNS, dtype=np.uint32)
+    # multi-GPU: the PRN x Doppler grid is sharded by PRN; the only exchange is the peak all-reduce
+    from gnss_sdr_b200 import dist as bd
+    my_slots = np.array(bd.shard_round_robin(ACQ_PRNS, world, rank), dtype=np.uint32)
+    slots = my_slots
     iq_dev = torch.from_numpy(iq.view(np.float32)).to(dev)
-    res_dev = torch.zeros(ACQ_PRNS * capi.ACQ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    for _ in range(warmup):
+    res_dev = torch.zeros(len(my_slots) * capi.ACQ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    prn_dev = torch.from_numpy((my_slots + 1).astype(np.int64)).to(dev)
+
+    def sweep():
         acq.search_dev(iq_dev.data_ptr(), slots, res_dev.data_ptr())
+        if world > 1:
+            # packed key (statistic bits | prn | doppler bin | code phase), MAX all-reduce over NVLink
+            r = res_dev.view(torch.int32).view(-1, 7).to(torch.int64)
+            key = ((r[:, 3] & 0xFFFFFFFF) << 32) | (prn_dev << 24) | (r[:, 1] << 15) | r[:, 0]
+            best = key.max().reshape(1)
+            dist.all_reduce(best, op=dist.ReduceOp.MAX)
+            return best
+        return None
+
+    for _ in range(warmup):
+        sweep()
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        acq.search_dev(iq_dev.data_ptr(), slots, res_dev.data_ptr())
+        best = sweep()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if dist is not None:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
     launches = eng.launch_count() - l0
-    res = np.frombuffer(res_dev.cpu().numpy().tobytes(), capi.ACQ_RESULT_DTYPE)
+    res_local = np.frombuffer(res_dev.cpu().numpy().tobytes(), capi.ACQ_RESULT_DTYPE)
+    if world > 1:
+        res = bd.gather_results(res_local, [int(x) for x in my_slots], ACQ_PRNS, device=dev)
+        _, bprn, bd_bin, bt = bd.unpack_peak_key(best.cpu().numpy())
+        w = int(np.argmax(res["test_statistics"]))
+        assert int(bprn[0]) == w + 1 and int(bt[0]) == int(res["index_time"][w]), "all-reduced peak != gathered table"
+    else:
+        res = res_local
     from oracle.acq_np import compute_threshold
     th = compute_threshold(0.001, ACQ_N, bins, 1)
     detected = sorted(int(p) for p in range(1, ACQ_PRNS + 1) if res[p - 1]["test_statistics"] > th)
@@ -217,6 +246,10 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu):
     for _ in range(steps):
         r2 = acq.search(iq, slots)
     dt = (time.perf_counter() - t0) / steps
+    if dist is not None:
+        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        dt = float(tdt.item())
     peak, peak_src = measured_peak_gbs()
     out = {"metric": "acquisitions/s over Doppler grid", "unit": "acquisitions/s",
            "config": {"workload": f"C4: GPS L1 C/A PCPS, {ACQ_PRNS} PRNs x {bins} Doppler bins x N={ACQ_N} (25 Msps, 1 ms), CFAR statistic, "
@@ -232,7 +265,8 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu):
                         "note": "16N bytes per (PRN,bin) row (SURVEY 8d); operands are L2-resident, the kernel is "
                                 "shared-memory/FP32 bound, see DESIGN.md"},
            "detected_prns": detected, "present_prns": present,
-           "e2e_matches_dev": bool(np.array_equal(r2["index_time"], res["index_time"]))}
+           "e2e_matches_dev": bool(np.array_equal(r2["index_time"], res_local["index_time"])),
+           "n_gpus": world, "sharding": "PRNs round-robin over ranks; one 8-byte MAX all-reduce of the packed peak key per sweep" if world > 1 else "single GPU"}
     if with_cpu:
         out["cpu_baseline"] = cpu_baseline_acq(iq)
     acq.close()
@@ -456,10 +490,13 @@ def main():
         e2e["max_rel_diff_vs_value_run"] = float(np.max(np.abs(res - taps)) / np.max(np.abs(taps)))
 
     acq = None
-    if not args.no_acq and rank == 0:
+    if not args.no_acq:
         try:
-            acq = bench_acq(torch, capi, eng, dev, max(5, min(args.steps, 50)), 3, with_cpu=(world == 1 and not args.no_cpu_baseline))
+            acq = bench_acq(torch, capi, eng, dev, max(5, min(args.steps, 50)), 3, with_cpu=(world == 1 and not args.no_cpu_baseline),
+                            dist=dist, rank=rank, world=world)
         except Exception as ex:  # the headline metric must still be reported
+            if world > 1:
+                raise
             acq = {"error": repr(ex)}
 
     if rank != 0:

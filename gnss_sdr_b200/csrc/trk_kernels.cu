@@ -47,6 +47,14 @@ __device__ __forceinline__ int chip_index_hd(float step, float rate, unsigned in
     return __float2int_rd(__fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(step, nf), __fmul_rn(rate, n2)), shift0), rem));
 }
 
+// high-dynamics, a_avx/u_avx association (same file :460-466): n*n is a FLOAT product here
+// floor(fl(fl(fl(step*n) + fl(rate*fl(n*n))) + fl(shift0 - rem)))
+__device__ __forceinline__ int chip_index_hd_avx(float step, float rate, float nf, float aux2)
+{
+    const float nn = __fmul_rn(nf, nf);
+    return __float2int_rd(__fadd_rn(__fadd_rn(__fmul_rn(step, nf), __fmul_rn(rate, nn)), aux2));
+}
+
 __device__ __forceinline__ int mod_pos(int k, int L)
 {
     int r = k % L;
@@ -370,7 +378,10 @@ __device__ __forceinline__ void correlate_range_hd(const ItemCtx& cx, float rate
                 {
                     unsigned int m = static_cast<unsigned int>(n) + static_cast<unsigned int>(shift_samples[t]);
                     if (m >= static_cast<unsigned int>(cx.N)) m -= static_cast<unsigned int>(cx.N);
-                    const int idx = chip_index_hd(cx.step, rate, m, shifts[0], cx.rem);
+                    // samples below 8*(N/8) follow the AVX kernel's association, the tail the generic one
+                    const int idx = (m < static_cast<unsigned int>(cx.body))
+                                        ? chip_index_hd_avx(cx.step, rate, static_cast<float>(m), __fsub_rn(shifts[0], cx.rem))
+                                        : chip_index_hd(cx.step, rate, m, shifts[0], cx.rem);
                     const float c = lut(idx);
                     acc[t].x = fmaf(wr, c, acc[t].x);
                     acc[t].y = fmaf(wi, c, acc[t].y);

@@ -74,6 +74,16 @@ class _Port:
                                        _fp(shifts), C.c_uint(len(code)), C.c_int(taps), C.c_uint(n))
         return out
 
+    def hd_resampler_avx(self, code, rem, step, rate, shifts, n, return_idx=False):
+        code = _f32(code)
+        shifts = _f32(shifts)
+        taps = len(shifts)
+        out = np.empty((taps, n), np.float32)
+        idx = np.empty(n, np.int32)
+        self.lib.port_hd_resampler_avx_32f(_fp(out), idx.ctypes.data_as(c_int_p), _fp(code), C.c_float(rem), C.c_float(step),
+                                           C.c_float(rate), _fp(shifts), C.c_uint(len(code)), C.c_int(taps), C.c_uint(n))
+        return (out, idx) if return_idx else out
+
     def _rot(self, fn, iq, phase_inc, phase, codes):
         iq = _c64(iq)
         codes = _f32(codes)

@@ -109,6 +109,56 @@ int port_hd_resampler_32f(float* out, const float* code, float rem, float step, 
     return 0;
 }
 
+/* a4  high-dynamics resampler with the a_avx / u_avx association (same file :433-513):
+ *   aux = fl(fl(step*n) + fl(rate*fl(n*n))) ; aux = fl(aux + fl(shift0 - rem)) ; floor
+ * with n*n a FLOAT product (no uint32 wrap, unlike the generic kernel), the "+1 then truncate"
+ * negative-index correction (:463-468), scalar generic tail for n >= 8*(N/8), then the same
+ * circular sample shifts for taps > 0.  idx_out (optional): tap-0 chip indices. */
+int port_hd_resampler_avx_32f(float* out, int* idx_out, const float* code, float rem, float step, float rate,
+    const float* shifts, unsigned int L, int taps, unsigned int n)
+{
+    const unsigned int body = (n / 8) * 8;
+    const float Lf = (float)L;
+    const float aux2 = shifts[0] - rem;
+    float nf = 0.0f;
+    for (unsigned int k = 0; k < body; k++)
+        {
+            float aux = step * nf;
+            const float nn = nf * nf;
+            const float aux3 = rate * nn;
+            aux = aux + aux3;
+            aux = aux + aux2;
+            aux = floorf(aux);
+            float c = aux / Lf;
+            const float c1 = c + 1.0f;
+            const int i = (int)c1;
+            const float base = (float)i * Lf;
+            int idx = (int)(aux - base);
+            c = (float)idx;
+            if (c < 0.0f) c = c + Lf;
+            idx = (int)c;
+            out[k] = code[idx];
+            if (idx_out) idx_out[k] = idx;
+            nf += 1.0f;
+        }
+    for (unsigned int k = body; k < n; k++)
+        {
+            int idx = (int)floor(step * (float)k + rate * (float)(k * k) + shifts[0] - rem);
+            if (idx < 0) idx += (int)L * (abs(idx) / L + 1);
+            idx = idx % L;
+            out[k] = code[idx];
+            if (idx_out) idx_out[k] = idx;
+        }
+    unsigned int shift_samples = 0;
+    for (int t = 1; t < taps; t++)
+        {
+            shift_samples += (int)round((shifts[t] - shifts[t - 1]) / step);
+            memcpy(&out[(size_t)t * n], &out[shift_samples], (n - shift_samples) * sizeof(float));
+            memcpy(&out[(size_t)t * n + n - shift_samples], &out[0], shift_samples * sizeof(float));
+        }
+    return 0;
+}
+
 /* complex helpers with the exact operation order of C99 `a * b` (no FMA: -ffp-contract=off) */
 static inline cf32 cmul(cf32 a, cf32 b)
 {

@@ -118,6 +118,20 @@ def test_hd_resampler_bitexact(oracle, ref):
         assert np.array_equal(_bits(a), _bits(b))
 
 
+@pytest.mark.parametrize("variant", ["a_avx", "u_avx"])
+def test_hd_resampler_avx_bitexact(oracle, ref, variant):
+    rng = np.random.default_rng(15)
+    for n, L, shifts, step, rate in [(8111, 2046, [-0.1, 0.0, 0.1], (2046 + 0.1) / 8111, 1e-9),
+                                     (25000, 1023, [-0.5, 0, 0.5], 0.04092, 3e-12),
+                                     (25003, 1023, [-0.5, 0, 0.5], 0.04092, -3e-12),
+                                     (200000, 8184, [-1.2, -0.3, 0, 0.3, 1.2], 0.04092, 1e-13),
+                                     (4000, 1023, [-0.5, 0, 0.5], 0.25575, 2e-10)]:
+        code = rng.standard_normal(L).astype(np.float32)
+        a = oracle.port.hd_resampler_avx(code, 0.37, step, rate, shifts, n)
+        b = ref.hd_resampler(variant, code, 0.37, step, rate, shifts, n)
+        assert np.array_equal(_bits(a), _bits(b)), (variant, n)
+
+
 def test_hd_rotator_bitexact(oracle, ref):
     rng = np.random.default_rng(6)
     n, taps = 3000, 3

@@ -303,3 +303,66 @@ def test_error_paths(capi, engine):
     out = mc.Carrier_wipeoff_multicorrelator_resampler(np.zeros(0, np.complex64), 0, 0, 0, 0, 0.1, 0, 0)
     assert np.all(out == 0)
     mc.free()
+
+
+# ---- high-dynamics variants (a4) ----------------------------------------------------------------------
+@pytest.mark.parametrize("n,L,shifts,step,rate", [
+    (25000, 1023, [-0.5, 0.0, 0.5], 0.04092, 3e-12),
+    (25003, 1023, [-0.5, 0.0, 0.5], 0.04092, -3e-12),
+    (8111, 2046, [-0.1, 0.0, 0.1], (2046 + 0.1) / 8111, 1e-9),
+    (4000, 1023, [-0.5, 0.0, 0.5], 0.25575, 2e-10),
+    (200000, 8184, [-1.2, -0.3, 0.0, 0.3, 1.2], 0.04092, 1e-13),
+])
+def test_high_dynamics_resampler_integer_exact(capi, engine, oracle, n, L, shifts, step, rate):
+    """high_dyn=true: quadratic code phase on tap 0 with the a_avx association, other taps are
+    circular sample shifts of tap 0 (VG ..._high_dynamics_resampler_32f_xn.h:433-513).  Integer data
+    and zero carrier make the expected taps exact integers."""
+    rng = np.random.default_rng(n)
+    x_int = rng.integers(-7, 8, n)
+    x_int[x_int == 0] = 1
+    code_int = ((np.arange(L) * 7919) % 31) - 15
+    code_int[code_int == 0] = 16
+    rem = 0.37
+    resampled = oracle.port.hd_resampler_avx(code_int.astype(np.float32), rem, step, rate, shifts, n)
+    want = (resampled.astype(np.int64) * x_int[None, :]).sum(axis=1)
+    mc = capi.Multicorrelator(engine, n, len(shifts))
+    mc.set_high_dynamics_resampler(True)
+    mc.set_local_code_and_taps(code_int.astype(np.float32), shifts)
+    got = mc.Carrier_wipeoff_multicorrelator_resampler(x_int.astype(np.complex64), 0.0, 0.0, 0.0, rem, step, rate)
+    mc.free()
+    assert np.array_equal(got.real.astype(np.int64), want)
+    assert np.all(got.imag == 0)
+
+
+def test_high_dynamics_rotator_parity(capi, engine, oracle):
+    """high_dyn=true with a carrier phase rate: against the reference class
+    (HD resampler + volk_gnsssdr_32fc_32f_high_dynamic_rotator_dot_prod_32fc_xn_generic, whose
+    cpowf-based phase is itself only float-accurate) within 1e-3, and against a float64 evaluation of
+    the same phase law (rate term lagging one sample, ..._high_dynamic_rotator...h:92-103) within 2e-5."""
+    n, L = 25000, 1023
+    rng = np.random.default_rng(77)
+    code = oracle.port.gps_ca_code(9)
+    shifts = np.array([-0.5, 0.0, 0.5], np.float32)
+    step, crate = np.float32(0.04092), np.float32(2e-12)
+    rem_code, rem_carr, dphi, drate = np.float32(0.3), np.float32(0.7), np.float32(1.1e-3), np.float32(2e-9)
+    k = np.arange(n)
+    resampled = oracle.port.hd_resampler_avx(code, float(rem_code), float(step), float(crate), shifts, n)
+    e = np.where(k >= 1, (k - 1.0) ** 2, 0.0)
+    ph = -(float(rem_carr) + k * float(dphi) + e * float(drate))
+    iq = (0.05 * resampled[1] * np.exp(-1j * ph) + rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    truth = (resampled.astype(np.float64) * (iq.astype(np.complex128) * np.exp(1j * ph))[None, :]).sum(axis=1)
+    mc = capi.Multicorrelator(engine, n, 3)
+    mc.set_high_dynamics_resampler(True)
+    mc.set_local_code_and_taps(code, shifts)
+    got = mc.Carrier_wipeoff_multicorrelator_resampler(iq, float(rem_carr), float(dphi), float(drate), float(rem_code),
+                                                       float(step), float(crate))
+    mc.free()
+    assert np.abs(truth[1]) > 5 * np.sqrt(n)
+    assert np.max(np.abs(got - truth)) / np.abs(truth[1]) < 2e-5
+    if oracle.ref is not None:
+        oracle.ref.select_arch("a_avx")
+        h = oracle.ref.mc_create(n, 3, high_dyn=True)
+        oracle.ref.mc_set_code(h, code, shifts)
+        want = oracle.ref.mc_correlate(h, iq, 3, float(rem_carr), float(dphi), float(drate), float(rem_code), float(step), float(crate))
+        oracle.ref.mc_destroy(h)
+        assert np.all(np.abs(got - want) / np.abs(want) < 1e-3)
