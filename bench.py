@@ -512,8 +512,10 @@ def main():
                 "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "algorithmic_bytes_per_launch": ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE,
                 "launch_ms": launch_ms, "peak_source": peak_src,
-                "note": "algorithmic bytes = 8 B per channel-sample (SURVEY 8d); the 32 channels share one IQ stream, "
-                        "so DRAM traffic is ~1/32 of that and the kernel is issue-bound, see DESIGN.md"}
+                "note": "algorithmic bytes = 8 B per channel-sample (SURVEY 8d); the 32 channels share one IQ stream, so DRAM "
+                        "traffic (the `traffic` field, from ncu) is ~1/32 of that: the stream is read from HBM once and the "
+                        "algorithmic bytes are served L2->SM at ~6.7-6.9 TB/s (ncu l1tex__m_xbar2l1tex_read_bytes = 6.43 GB per "
+                        "launch), the chip's L2 fabric cap; frac > 1 against the HBM copy peak is therefore possible, see DESIGN.md"}
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_baseline()
