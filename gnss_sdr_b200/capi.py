@@ -65,6 +65,8 @@ _SIGS = {
     "b200_trk_channel_set_code": ([_vp, C.c_int, C.c_int, _vp, _vp, C.c_int], C.c_int),
     "b200_trk_batch": ([_vp, _vp, C.c_int, _vp, C.c_int], C.c_int),
     "b200_trk_batch_dev": ([_vp, _vp, C.c_int, _vp, C.c_int, C.c_int], C.c_int),
+    "b200_trk_submit": ([_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_uint64)], C.c_int),
+    "b200_trk_wait": ([_vp, C.c_uint64, _vp], C.c_int),
 }
 
 
@@ -190,6 +192,18 @@ class Engine:
         items = np.ascontiguousarray(items, TRK_ITEM_DTYPE)
         out = np.zeros((items.size, out_stride), np.complex64)
         _chk(lib.b200_trk_batch(self.h, items.ctypes.data, items.size, out.ctypes.data, out_stride), "b200_trk_batch")
+        return out
+
+    def trk_submit(self, items: np.ndarray, out_stride: int) -> tuple:
+        items = np.ascontiguousarray(items, TRK_ITEM_DTYPE)
+        t = C.c_uint64(0)
+        _chk(lib.b200_trk_submit(self.h, items.ctypes.data, items.size, out_stride, C.byref(t)), "b200_trk_submit")
+        return (t.value, items.size, out_stride)
+
+    def trk_wait(self, ticket: tuple) -> np.ndarray:
+        t, n, stride = ticket
+        out = np.zeros((n, stride), np.complex64)
+        _chk(lib.b200_trk_wait(self.h, t, out.ctypes.data), "b200_trk_wait")
         return out
 
     def trk_batch_dev(self, items_dev_ptr: int, n_items: int, out_dev_ptr: int, out_stride: int, slices: int = 1):

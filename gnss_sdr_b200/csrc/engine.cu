@@ -183,6 +183,14 @@ extern "C"
         if (e->out_pin) cudaFreeHost(e->out_pin);
         if (e->partial) cudaFree(e->partial);
         if (e->counters) cudaFree(e->counters);
+        for (auto& sl : e->slots)
+            {
+                if (sl.items_dev) cudaFree(sl.items_dev);
+                if (sl.items_pin) cudaFreeHost(sl.items_pin);
+                if (sl.out_dev) cudaFree(sl.out_dev);
+                if (sl.out_pin) cudaFreeHost(sl.out_pin);
+                if (sl.done) cudaEventDestroy(sl.done);
+            }
         cudaEventDestroy(e->copy_done);
         cudaEventDestroy(e->t0);
         cudaEventDestroy(e->t1);
@@ -377,10 +385,10 @@ extern "C"
         return rc;
     }
 
-    int b200_trk_batch(b200_engine* e, const b200_trk_item* items_host, int n_items, b200_cf32* out_host, int out_stride)
+    int b200_trk_submit(b200_engine* e, const b200_trk_item* items_host, int n_items, int out_stride, uint64_t* ticket)
     {
-        if (!e || n_items < 0 || (n_items && (!items_host || !out_host)) || out_stride < 1) return B200_ERR_ARG;
-        if (n_items == 0) return B200_OK;
+        if (!e || !ticket || n_items < 1 || !items_host || out_stride < 1) return B200_ERR_ARG;
+        b200_engine::Slot* sl = nullptr;
         {
             std::lock_guard<std::mutex> lk(e->mu);
             B200_CUDA_TRY(cudaSetDevice(e->device));
@@ -398,39 +406,88 @@ extern "C"
                             return B200_ERR_ARG;
                         }
                 }
-            if (n_items > e->batch_cap)
+            for (auto& s : e->slots)
+                if (!s.busy)
+                    {
+                        sl = &s;
+                        break;
+                    }
+            if (!sl)
                 {
-                    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
-                    if (e->items_dev) B200_CUDA_TRY(cudaFree(e->items_dev));
-                    if (e->items_pin) B200_CUDA_TRY(cudaFreeHost(e->items_pin));
-                    e->batch_cap = n_items + n_items / 2 + 64;
-                    B200_CUDA_TRY(cudaMalloc(&e->items_dev, sizeof(b200_trk_item) * e->batch_cap));
-                    B200_CUDA_TRY(cudaMallocHost(&e->items_pin, sizeof(b200_trk_item) * e->batch_cap));
+                    set_error("more than %d batches in flight: call b200_trk_wait", b200_engine::kSlots);
+                    return B200_ERR_STATE;
+                }
+            if (!sl->done) B200_CUDA_TRY(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
+            if (n_items > sl->items_cap)
+                {
+                    if (sl->items_dev) B200_CUDA_TRY(cudaFree(sl->items_dev));
+                    if (sl->items_pin) B200_CUDA_TRY(cudaFreeHost(sl->items_pin));
+                    sl->items_cap = n_items + n_items / 2 + 64;
+                    B200_CUDA_TRY(cudaMalloc(&sl->items_dev, sizeof(b200_trk_item) * sl->items_cap));
+                    B200_CUDA_TRY(cudaMallocHost(&sl->items_pin, sizeof(b200_trk_item) * sl->items_cap));
                 }
             const int out_elems = n_items * out_stride;
-            if (out_elems > e->out_cap)
+            if (out_elems > sl->out_cap)
                 {
-                    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
-                    if (e->out_dev) B200_CUDA_TRY(cudaFree(e->out_dev));
-                    if (e->out_pin) B200_CUDA_TRY(cudaFreeHost(e->out_pin));
-                    e->out_cap = out_elems + out_elems / 2 + 64;
-                    B200_CUDA_TRY(cudaMalloc(&e->out_dev, sizeof(float2) * e->out_cap));
-                    B200_CUDA_TRY(cudaMallocHost(&e->out_pin, sizeof(float2) * e->out_cap));
+                    if (sl->out_dev) B200_CUDA_TRY(cudaFree(sl->out_dev));
+                    if (sl->out_pin) B200_CUDA_TRY(cudaFreeHost(sl->out_pin));
+                    sl->out_cap = out_elems + out_elems / 2 + 64;
+                    B200_CUDA_TRY(cudaMalloc(&sl->out_dev, sizeof(float2) * sl->out_cap));
+                    B200_CUDA_TRY(cudaMallocHost(&sl->out_pin, sizeof(float2) * sl->out_cap));
                 }
-            std::memcpy(e->items_pin, items_host, sizeof(b200_trk_item) * n_items);
-            B200_CUDA_TRY(cudaMemcpyAsync(e->items_dev, e->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->stream));
-            B200_CUDA_TRY(cudaMemsetAsync(e->out_dev, 0, sizeof(float2) * out_elems, e->stream));
+            sl->busy = true;
+            sl->n_items = n_items;
+            sl->out_stride = out_stride;
+            sl->ticket = e->next_ticket++;
+            std::memcpy(sl->items_pin, items_host, sizeof(b200_trk_item) * n_items);
+            B200_CUDA_TRY(cudaMemcpyAsync(sl->items_dev, sl->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->stream));
         }
         // few items: split epochs into slices so the whole chip works on them
         int slices = 1;
         if (n_items < 592) slices = (592 + n_items - 1) / n_items;
         if (slices > 64) slices = 64;
-        int rc = b200_trk_batch_dev(e, e->items_dev, n_items, reinterpret_cast<b200_cf32*>(e->out_dev), out_stride, slices);
-        if (rc) return rc;
-        B200_CUDA_TRY(cudaMemcpyAsync(e->out_pin, e->out_dev, sizeof(float2) * n_items * out_stride, cudaMemcpyDeviceToHost, e->stream));
-        B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
-        std::memcpy(out_host, e->out_pin, sizeof(float2) * n_items * out_stride);
+        int rc = b200_trk_batch_dev(e, sl->items_dev, n_items, reinterpret_cast<b200_cf32*>(sl->out_dev), out_stride, slices);
+        if (rc)
+            {
+                sl->busy = false;
+                return rc;
+            }
+        B200_CUDA_TRY(cudaMemcpyAsync(sl->out_pin, sl->out_dev, sizeof(float2) * n_items * out_stride, cudaMemcpyDeviceToHost, e->stream));
+        B200_CUDA_TRY(cudaEventRecord(sl->done, e->stream));
+        *ticket = sl->ticket;
         return B200_OK;
+    }
+
+    int b200_trk_wait(b200_engine* e, uint64_t ticket, b200_cf32* out_host)
+    {
+        if (!e || !out_host) return B200_ERR_ARG;
+        b200_engine::Slot* sl = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            for (auto& s : e->slots)
+                if (s.busy && s.ticket == ticket) sl = &s;
+        }
+        if (!sl)
+            {
+                set_error("unknown ticket %llu", static_cast<unsigned long long>(ticket));
+                return B200_ERR_ARG;
+            }
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_CUDA_TRY(cudaEventSynchronize(sl->done));
+        std::memcpy(out_host, sl->out_pin, sizeof(float2) * sl->n_items * sl->out_stride);
+        std::lock_guard<std::mutex> lk(e->mu);
+        sl->busy = false;
+        return B200_OK;
+    }
+
+    int b200_trk_batch(b200_engine* e, const b200_trk_item* items_host, int n_items, b200_cf32* out_host, int out_stride)
+    {
+        if (!e || n_items < 0 || (n_items && (!items_host || !out_host)) || out_stride < 1) return B200_ERR_ARG;
+        if (n_items == 0) return B200_OK;
+        uint64_t ticket = 0;
+        int rc = b200_trk_submit(e, items_host, n_items, out_stride, &ticket);
+        if (rc) return rc;
+        return b200_trk_wait(e, ticket, out_host);
     }
 }
 

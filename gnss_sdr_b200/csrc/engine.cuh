@@ -60,5 +60,23 @@ struct b200_engine
     size_t partial_cap{0};
     int counters_cap{0};
     uint64_t launches{0};
+    // asynchronous batches (b200_trk_submit / b200_trk_wait)
+    struct Slot
+    {
+        b200_trk_item* items_pin{nullptr};
+        b200_trk_item* items_dev{nullptr};
+        float2* out_dev{nullptr};
+        float2* out_pin{nullptr};
+        int items_cap{0};
+        int out_cap{0};
+        int n_items{0};
+        int out_stride{0};
+        cudaEvent_t done{nullptr};
+        bool busy{false};
+        uint64_t ticket{0};
+    };
+    static constexpr int kSlots = 16;
+    Slot slots[kSlots];
+    uint64_t next_ticket{1};
 };
 

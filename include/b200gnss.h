@@ -127,6 +127,12 @@ extern "C"
      * engine stream. */
     int b200_trk_batch(b200_engine* e, const b200_trk_item* items_host, int n_items, b200_cf32* out_host, int out_stride);
     int b200_trk_batch_dev(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices);
+    /* Asynchronous form of b200_trk_batch: submit returns at once with a ticket (items are copied;
+     * the launch is ordered after every b200_iq_push made so far), wait blocks until that batch's
+     * taps are in out_host.  Up to 16 batches may be in flight, so IQ pushes (copy engine) and
+     * correlation (SMs) overlap.  These are the trk_submit / trk_wait of SURVEY 8b. */
+    int b200_trk_submit(b200_engine* e, const b200_trk_item* items_host, int n_items, int out_stride, uint64_t* ticket);
+    int b200_trk_wait(b200_engine* e, uint64_t ticket, b200_cf32* out_host);
     /* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
     int b200_engine_launch_count(b200_engine* e, uint64_t* n);
 

@@ -366,3 +366,31 @@ def test_high_dynamics_rotator_parity(capi, engine, oracle):
         want = oracle.ref.mc_correlate(h, iq, 3, float(rem_carr), float(dphi), float(drate), float(rem_code), float(step), float(crate))
         oracle.ref.mc_destroy(h)
         assert np.all(np.abs(got - want) / np.abs(want) < 1e-3)
+
+
+def test_submit_wait_overlapped_batches(capi, engine, oracle):
+    """b200_trk_submit / b200_trk_wait: several batches in flight, waited out of order, equal the
+    synchronous b200_trk_batch results bit for bit."""
+    n, L = 4000, 1023
+    rng = np.random.default_rng(21)
+    iq = (rng.standard_normal(n * 6 + 8) + 1j * rng.standard_normal(n * 6 + 8)).astype(np.complex64)
+    e = engine
+    band = 5
+    e.iq_create(band, len(iq))
+    first = e.iq_push(band, iq)
+    cid = e.channel_create(band, 3)
+    e.channel_set_code(cid, oracle.port.gps_ca_code(4), [-0.5, 0.0, 0.5])
+    items = np.zeros(6, capi.TRK_ITEM_DTYPE)
+    items["channel"] = cid
+    items["n"] = n
+    items["sample_index"] = first + np.arange(6) * n + 1
+    items["rem_carrier_phase_rad"] = 0.2
+    items["phase_step_rad"] = 2e-3
+    items["rem_code_phase_chips"] = 0.1
+    items["code_phase_step_chips"] = 0.25575
+    want = e.trk_batch(items, 3)
+    t = [e.trk_submit(items[k:k + 2], 3) for k in (0, 2, 4)]
+    got = {k: e.trk_wait(t[k]) for k in (2, 0, 1)}
+    assert np.array_equal(np.concatenate([got[0], got[1], got[2]]), want)
+    with pytest.raises(capi.B200Error):
+        e.trk_wait(t[0])      # ticket already consumed
