@@ -503,6 +503,47 @@ def main():
         # e2e result must agree with the device-resident run
         e2e["max_rel_diff_vs_value_run"] = float(np.max(np.abs(res - taps)) / np.max(np.abs(taps)))
 
+        # ---- same e2e step with 16-bit / 8-bit front-end samples (SURVEY "next" row N3): the raw integers
+        # cross PCIe and are converted on the device (b200_iq_push_i16/_i8) instead of on the host.
+        for bits, scale in ((16, 256.0), (8, 16.0)):
+            q = torch.clamp(torch.round(iq_dev[:n_iq] * scale), -(2 ** (bits - 1) - 1), 2 ** (bits - 1) - 1)
+            host_q = torch.empty((n_iq, 2), dtype=torch.int16 if bits == 16 else torch.int8, pin_memory=True)
+            host_q.copy_(q.to(host_q.dtype))
+            torch.cuda.synchronize()
+            del q
+            bpc = bits // 8
+
+            def step_int():
+                tickets = []
+                first0 = None
+                for c in range(E2E_CHUNKS):
+                    a, b = c * ep_per_chunk, (c + 1) * ep_per_chunk if c < E2E_CHUNKS - 1 else N_EPOCHS
+                    first = eng.iq_push_int(1, (host_q.data_ptr() + a * EPOCH * 2 * bpc, bits), (b - a) * EPOCH)
+                    if first0 is None:
+                        first0 = first
+                        items1["sample_index"] = base_idx + np.uint64(first0)
+                    tickets.append(eng.trk_submit(items1_v[a:b].reshape(-1), TAPS))
+                return np.concatenate([eng.trk_wait(t) for t in tickets], axis=0)
+
+            for _ in range(3):
+                ri = step_int()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ri = step_int()
+            barrier()
+            dti = time.perf_counter() - t0
+            tti = torch.tensor([dti], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tti, op=dist.ReduceOp.MAX)
+            dti = float(tti.item())
+            e2e[f"int{bits}_front_end"] = {"value": world * ch_samples_step * args.steps / dti / 1e6, "unit": UNIT,
+                                           "h2d_bytes_per_step": int(n_iq * 2 * bpc + items1.nbytes),
+                                           "d2h_bytes_per_step": int(n_items * TAPS * 8), "ms_per_step": dti / args.steps * 1e3,
+                                           "prompt_over_noise": float(np.mean(np.abs(ri[:, 1])) / scale / np.sqrt(EPOCH * 2.0)),
+                                           "path": f"b200_iq_push_i{bits} (raw {bits}-bit I/Q over PCIe, converted on the device)"}
+            del host_q
+
     acq = None
     if not args.no_acq:
         try:

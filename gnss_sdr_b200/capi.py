@@ -55,6 +55,8 @@ _SIGS = {
     "b200_engine_launch_count": ([_vp, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_create": ([_vp, C.c_int, C.c_uint64], C.c_int),
     "b200_iq_push": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
+    "b200_iq_push_i16": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
+    "b200_iq_push_i8": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_attach_dev": ([_vp, C.c_int, _vp, C.c_uint64, C.c_uint64], C.c_int),
     "b200_trk_create": ([_vp, C.POINTER(_vp), C.c_int, C.c_int], C.c_int),
     "b200_trk_set_high_dynamics_resampler": ([_vp, C.c_int], C.c_int),
@@ -171,6 +173,20 @@ class Engine:
     def iq_push_ptr(self, band: int, host_ptr: int, n: int) -> int:
         first = C.c_uint64(0)
         _chk(lib.b200_iq_push(self.h, band, host_ptr, n, C.byref(first)), "b200_iq_push")
+        return first.value
+
+    def iq_push_int(self, band: int, host_ptr_or_array, n: int = None) -> int:
+        """interleaved int16 or int8 (I,Q) samples; n = number of complex samples"""
+        first = C.c_uint64(0)
+        if isinstance(host_ptr_or_array, np.ndarray):
+            a = np.ascontiguousarray(host_ptr_or_array)
+            assert a.dtype in (np.int16, np.int8)
+            fn = lib.b200_iq_push_i16 if a.dtype == np.int16 else lib.b200_iq_push_i8
+            _chk(fn(self.h, band, a.ctypes.data, a.size // 2, C.byref(first)), "b200_iq_push_int")
+        else:
+            ptr, bits = host_ptr_or_array
+            fn = lib.b200_iq_push_i16 if bits == 16 else lib.b200_iq_push_i8
+            _chk(fn(self.h, band, ptr, n, C.byref(first)), "b200_iq_push_int")
         return first.value
 
     def iq_attach_dev(self, band: int, dev_ptr: int, n_samples: int, first_index: int = 0):

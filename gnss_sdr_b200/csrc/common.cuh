@@ -59,6 +59,13 @@ size_t trk_partial_elems(int n_items, int slices);
 
 }  // namespace b200
 
+namespace b200
+{
+// sample-type adapters (ingest_kernels.cu)
+int launch_convert_i16(const short* raw, float2* ring, unsigned long long mask, unsigned long long dst_off, unsigned long long n, cudaStream_t st);
+int launch_convert_i8(const signed char* raw, float2* ring, unsigned long long mask, unsigned long long dst_off, unsigned long long n, cudaStream_t st);
+}  // namespace b200
+
 // ---- acquisition launchers (acq_kernels.cu) ----------------------------------------------------------
 namespace b200
 {

@@ -172,7 +172,10 @@ extern "C"
         cudaStreamSynchronize(e->stream);
         cudaStreamSynchronize(e->copy_stream);
         for (auto& b : e->bands)
-            if (b.dev) cudaFree(b.dev);
+            {
+                if (b.dev) cudaFree(b.dev);
+                if (b.raw_stage) cudaFree(b.raw_stage);
+            }
         for (auto& c : e->chans)
             if (c.code_dev) cudaFree(c.code_dev);
         if (e->bands_dev) cudaFree(e->bands_dev);
@@ -290,6 +293,57 @@ extern "C"
         B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
         b.write_index += n;
         return B200_OK;
+    }
+
+    // shared implementation of the integer-sample pushes: raw bytes H2D, then conversion into the ring
+    static int push_raw(b200_engine* e, int band, const void* host, uint64_t n, uint64_t* first_index, int bytes_per_component)
+    {
+        if (!e || band < 0 || band >= kMaxBands || (!host && n)) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> lk(e->mu);
+        Band& b = e->bands[band];
+        if (!b.in_use || b.attached || !b.dev)
+            {
+                set_error("band %d is not an owned ring (call b200_iq_create)", band);
+                return B200_ERR_STATE;
+            }
+        if (n > b.capacity)
+            {
+                set_error("push of %llu samples exceeds ring capacity %llu", (unsigned long long)n, b.capacity);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        if (first_index) *first_index = b.write_index;
+        const unsigned long long bytes = n * 2ULL * static_cast<unsigned long long>(bytes_per_component);
+        if (bytes > b.raw_cap)
+            {
+                B200_CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+                if (b.raw_stage) B200_CUDA_TRY(cudaFree(b.raw_stage));
+                b.raw_cap = bytes + bytes / 4 + 256;
+                B200_CUDA_TRY(cudaMalloc(&b.raw_stage, b.raw_cap));
+            }
+        if (n)
+            {
+                B200_CUDA_TRY(cudaMemcpyAsync(b.raw_stage, host, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+                int rc = (bytes_per_component == 2)
+                             ? launch_convert_i16(static_cast<const short*>(b.raw_stage), b.dev, b.mask, b.write_index, n, e->copy_stream)
+                             : launch_convert_i8(static_cast<const signed char*>(b.raw_stage), b.dev, b.mask, b.write_index, n, e->copy_stream);
+                if (rc) return rc;
+                e->launches++;
+            }
+        B200_CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
+        B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
+        b.write_index += n;
+        return B200_OK;
+    }
+
+    int b200_iq_push_i16(b200_engine* e, int band, const int16_t* host_iq, uint64_t n, uint64_t* first_index)
+    {
+        return push_raw(e, band, host_iq, n, first_index, 2);
+    }
+
+    int b200_iq_push_i8(b200_engine* e, int band, const int8_t* host_iq, uint64_t n, uint64_t* first_index)
+    {
+        return push_raw(e, band, host_iq, n, first_index, 1);
     }
 
     int b200_iq_attach_dev(b200_engine* e, int band, const b200_cf32* dev, uint64_t n_samples, uint64_t first_index)

@@ -20,6 +20,8 @@ struct Band
     unsigned long long write_index{0};  // absolute index of the next pushed sample
     bool attached{false};
     bool in_use{false};
+    void* raw_stage{nullptr};           // device staging for integer sample pushes
+    unsigned long long raw_cap{0};      // bytes
 };
 
 struct Channel

@@ -76,6 +76,13 @@ extern "C"
     /* Append n host samples (async H2D on the copy stream, ordered before later launches).
      * *first_index receives the absolute index of host[0]. */
     int b200_iq_push(b200_engine* e, int band, const b200_cf32* host, uint64_t n, uint64_t* first_index);
+    /* Same for front ends that deliver interleaved 16-bit / 8-bit (I,Q) integers (lv_16sc_t / lv_8sc_t):
+     * the raw integers cross PCIe and are converted to float on the device, replacing the CPU
+     * adapters src/algorithms/data_type_adapter/gnuradio_blocks/cshort_to_gr_complex.cc:48
+     * (volk_gnsssdr_16ic_convert_32fc) and adapters/ibyte_to_complex.cc.  n counts complex samples;
+     * host_iq holds 2*n integers.  Conversion is exact (int -> float). */
+    int b200_iq_push_i16(b200_engine* e, int band, const int16_t* host_iq, uint64_t n, uint64_t* first_index);
+    int b200_iq_push_i8(b200_engine* e, int band, const int8_t* host_iq, uint64_t n, uint64_t* first_index);
     /* Use caller-owned device memory as the band (no copy): dev[0] is absolute index
      * first_index; n_samples need not be a power of two (no wrap). */
     int b200_iq_attach_dev(b200_engine* e, int band, const b200_cf32* dev, uint64_t n_samples, uint64_t first_index);

@@ -394,3 +394,36 @@ def test_submit_wait_overlapped_batches(capi, engine, oracle):
     assert np.array_equal(np.concatenate([got[0], got[1], got[2]]), want)
     with pytest.raises(capi.B200Error):
         e.trk_wait(t[0])      # ticket already consumed
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int8])
+def test_integer_sample_ingestion_bitexact(capi, engine, oracle, dtype):
+    """b200_iq_push_i16 / _i8: raw integer I/Q over PCIe, converted on the device
+    (volk_gnsssdr_16ic_convert_32fc semantics: plain int -> float), must give exactly the taps
+    of pushing the same samples as complex64, including across the ring wrap."""
+    n, L = 4000, 1023
+    rng = np.random.default_rng(31)
+    hi = 2000 if dtype == np.int16 else 100
+    raw = rng.integers(-hi, hi + 1, 2 * (n * 5 + 11)).astype(dtype)
+    as_c64 = (raw[0::2].astype(np.float32) + 1j * raw[1::2].astype(np.float32)).astype(np.complex64)
+    e = engine
+    res = {}
+    for name, band in (("float", 6), ("int", 7)):
+        e.iq_create(band, 16384)
+        # misalign the write position so that the data wraps around the ring end
+        e.iq_push(band, np.zeros(9001, np.complex64))
+        first = e.iq_push(band, as_c64) if name == "float" else e.iq_push_int(band, raw)
+        assert first == 9001
+        cid = e.channel_create(band, 3)
+        e.channel_set_code(cid, oracle.port.gps_ca_code(6), [-0.5, 0.0, 0.5])
+        items = np.zeros(5, capi.TRK_ITEM_DTYPE)
+        items["channel"] = cid
+        items["n"] = n
+        items["sample_index"] = first + np.arange(5) * n + 3
+        items["rem_carrier_phase_rad"] = 0.2
+        items["phase_step_rad"] = 2e-3
+        items["rem_code_phase_chips"] = 0.1
+        items["code_phase_step_chips"] = 0.25575
+        res[name] = e.trk_batch(items, 3)
+    assert np.array_equal(res["float"], res["int"])
+    assert np.all(np.abs(res["int"]) > 0)
