@@ -33,6 +33,7 @@ struct BandDesc
     const float2* base;
     unsigned long long mask;
     unsigned long long first_index;
+    unsigned long long limit;  // samples addressable from base (ring capacity or attached length)
 };
 
 // One tracking channel registration: code table (device), its length, taps and shifts.
@@ -56,6 +57,10 @@ int launch_trk_batch(const b200_trk_item* items, int n_items, const ChanDesc* ch
     float2* out, int out_stride, int slices, float2* partial, unsigned int* counters,
     int max_code_len, int taps_uniform, cudaStream_t stream);
 size_t trk_partial_elems(int n_items, int slices);
+// shared-window kernel (trk_shared_kernel.cu): groups of 8 items share one copy of the samples
+int launch_trk_shared(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands, float2* out,
+    int out_stride, int taps_uniform, cudaStream_t stream);
+int trk_shared_max_code_len();
 
 }  // namespace b200
 

@@ -5,6 +5,8 @@
 
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -40,6 +42,7 @@ int upload_tables(b200_engine* e)
             bd[i].base = e->bands[i].base;
             bd[i].mask = e->bands[i].mask;
             bd[i].first_index = e->bands[i].first_index;
+            bd[i].limit = e->bands[i].capacity;
         }
     B200_CUDA_TRY(cudaMemcpyAsync(e->bands_dev, bd, sizeof(bd), cudaMemcpyHostToDevice, e->stream));
     const int n = static_cast<int>(e->chans.size());
@@ -51,6 +54,7 @@ int upload_tables(b200_engine* e)
         }
     e->max_code_len = 0;
     e->taps_uniform = -1;
+    e->any_high_dyn = false;
     if (n > 0)
         {
             std::vector<ChanDesc> cd(n);
@@ -59,6 +63,7 @@ int upload_tables(b200_engine* e)
                     cd[i] = e->chans[i].desc;
                     if (cd[i].code_len > e->max_code_len) e->max_code_len = cd[i].code_len;
                     if (cd[i].code == nullptr) continue;
+                    if (cd[i].high_dyn) e->any_high_dyn = true;
                     if (e->taps_uniform == -1)
                         e->taps_uniform = cd[i].taps;
                     else if (e->taps_uniform != cd[i].taps)
@@ -433,8 +438,20 @@ extern "C"
         if (slices < 1) slices = 1;
         rc = ensure_partials(e, n_items, slices);
         if (rc) return rc;
-        rc = launch_trk_batch(items_dev, n_items, e->chans_dev, e->bands_dev, reinterpret_cast<float2*>(out_dev), out_stride,
-            slices, e->partial, e->counters, e->max_code_len, e->taps_uniform, e->stream);
+        if (e->shared_mode < 0)
+            {
+                const char* env = std::getenv("B200_TRK_SHARED");
+                e->shared_mode = env ? std::atoi(env) : 2;  // 2 = automatic
+            }
+        const bool shared_legal = (e->taps_uniform == 1 || e->taps_uniform == 3 || e->taps_uniform == 5) && !e->any_high_dyn &&
+                                  e->max_code_len <= trk_shared_max_code_len() && slices == 1;
+        const bool use_shared = shared_legal && (e->shared_mode == 1 || (e->shared_mode == 2 && n_items >= 1024));
+        if (use_shared)
+            rc = launch_trk_shared(items_dev, n_items, e->chans_dev, e->bands_dev, reinterpret_cast<float2*>(out_dev), out_stride,
+                e->taps_uniform, e->stream);
+        else
+            rc = launch_trk_batch(items_dev, n_items, e->chans_dev, e->bands_dev, reinterpret_cast<float2*>(out_dev), out_stride,
+                slices, e->partial, e->counters, e->max_code_len, e->taps_uniform, e->stream);
         if (rc == B200_OK) e->launches++;
         return rc;
     }
@@ -493,7 +510,24 @@ extern "C"
             sl->n_items = n_items;
             sl->out_stride = out_stride;
             sl->ticket = e->next_ticket++;
-            std::memcpy(sl->items_pin, items_host, sizeof(b200_trk_item) * n_items);
+            // The shared-window kernel serves items 8g..8g+7 from one copy of the samples, so items
+            // should be ordered by start sample.  Already-ordered input (the usual epoch-major layout)
+            // is copied as is; otherwise sort a permutation and undo it in b200_trk_wait.
+            bool sorted = true;
+            for (int i = 1; i < n_items && sorted; i++) sorted = items_host[i - 1].sample_index <= items_host[i].sample_index;
+            sl->perm.clear();
+            if (sorted)
+                {
+                    std::memcpy(sl->items_pin, items_host, sizeof(b200_trk_item) * n_items);
+                }
+            else
+                {
+                    sl->perm.resize(n_items);
+                    for (int i = 0; i < n_items; i++) sl->perm[i] = i;
+                    std::stable_sort(sl->perm.begin(), sl->perm.end(),
+                        [&](int a, int b) { return items_host[a].sample_index < items_host[b].sample_index; });
+                    for (int i = 0; i < n_items; i++) sl->items_pin[i] = items_host[sl->perm[i]];
+                }
             B200_CUDA_TRY(cudaMemcpyAsync(sl->items_dev, sl->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->stream));
         }
         // few items: split epochs into slices so the whole chip works on them
@@ -528,7 +562,16 @@ extern "C"
             }
         B200_CUDA_TRY(cudaSetDevice(e->device));
         B200_CUDA_TRY(cudaEventSynchronize(sl->done));
-        std::memcpy(out_host, sl->out_pin, sizeof(float2) * sl->n_items * sl->out_stride);
+        if (sl->perm.empty())
+            {
+                std::memcpy(out_host, sl->out_pin, sizeof(float2) * sl->n_items * sl->out_stride);
+            }
+        else
+            {
+                for (int k = 0; k < sl->n_items; k++)
+                    std::memcpy(out_host + static_cast<size_t>(sl->perm[k]) * sl->out_stride, sl->out_pin + static_cast<size_t>(k) * sl->out_stride,
+                        sizeof(float2) * sl->out_stride);
+            }
         std::lock_guard<std::mutex> lk(e->mu);
         sl->busy = false;
         return B200_OK;
@@ -654,6 +697,7 @@ extern "C"
         c->band.base = t->sig_dev;
         c->band.mask = ~0ULL;
         c->band.first_index = 0;
+        c->band.limit = static_cast<unsigned long long>(t->max_len) + 2ULL;
         c->item.channel = 0;
         c->item.n = n;
         c->item.sample_index = 0;

@@ -50,6 +50,8 @@ struct b200_engine
     bool tables_dirty{true};
     int max_code_len{0};
     int taps_uniform{-1};
+    bool any_high_dyn{false};
+    int shared_mode{-1};   // -1 auto, 0 never, 1 always-when-legal (env B200_TRK_SHARED)
     // batch staging
     b200_trk_item* items_dev{nullptr};
     b200_trk_item* items_pin{nullptr};
@@ -76,6 +78,7 @@ struct b200_engine
         cudaEvent_t done{nullptr};
         bool busy{false};
         uint64_t ticket{0};
+        std::vector<int> perm;  // results k belong to the caller's item perm[k] (empty = identity)
     };
     static constexpr int kSlots = 16;
     Slot slots[kSlots];

@@ -1,0 +1,481 @@
+// Tracking correlator, "shared window" kernel for sm_100a.
+//
+// Why: the per-item kernel (trk_kernels.cu) re-reads every IQ sample from L2 once per channel.  With
+// 32 channels on one band that is 6.4 GB through the L2->SM crossbar per second of signal, and the
+// crossbar (~6.7 TB/s measured, profiles/roofline_traffic.json) becomes the bound.  Channels that are
+// in lock on the same band correlate the SAME samples, so here one CTA serves a GROUP of up to 8 work
+// items (one consumer warp each) from one copy of the samples:
+//
+//   producer warp   cp.async.bulk (TMA bulk copy, UBLKCP) of 512-sample tiles of the band store into a
+//                   4-stage shared-memory ring, completion signalled on mbarriers (expect_tx bytes);
+//   8 consumer warps each owns one (channel, epoch) item of the group: waits for the tile, reads its
+//                   samples with conflict-free LDS.128, rotates, looks its three (five, ...) chips up
+//                   in a warp-private shared-memory code table, accumulates E/P/L in packed f32x2
+//                   registers, releases the tile.
+//
+// The arithmetic per sample is exactly that of trk_kernels.cu (same chip-index float sequence, same
+// 64-bit fixed-point carrier phase), so results follow the same contract.  Items of a group need
+// not start at the same sample: the tile range is the hull of the group and a warp only works on
+// tiles that intersect its own epoch (masked at the ends).  Group membership is the caller's item
+// ORDER (items 8g .. 8g+7); the host API sorts by start sample, bench.py's epoch-major order already
+// has that shape.
+#include "trk_device.cuh"
+
+namespace b200
+{
+constexpr int kShK = 8;          // items (consumer warps) per CTA
+constexpr int kShTile = 512;     // samples per tile (4 KB)
+constexpr int kShStages = 4;
+constexpr int kShTblCap = 1152;  // floats per warp-private extended code table
+constexpr int kShThreads = (kShK + 1) * 32;
+constexpr int kShReseed = 64;    // 64-sample steps between exact phasor re-seeds (4096 samples)
+
+namespace
+{
+struct __align__(128) ShSmem
+{
+    float2 tiles[kShStages][kShTile];
+    float tbl[kShK][kShTblCap];
+    unsigned long long full[kShStages];
+    unsigned long long empty[kShStages];
+    unsigned long long item_start[kShK];  // offset of the item's first sample in the band (band-relative)
+    int item_n[kShK];
+    int item_band[kShK];
+    unsigned long long hull_start;
+    int n_tiles;
+    int share;
+};
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return static_cast<unsigned int>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned int bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Correct-for-anything fallback for one warp: direct global loads, exact phasor per sample, integer
+// modulo lookup in the global code table.  Used when an item cannot take the table path.
+template <int TAPS>
+__device__ void warp_correlate_general(const b200_trk_item& it, const ChanDesc& ch, const BandDesc& bd, float2 (&acc)[TAPS])
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long s0 = it.sample_index - bd.first_index;
+    const unsigned long long T0 = turns_from_rad(-static_cast<double>(it.rem_carrier_phase_rad));
+    const unsigned long long DT = turns_from_rad(-static_cast<double>(it.phase_step_rad));
+    const int body = (it.n / 8) * 8;
+    for (int n = lane; n < it.n; n += 32)
+        {
+            const float2 x = ldg_stream8(bd.base + ((s0 + static_cast<unsigned long long>(n)) & bd.mask));
+            const float2 z = phasor_from_turns(T0 + DT * static_cast<unsigned long long>(n));
+            const float wr = fmaf(x.x, z.x, -x.y * z.y);
+            const float wi = fmaf(x.x, z.y, x.y * z.x);
+            const float nf = static_cast<float>(n);
+#pragma unroll
+            for (int t = 0; t < TAPS; t++)
+                {
+                    const int idx = (n < body) ? chip_index_avx(it.code_phase_step_chips, nf, __fsub_rn(ch.shifts[t], it.rem_code_phase_chips))
+                                               : chip_index_generic(it.code_phase_step_chips, nf, ch.shifts[t], it.rem_code_phase_chips);
+                    const float c = ch.code[mod_pos(idx, ch.code_len)];
+                    acc[t].x = fmaf(wr, c, acc[t].x);
+                    acc[t].y = fmaf(wi, c, acc[t].y);
+                }
+        }
+}
+
+// One tile (512 samples in shared memory) for one warp.  MASKED = the tile sticks out of [0, body):
+// samples outside contribute zero and evaluate the chip index at n = 0 / 1 (inside the table).
+template <int TAPS, bool MASKED>
+__device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int n_tile0, int body, float step,
+    const float2 (&aux2)[TAPS], unsigned int tbl_off, float2 Dr2, float2 Di2, float2 Gr2, float2 Gi2, float2& zr2, float2& zi2,
+    float2& zr, float2& zi, int& steps_in_group, float2 (&are)[TAPS], float2 (&aim)[TAPS])
+{
+    const int lane = threadIdx.x & 31;
+    const float2 magic2 = make_float2(12582912.0f, 12582912.0f);
+#pragma unroll 4
+    for (int k = 0; k < kShTile / 64; k++)
+        {
+            const int off = 2 * lane + 64 * k;          // sample offset inside the tile (even)
+            const float4 v = *reinterpret_cast<const float4*>(tile + off);
+            const int na = n_tile0 + off;
+            float fa = static_cast<float>(na), fb = static_cast<float>(na + 1);
+            float2 xa = make_float2(v.x, v.y), xb = make_float2(v.z, v.w);
+            if (MASKED)
+                {
+                    const bool va = static_cast<unsigned int>(na) < static_cast<unsigned int>(body);
+                    const bool vb = static_cast<unsigned int>(na + 1) < static_cast<unsigned int>(body);
+                    if (!va)
+                        {
+                            xa = make_float2(0.f, 0.f);
+                            fa = 0.0f;
+                        }
+                    if (!vb)
+                        {
+                            xb = make_float2(0.f, 0.f);
+                            fb = 1.0f;
+                        }
+                }
+            float2 wr2, wi2;
+            wr2.x = fmaf(xa.x, zr.x, -xa.y * zi.x);
+            wi2.x = fmaf(xa.x, zi.x, xa.y * zr.x);
+            wr2.y = fmaf(xb.x, zr.y, -xb.y * zi.y);
+            wi2.y = fmaf(xb.x, zi.y, xb.y * zr.y);
+            const float2 m2 = make_float2(__fmul_rn(step, fa), __fmul_rn(step, fb));
+#pragma unroll
+            for (int t = 0; t < TAPS; t++)
+                {
+                    const float2 tt = __fadd2_rd(__fadd2_rn(m2, aux2[t]), magic2);
+                    const float ca = lds_f32((__float_as_uint(tt.x) << 2) + tbl_off);
+                    const float cb = lds_f32((__float_as_uint(tt.y) << 2) + tbl_off);
+                    const float2 c2 = make_float2(ca, cb);
+                    are[t] = __ffma2_rn(wr2, c2, are[t]);
+                    aim[t] = __ffma2_rn(wi2, c2, aim[t]);
+                }
+            steps_in_group++;
+            if (steps_in_group == kShReseed)
+                {
+                    // exact-ish re-seed: the group seed advances by G = exp(j DT 64*kShReseed)
+                    const float2 t2 = __fmul2_rn(zi2, Gi2);
+                    const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
+                    zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
+                    zr2 = ngr;
+                    zr = zr2;
+                    zi = zi2;
+                    steps_in_group = 0;
+                }
+            else
+                {
+                    const float2 t1 = __fmul2_rn(zi, Di2);
+                    const float2 nzr = __ffma2_rn(zr, Dr2, make_float2(-t1.x, -t1.y));
+                    zi = __ffma2_rn(zr, Di2, __fmul2_rn(zi, Dr2));
+                    zr = nzr;
+                }
+        }
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(kShThreads, 3) trk_shared_kernel(const b200_trk_item* __restrict__ items, int n_items,
+    const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, float2* __restrict__ out, int out_stride)
+{
+    extern __shared__ __align__(128) unsigned char sh_raw[];
+    ShSmem& sm = *reinterpret_cast<ShSmem*>(sh_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.x;
+    const int item_id = group * kShK + warp;
+    const bool consumer = warp < kShK;
+    const bool have_item = consumer && item_id < n_items;
+
+    b200_trk_item it;
+    ChanDesc const* ch = nullptr;
+    BandDesc bd;
+    if (have_item)
+        {
+            it = items[item_id];
+            ch = &chans[it.channel];
+            bd = bands[ch->band];
+        }
+    if (threadIdx.x == 0)
+        {
+            for (int s = 0; s < kShStages; s++)
+                {
+                    mbar_init(&sm.full[s], 1);
+                    mbar_init(&sm.empty[s], kShK);
+                }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    if (consumer && lane == 0)
+        {
+            sm.item_n[warp] = have_item ? it.n : 0;
+            sm.item_band[warp] = have_item ? ch->band : -1;
+            sm.item_start[warp] = have_item ? (it.sample_index - bd.first_index) : 0ULL;
+        }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        {
+            // hull of the group's sample ranges (same band only, no ring wrap inside an item's range
+            // relative to the hull start, bounded sparsity) -- otherwise the warps load for themselves
+            unsigned long long lo = ~0ULL, hi = 0ULL;
+            int band = -1, share = 1, nmax = 0;
+            for (int w = 0; w < kShK; w++)
+                {
+                    if (sm.item_n[w] <= 0) continue;
+                    if (band < 0) band = sm.item_band[w];
+                    if (sm.item_band[w] != band) share = 0;
+                    lo = min(lo, sm.item_start[w]);
+                    hi = max(hi, sm.item_start[w] + static_cast<unsigned long long>(sm.item_n[w]));
+                    nmax = max(nmax, sm.item_n[w]);
+                }
+            if (band < 0) share = 0;
+            lo &= ~1ULL;  // 16-byte aligned tile starts
+            if (share && (hi - lo) > 3ULL * static_cast<unsigned long long>(nmax) + 2ULL * kShTile) share = 0;
+            sm.hull_start = lo;
+            sm.n_tiles = share ? static_cast<int>((hi - lo + kShTile - 1) / kShTile) : 0;
+            sm.share = share;
+        }
+    __syncthreads();
+    const int n_tiles = sm.n_tiles;
+    const unsigned long long hull_start = sm.hull_start;
+
+    if (!consumer)
+        {
+            // ---- producer warp: stream the hull through the ring ---------------------------------------
+            if (lane == 0 && n_tiles > 0)
+                {
+                    BandDesc pb;
+                    {
+                        int w0 = 0;
+                        while (sm.item_n[w0] <= 0) w0++;
+                        pb = bands[sm.item_band[w0]];
+                    }
+                    const bool ring = (pb.mask != ~0ULL);
+                    const unsigned long long cap = ring ? pb.mask + 1ULL : pb.limit;
+                    for (int t = 0; t < n_tiles; t++)
+                        {
+                            const int s = t % kShStages;
+                            const unsigned int par = static_cast<unsigned int>((t / kShStages) & 1);
+                            mbar_wait(&sm.empty[s], par ^ 1u);
+                            unsigned long long src = hull_start + static_cast<unsigned long long>(t) * kShTile;
+                            unsigned int n1 = kShTile, n2 = 0;
+                            if (ring)
+                                {
+                                    src &= pb.mask;
+                                    if (src + kShTile > cap)
+                                        {
+                                            n1 = static_cast<unsigned int>(cap - src);
+                                            n2 = kShTile - n1;
+                                        }
+                                }
+                            else
+                                {
+                                    // linear band: never read past its end (the clipped samples are outside every item)
+                                    if (src >= cap)
+                                        n1 = 0;
+                                    else if (src + kShTile > cap)
+                                        n1 = static_cast<unsigned int>(cap - src) & ~1u;
+                                }
+                            mbar_arrive_expect_tx(&sm.full[s], (n1 + n2) * 8u);
+                            if (n1) bulk_g2s(&sm.tiles[s][0], pb.base + src, n1 * 8u, &sm.full[s]);
+                            if (n2) bulk_g2s(&sm.tiles[s][n1], pb.base, n2 * 8u, &sm.full[s]);
+                        }
+                }
+            return;
+        }
+
+    // ---- consumer warp: one item ---------------------------------------------------------------------
+    float2 acc[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) acc[t] = make_float2(0.f, 0.f);
+
+    bool table_path = false;
+    int body = 0, a_i = 0, t_first = 0, t_last = 0;
+    float step = 0.f;
+    unsigned int tbl_off = 0;
+    float2 aux2[TAPS];
+    float2 Dr2, Di2, Gr2, Gi2, zr2, zi2, zr, zi;
+    unsigned long long T0 = 0, DT = 0;
+    if (have_item && it.n > 0)
+        {
+            body = (it.n / 8) * 8;
+            step = it.code_phase_step_chips;
+            const float rem = it.rem_code_phase_chips;
+            T0 = turns_from_rad(-static_cast<double>(it.rem_carrier_phase_rad));
+            DT = turns_from_rad(-static_cast<double>(it.phase_step_rad));
+            // chip-index range (monotone in n inside each association)
+            long long lo = 0x7fffffff, hi = -0x7fffffff - 1LL;
+            const float nl_avx = static_cast<float>(max(body - 1, 0));
+            const float n_last = static_cast<float>(it.n - 1);
+            const float n_body = static_cast<float>(body);
+#pragma unroll
+            for (int t = 0; t < TAPS; t++)
+                {
+                    const float sh = ch->shifts[t];
+                    const float a2 = __fsub_rn(sh, rem);
+                    aux2[t] = make_float2(a2, a2);
+                    int v[6];
+                    v[0] = chip_index_avx(step, 0.f, a2);
+                    v[1] = chip_index_avx(step, nl_avx, a2);
+                    v[2] = chip_index_generic(step, n_body, sh, rem);
+                    v[3] = chip_index_generic(step, n_last, sh, rem);
+                    v[4] = chip_index_generic(step, 0.f, sh, rem);
+                    v[5] = chip_index_avx(step, 1.f, a2);
+#pragma unroll
+                    for (int q = 0; q < 6; q++)
+                        {
+                            lo = min(lo, static_cast<long long>(v[q]));
+                            hi = max(hi, static_cast<long long>(v[q]));
+                        }
+                }
+            const long long span = hi - lo + 5;
+            table_path = sm.share && !ch->high_dyn && span <= kShTblCap && lo > -4000000LL && hi < 4000000LL;
+            if (table_path)
+                {
+                    const int base_i = static_cast<int>(lo - 2);
+                    const int L = ch->code_len;
+                    int r = mod_pos(base_i + lane, L);
+                    const int stride = 32 % L;
+                    for (int j = lane; j < static_cast<int>(span); j += 32)
+                        {
+                            sm.tbl[warp][j] = ch->code[r];
+                            r += stride;
+                            if (r >= L) r -= L;
+                        }
+                    asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.tbl[warp][0])), "r"(4u * (static_cast<unsigned int>(base_i) + 0x4B400000u)));
+                    a_i = static_cast<int>(sm.item_start[warp] - hull_start);
+                    t_first = a_i / kShTile;
+                    t_last = (a_i + body + kShTile - 1) / kShTile;
+                    const float2 D = phasor_from_turns(DT * 64ULL);
+                    const float2 G = phasor_from_turns(DT * static_cast<unsigned long long>(64 * kShReseed));
+                    Dr2 = make_float2(D.x, D.x);
+                    Di2 = make_float2(D.y, D.y);
+                    Gr2 = make_float2(G.x, G.x);
+                    Gi2 = make_float2(G.y, G.y);
+                    // phasors of the lane's two samples at the first tile (n may be negative: modular phase)
+                    const long long n0 = static_cast<long long>(t_first) * kShTile + 2 * lane - a_i;
+                    const float2 za = phasor_from_turns(T0 + DT * static_cast<unsigned long long>(n0));
+                    const float2 zb = phasor_from_turns(T0 + DT * static_cast<unsigned long long>(n0 + 1));
+                    zr2 = make_float2(za.x, zb.x);
+                    zi2 = make_float2(za.y, zb.y);
+                    zr = zr2;
+                    zi = zi2;
+                }
+            __syncwarp();
+        }
+
+    float2 are[TAPS], aim[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) are[t] = aim[t] = make_float2(0.f, 0.f);
+    int steps_in_group = 0;
+    for (int t = 0; t < n_tiles; t++)
+        {
+            const int s = t % kShStages;
+            const unsigned int par = static_cast<unsigned int>((t / kShStages) & 1);
+            // Every consumer waits for every tile, also the ones it skips: a warp that ran ahead could
+            // otherwise arrive twice on empty[s] within one phase and let the producer overwrite a slot
+            // that a slower warp is still reading.
+            mbar_wait(&sm.full[s], par);
+            if (table_path && t >= t_first && t < t_last)
+                {
+                    const int n_tile0 = t * kShTile - a_i;
+                    const bool interior = (n_tile0 >= 0) && (n_tile0 + kShTile <= body);
+                    if (interior)
+                        warp_tile<TAPS, false>(&sm.tiles[s][0], n_tile0, body, step, aux2, tbl_off, Dr2, Di2, Gr2, Gi2, zr2, zi2, zr, zi, steps_in_group, are, aim);
+                    else
+                        warp_tile<TAPS, true>(&sm.tiles[s][0], n_tile0, body, step, aux2, tbl_off, Dr2, Di2, Gr2, Gi2, zr2, zi2, zr, zi, steps_in_group, are, aim);
+                    __syncwarp();
+                }
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+    if (have_item && it.n > 0)
+        {
+            if (table_path)
+                {
+#pragma unroll
+                    for (int t = 0; t < TAPS; t++)
+                        {
+                            acc[t].x = are[t].x + are[t].y;
+                            acc[t].y = aim[t].x + aim[t].y;
+                        }
+                    // tail n in [body, N): generic association, a handful of samples
+                    const int n = body + lane;
+                    if (n < it.n)
+                        {
+                            const unsigned long long s0 = it.sample_index - bd.first_index;
+                            const float2 x = ldg_stream8(bd.base + ((s0 + static_cast<unsigned long long>(n)) & bd.mask));
+                            const float2 z = phasor_from_turns(T0 + DT * static_cast<unsigned long long>(n));
+                            const float wr = fmaf(x.x, z.x, -x.y * z.y);
+                            const float wi = fmaf(x.x, z.y, x.y * z.x);
+#pragma unroll
+                            for (int t = 0; t < TAPS; t++)
+                                {
+                                    const int idx = chip_index_generic(step, static_cast<float>(n), ch->shifts[t], it.rem_code_phase_chips);
+                                    const float c = lds_f32((static_cast<unsigned int>(idx + 0x4B400000) << 2) + tbl_off);
+                                    acc[t].x = fmaf(wr, c, acc[t].x);
+                                    acc[t].y = fmaf(wi, c, acc[t].y);
+                                }
+                        }
+                }
+            else
+                {
+                    warp_correlate_general<TAPS>(it, *ch, bd, acc);
+                }
+#pragma unroll
+            for (int t = 0; t < TAPS; t++)
+                {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        {
+                            acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, o);
+                            acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, o);
+                        }
+                }
+            if (lane < TAPS)
+                {
+                    float2 r = acc[0];
+#pragma unroll
+                    for (int t = 1; t < TAPS; t++)
+                        if (lane == t) r = acc[t];
+                    out[static_cast<size_t>(item_id) * out_stride + lane] = r;
+                }
+        }
+    else if (have_item && lane < ch->taps)
+        {
+            out[static_cast<size_t>(item_id) * out_stride + lane] = make_float2(0.f, 0.f);
+        }
+}
+}  // namespace
+
+int launch_trk_shared(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands, float2* out,
+    int out_stride, int taps_uniform, cudaStream_t stream)
+{
+    if (n_items <= 0) return B200_OK;
+    const int groups = (n_items + kShK - 1) / kShK;
+    static bool attr_done = false;
+    if (!attr_done)
+        {
+            B200_CUDA_TRY(cudaFuncSetAttribute(trk_shared_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ShSmem))));
+            B200_CUDA_TRY(cudaFuncSetAttribute(trk_shared_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ShSmem))));
+            B200_CUDA_TRY(cudaFuncSetAttribute(trk_shared_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ShSmem))));
+            attr_done = true;
+        }
+    const size_t smem = sizeof(ShSmem);
+    switch (taps_uniform)
+        {
+        case 1: trk_shared_kernel<1><<<groups, kShThreads, smem, stream>>>(items, n_items, chans, bands, out, out_stride); break;
+        case 3: trk_shared_kernel<3><<<groups, kShThreads, smem, stream>>>(items, n_items, chans, bands, out, out_stride); break;
+        case 5: trk_shared_kernel<5><<<groups, kShThreads, smem, stream>>>(items, n_items, chans, bands, out, out_stride); break;
+        default: return B200_ERR_ARG;
+        }
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int trk_shared_max_code_len() { return kShTblCap - kTrkTablePad; }
+
+}  // namespace b200
