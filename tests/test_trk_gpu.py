@@ -409,11 +409,11 @@ def test_integer_sample_ingestion_bitexact(capi, engine, oracle, dtype):
     e = engine
     res = {}
     for name, band in (("float", 6), ("int", 7)):
-        e.iq_create(band, 16384)
+        e.iq_create(band, 32768)
         # misalign the write position so that the data wraps around the ring end
-        e.iq_push(band, np.zeros(9001, np.complex64))
+        e.iq_push(band, np.zeros(20001, np.complex64))
         first = e.iq_push(band, as_c64) if name == "float" else e.iq_push_int(band, raw)
-        assert first == 9001
+        assert first == 20001
         cid = e.channel_create(band, 3)
         e.channel_set_code(cid, oracle.port.gps_ca_code(6), [-0.5, 0.0, 0.5])
         items = np.zeros(5, capi.TRK_ITEM_DTYPE)
