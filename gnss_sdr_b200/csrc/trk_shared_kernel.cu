@@ -66,12 +66,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
         "{\n\t"
         ".reg .pred P1;\n\t"
         "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware instead of spinning
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned int bytes, unsigned long long* bar)
@@ -110,36 +110,38 @@ __device__ void warp_correlate_general(const b200_trk_item& it, const ChanDesc& 
         }
 }
 
-// One tile (512 samples in shared memory) for one warp.  MASKED = the tile sticks out of [0, body):
-// samples outside contribute zero and evaluate the chip index at n = 0 / 1 (inside the table).
+// One tile (512 samples in shared memory) for one warp: 8 steps of 64 samples, lane l takes the pair
+// (2l, 2l+1) of every step.  fa/fb (sample index within the epoch, as floats) and the running phasors
+// are lane state that continues seamlessly from tile to tile (tiles are contiguous).
+// MASKED = the tile sticks out of [0, body): samples outside contribute zero and evaluate the chip
+// index at n = 0 / 1 (inside the table).
 template <int TAPS, bool MASKED>
-__device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int n_tile0, int body, float step,
-    const float2 (&aux2)[TAPS], unsigned int tbl_off, float2 Dr2, float2 Di2, float2 Gr2, float2 Gi2, float2& zr2, float2& zi2,
-    float2& zr, float2& zi, int& steps_in_group, float2 (&are)[TAPS], float2 (&aim)[TAPS])
+__device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int body, float step, const float2 (&aux2)[TAPS],
+    unsigned int tbl_off, float2 Dr2, float2 Di2, float& fa, float& fb, float2& zr, float2& zi, float2 (&are)[TAPS], float2 (&aim)[TAPS])
 {
     const int lane = threadIdx.x & 31;
     const float2 magic2 = make_float2(12582912.0f, 12582912.0f);
-#pragma unroll 4
+    const float4* p = reinterpret_cast<const float4*>(tile) + lane;
+#pragma unroll
     for (int k = 0; k < kShTile / 64; k++)
         {
-            const int off = 2 * lane + 64 * k;          // sample offset inside the tile (even)
-            const float4 v = *reinterpret_cast<const float4*>(tile + off);
-            const int na = n_tile0 + off;
-            float fa = static_cast<float>(na), fb = static_cast<float>(na + 1);
+            const float4 v = p[32 * k];
+            float ua = fa, ub = fb;
             float2 xa = make_float2(v.x, v.y), xb = make_float2(v.z, v.w);
             if (MASKED)
                 {
-                    const bool va = static_cast<unsigned int>(na) < static_cast<unsigned int>(body);
-                    const bool vb = static_cast<unsigned int>(na + 1) < static_cast<unsigned int>(body);
+                    const float bodyf = static_cast<float>(body);
+                    const bool va = (fa >= 0.0f) && (fa < bodyf);   // sample indices are exact in float (< 2^24)
+                    const bool vb = (fb >= 0.0f) && (fb < bodyf);
                     if (!va)
                         {
                             xa = make_float2(0.f, 0.f);
-                            fa = 0.0f;
+                            ua = 0.0f;
                         }
                     if (!vb)
                         {
                             xb = make_float2(0.f, 0.f);
-                            fb = 1.0f;
+                            ub = 1.0f;
                         }
                 }
             float2 wr2, wi2;
@@ -147,7 +149,7 @@ __device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int n
             wi2.x = fmaf(xa.x, zi.x, xa.y * zr.x);
             wr2.y = fmaf(xb.x, zr.y, -xb.y * zi.y);
             wi2.y = fmaf(xb.x, zi.y, xb.y * zr.y);
-            const float2 m2 = make_float2(__fmul_rn(step, fa), __fmul_rn(step, fb));
+            const float2 m2 = make_float2(__fmul_rn(step, ua), __fmul_rn(step, ub));
 #pragma unroll
             for (int t = 0; t < TAPS; t++)
                 {
@@ -158,25 +160,12 @@ __device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int n
                     are[t] = __ffma2_rn(wr2, c2, are[t]);
                     aim[t] = __ffma2_rn(wi2, c2, aim[t]);
                 }
-            steps_in_group++;
-            if (steps_in_group == kShReseed)
-                {
-                    // exact-ish re-seed: the group seed advances by G = exp(j DT 64*kShReseed)
-                    const float2 t2 = __fmul2_rn(zi2, Gi2);
-                    const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
-                    zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
-                    zr2 = ngr;
-                    zr = zr2;
-                    zi = zi2;
-                    steps_in_group = 0;
-                }
-            else
-                {
-                    const float2 t1 = __fmul2_rn(zi, Di2);
-                    const float2 nzr = __ffma2_rn(zr, Dr2, make_float2(-t1.x, -t1.y));
-                    zi = __ffma2_rn(zr, Di2, __fmul2_rn(zi, Dr2));
-                    zr = nzr;
-                }
+            const float2 t1 = __fmul2_rn(zi, Di2);
+            const float2 nzr = __ffma2_rn(zr, Dr2, make_float2(-t1.x, -t1.y));
+            zi = __ffma2_rn(zr, Di2, __fmul2_rn(zi, Dr2));
+            zr = nzr;
+            fa += 64.0f;
+            fb += 64.0f;
         }
 }
 
@@ -371,7 +360,8 @@ __global__ void __launch_bounds__(kShThreads, 3) trk_shared_kernel(const b200_tr
     float2 are[TAPS], aim[TAPS];
 #pragma unroll
     for (int t = 0; t < TAPS; t++) are[t] = aim[t] = make_float2(0.f, 0.f);
-    int steps_in_group = 0;
+    int tiles_in_group = 0;
+    float fa = static_cast<float>(t_first * kShTile + 2 * lane - a_i), fb = fa + 1.0f;
     for (int t = 0; t < n_tiles; t++)
         {
             const int s = t % kShStages;
@@ -385,9 +375,21 @@ __global__ void __launch_bounds__(kShThreads, 3) trk_shared_kernel(const b200_tr
                     const int n_tile0 = t * kShTile - a_i;
                     const bool interior = (n_tile0 >= 0) && (n_tile0 + kShTile <= body);
                     if (interior)
-                        warp_tile<TAPS, false>(&sm.tiles[s][0], n_tile0, body, step, aux2, tbl_off, Dr2, Di2, Gr2, Gi2, zr2, zi2, zr, zi, steps_in_group, are, aim);
+                        warp_tile<TAPS, false>(&sm.tiles[s][0], body, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
                     else
-                        warp_tile<TAPS, true>(&sm.tiles[s][0], n_tile0, body, step, aux2, tbl_off, Dr2, Di2, Gr2, Gi2, zr2, zi2, zr, zi, steps_in_group, are, aim);
+                        warp_tile<TAPS, true>(&sm.tiles[s][0], body, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
+                    if (++tiles_in_group == kShReseed / 8)
+                        {
+                            // re-seed: the group seed advances by G = exp(j DT 64*kShReseed) and replaces the
+                            // running phasor (bounds the drift of the 64 recurrence steps in between)
+                            const float2 t2 = __fmul2_rn(zi2, Gi2);
+                            const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
+                            zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
+                            zr2 = ngr;
+                            zr = zr2;
+                            zi = zi2;
+                            tiles_in_group = 0;
+                        }
                     __syncwarp();
                 }
             if (lane == 0) mbar_arrive(&sm.empty[s]);
