@@ -96,6 +96,8 @@ _SIGS.update({
     "b200_acq_set_local_code": ([_vp, C.c_uint32, _vp], C.c_int),
     "b200_acq_set_doppler_center": ([_vp, C.c_int32, C.c_int32], C.c_int),
     "b200_acq_search": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
+    "b200_acq_set_step_two": ([_vp, C.c_float, C.c_float, C.c_uint32], C.c_int),
+    "b200_acq_search_step_two": ([_vp, _vp, C.c_uint32, C.c_uint32, C.c_float, _vp], C.c_int),
     "b200_acq_search_dev": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
     "b200_acq_read_grid": ([_vp, C.c_uint32, _vp], C.c_int),
     "b200_acq_read_wipeoffs": ([_vp, _vp], C.c_int),
@@ -310,6 +312,16 @@ class PcpsAcquisition:
         _chk(lib.b200_acq_search(self.h, iq.ctypes.data, slots.ctypes.data, slots.size, dwell_counter, res.ctypes.data),
              "b200_acq_search")
         return res
+
+    def set_step_two(self, center: float, step2: float, bins2: int):
+        _chk(lib.b200_acq_set_step_two(self.h, center, step2, bins2), "b200_acq_set_step_two")
+
+    def search_step_two(self, iq, slot: int, prev_input_power: float, dwell_counter: int = 1) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, np.complex64)
+        res = np.zeros(1, ACQ_RESULT_DTYPE)
+        _chk(lib.b200_acq_search_step_two(self.h, iq.ctypes.data, slot, dwell_counter, prev_input_power, res.ctypes.data),
+             "b200_acq_search_step_two")
+        return res[0]
 
     def search_dev(self, in_dev_ptr: int, slots, results_dev_ptr: int, dwell_counter: int = 1):
         slots = np.ascontiguousarray(slots, np.uint32)

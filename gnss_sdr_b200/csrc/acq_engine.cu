@@ -38,6 +38,9 @@ struct b200_acq
     float2* in_dev{nullptr};   // consumed
     float2* code_stage{nullptr};
     float* grid{nullptr};      // slots x bins x ne (optional)
+    float2* wipe2{nullptr};    // step-two wipe-offs (bins2 x n)
+    float center2{0.f}, step2{0.f};
+    uint32_t bins2{0};
     AcqRowStat* rowstat{nullptr};
     int* slot_list{nullptr};
     void* best{nullptr};
@@ -51,7 +54,7 @@ struct b200_acq
 namespace
 {
 int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32_t n_slots, uint32_t dwell_counter,
-    b200_acq_result* results_dev)
+    b200_acq_result* results_dev, int step_two = 0, float prev_input_power = 0.f)
 {
     const b200_acq_conf& c = a->c;
     if (n_slots == 0) return B200_OK;
@@ -74,16 +77,22 @@ int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32
     cudaStream_t st = a->stream;
     B200_CUDA_TRY(cudaMemcpyAsync(a->slot_list, a->slot_pin, sizeof(int) * n_slots, cudaMemcpyHostToDevice, st));
     const int n = static_cast<int>(c.fft_size);
-    const int bins = static_cast<int>(c.num_doppler_bins);
+    if (step_two && (a->bins2 == 0 || !a->wipe2 || n_slots != 1))
+        {
+            set_error("step two needs b200_acq_set_step_two first and exactly one slot");
+            return B200_ERR_STATE;
+        }
+    const int bins = step_two ? static_cast<int>(a->bins2) : static_cast<int>(c.num_doppler_bins);
+    const float2* wipe = step_two ? a->wipe2 : a->wipe;
     const int ne = static_cast<int>(c.effective_fft_size);
     const int off = c.bit_transition_flag ? ne : 0;
-    int rc = acq_launch_fwd(in_dev, static_cast<int>(c.consumed_samples), a->wipe, a->X, bins, a->plan, a->tw, st);
+    int rc = acq_launch_fwd(in_dev, static_cast<int>(c.consumed_samples), wipe, a->X, bins, a->plan, a->tw, st);
     if (rc) return rc;
     rc = acq_launch_corr(a->X, a->codes, a->slot_list, static_cast<int>(n_slots), bins, a->plan, a->tw, off, ne, a->rowstat, a->grid,
         dwell_counter > 1 ? 1 : 0, 0, nullptr, 0, nullptr, st);
     if (rc) return rc;
     rc = acq_launch_stats(a->rowstat, static_cast<int>(n_slots), bins, ne, c.doppler_max, a->doppler_center, c.doppler_step,
-        dwell_counter, c.use_cfar, a->best, results_dev, st);
+        dwell_counter, c.use_cfar, a->best, results_dev, step_two, a->center2, a->step2, prev_input_power, st);
     if (rc) return rc;
     uint64_t launched = 3;
     if (!c.use_cfar)
@@ -169,7 +178,7 @@ extern "C"
             }
         rc = acq_launch_twiddles(a->tw, a->plan, a->stream);
         if (rc) return rc;
-        rc = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, a->stream);
+        rc = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, 0, 0.f, 0.f, a->stream);
         if (rc) return rc;
         B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
         *out = a;
@@ -199,7 +208,7 @@ extern "C"
         a->doppler_bias = doppler_bias;
         const b200_acq_conf& c = a->c;
         int rc = acq_launch_wipeoff(a->wipe, static_cast<int>(c.fft_size), static_cast<int>(c.num_doppler_bins), c.doppler_max,
-            doppler_center, c.doppler_step, doppler_bias, c.fs_in, a->stream);
+            doppler_center, c.doppler_step, doppler_bias, c.fs_in, 0, 0.f, 0.f, a->stream);
         if (rc) return rc;
         B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
         return B200_OK;
@@ -216,6 +225,45 @@ extern "C"
         B200_CUDA_TRY(cudaMemcpyAsync(a->results_pin, a->results_dev, sizeof(b200_acq_result) * n_slots, cudaMemcpyDeviceToHost, a->stream));
         B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
         std::memcpy(results_host, a->results_pin, sizeof(b200_acq_result) * n_slots);
+        return B200_OK;
+    }
+
+    int b200_acq_set_step_two(b200_acq* a, float doppler_center_step_two, float doppler_step2, uint32_t num_doppler_bins_step2)
+    {
+        if (!a || num_doppler_bins_step2 < 1) return B200_ERR_ARG;
+        if (num_doppler_bins_step2 > a->c.num_doppler_bins)
+            {
+                set_error("step-two bins %u exceed the grid's %u rows", num_doppler_bins_step2, a->c.num_doppler_bins);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        if (!a->wipe2 || a->bins2 < num_doppler_bins_step2)
+            {
+                B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+                if (a->wipe2) B200_CUDA_TRY(cudaFree(a->wipe2));
+                B200_CUDA_TRY(cudaMalloc(&a->wipe2, sizeof(float2) * a->c.fft_size * num_doppler_bins_step2));
+            }
+        a->bins2 = num_doppler_bins_step2;
+        a->center2 = doppler_center_step_two;
+        a->step2 = doppler_step2;
+        int rc = acq_launch_wipeoff(a->wipe2, static_cast<int>(a->c.fft_size), static_cast<int>(a->bins2), 0, 0, 0, a->doppler_bias, a->c.fs_in, 1,
+            doppler_center_step_two, doppler_step2, a->stream);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return B200_OK;
+    }
+
+    int b200_acq_search_step_two(b200_acq* a, const b200_cf32* in_host, uint32_t slot, uint32_t dwell_counter, float prev_input_power,
+        b200_acq_result* result_host)
+    {
+        if (!a || !in_host || !result_host) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_CUDA_TRY(cudaMemcpyAsync(a->in_dev, in_host, sizeof(float2) * a->c.consumed_samples, cudaMemcpyHostToDevice, a->stream));
+        int rc = search_impl(a, a->in_dev, &slot, 1, dwell_counter, a->results_dev, 1, prev_input_power);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaMemcpyAsync(a->results_pin, a->results_dev, sizeof(b200_acq_result), cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        *result_host = a->results_pin[0];
         return B200_OK;
     }
 
@@ -260,6 +308,7 @@ extern "C"
         if (a->stream) cudaStreamSynchronize(a->stream);
         cudaFree(a->tw);
         cudaFree(a->wipe);
+        cudaFree(a->wipe2);
         cudaFree(a->X);
         cudaFree(a->codes);
         cudaFree(a->in_dev);

@@ -87,14 +87,24 @@ __device__ __forceinline__ float2 cephes_sincos(float p)
 // grid: bins blocks of 32 threads; lanes 0..7 carry the eight float32 phase accumulators of the
 // AVX2 kernel (p_l = phase + l*inc, advanced by fl(8*inc) per iteration); lane 0 does the tail.
 __global__ void acq_wipeoff_kernel(float2* __restrict__ wipe, int n, int bins, int doppler_max, int doppler_center,
-    int doppler_step, int doppler_bias, long long fs_in)
+    int doppler_step, int doppler_bias, long long fs_in, int step_two, float center2, float step2)
 {
     const int d = blockIdx.x;
     const int lane = threadIdx.x;
     if (d >= bins || lane >= 8) return;
-    // pcps_acquisition.cc:288-289 and :277-278
-    const int doppler = -doppler_max + doppler_center + doppler_step * d;
-    const float freq = static_cast<float>(doppler_bias + doppler);
+    float freq;
+    if (!step_two)
+        {
+            // pcps_acquisition.cc:288-289 and :277-278
+            const int doppler = -doppler_max + doppler_center + doppler_step * d;
+            freq = static_cast<float>(doppler_bias + doppler);
+        }
+    else
+        {
+            // update_grid_doppler_wipeoffs_step2 (:294-301): float Doppler around the step-one estimate
+            const float doppler = __fmul_rn(__fsub_rn(static_cast<float>(d), static_cast<float>(floor(bins / 2.0))), step2);
+            freq = __fadd_rn(center2, doppler);
+        }
     const float phase_step_rad = __fdiv_rn(__fmul_rn(static_cast<float>(6.283185307179586), freq), static_cast<float>(fs_in));
     const float inc = -phase_step_rad;
     const int iters = n / 8;
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* 
 // one thread per searched PRN (bins <= a few hundred): pcps_acquisition.cc:417-449 / :464-482
 __global__ void acq_stats_kernel(const AcqRowStat* __restrict__ rowstat, int n_slots, int bins, int ne, int doppler_max,
     int doppler_center, int doppler_step, unsigned int dwell_counter, int use_cfar, AcqBest* __restrict__ best,
-    b200_acq_result* __restrict__ results)
+    b200_acq_result* __restrict__ results, int step_two, float center2, float step2, float prev_input_power)
 {
     const int sp = blockIdx.x * blockDim.x + threadIdx.x;
     if (sp >= n_slots) return;
@@ -381,12 +391,21 @@ __global__ void acq_stats_kernel(const AcqRowStat* __restrict__ rowstat, int n_s
     b200_acq_result r;
     r.index_time = index_time;
     r.index_doppler = index_doppler;
-    r.doppler = -doppler_max + doppler_center + doppler_step * static_cast<int>(index_doppler);
+    if (!step_two)
+        r.doppler = -doppler_max + doppler_center + doppler_step * static_cast<int>(index_doppler);
+    else  // (:436, :480) static_cast<int32_t>(center2 + (float(index) - float(floor(bins2 / 2.0))) * step2)
+        r.doppler = static_cast<int>(__fadd_rn(center2, __fmul_rn(__fsub_rn(static_cast<float>(index_doppler), static_cast<float>(floor(bins / 2.0))), step2)));
     r.grid_maximum = grid_maximum;
     r.test_statistics = 0.0f;
     r.input_power = 0.0f;
     r.second_peak = 0.0f;
-    if (use_cfar)
+    if (use_cfar && step_two)
+        {
+            // the second step keeps d_input_power from the first one (:428-438)
+            r.input_power = prev_input_power;
+            r.test_statistics = (prev_input_power < 1.1920929e-07f) ? 0.0f : __fdiv_rn(grid_maximum, prev_input_power);
+        }
+    else if (use_cfar)
         {
             const unsigned int index_opp = (index_doppler + static_cast<unsigned int>(bins) / 2u) % static_cast<unsigned int>(bins);
             // static_cast<float>(accumulate(...) / N_eff / 2.0 / counter)   (:431)
@@ -493,9 +512,9 @@ int acq_launch_twiddles(float2* tw, const FftPlan& pl, cudaStream_t st)
 }
 
 int acq_launch_wipeoff(float2* wipe, int n, int bins, int doppler_max, int doppler_center, int doppler_step,
-    int doppler_bias, long long fs_in, cudaStream_t st)
+    int doppler_bias, long long fs_in, int step_two, float center2, float step2, cudaStream_t st)
 {
-    acq_wipeoff_kernel<<<bins, 32, 0, st>>>(wipe, n, bins, doppler_max, doppler_center, doppler_step, doppler_bias, fs_in);
+    acq_wipeoff_kernel<<<bins, 32, 0, st>>>(wipe, n, bins, doppler_max, doppler_center, doppler_step, doppler_bias, fs_in, step_two, center2, step2);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }
@@ -532,10 +551,11 @@ int acq_launch_corr(const float2* X, const float2* codes, const int* slot_list, 
 }
 
 int acq_launch_stats(const AcqRowStat* rowstat, int n_slots, int bins, int ne, int doppler_max, int doppler_center,
-    int doppler_step, unsigned int dwell_counter, int use_cfar, void* best, b200_acq_result* results, cudaStream_t st)
+    int doppler_step, unsigned int dwell_counter, int use_cfar, void* best, b200_acq_result* results, int step_two, float center2,
+    float step2, float prev_input_power, cudaStream_t st)
 {
     acq_stats_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(rowstat, n_slots, bins, ne, doppler_max, doppler_center, doppler_step,
-        dwell_counter, use_cfar, static_cast<AcqBest*>(best), results);
+        dwell_counter, use_cfar, static_cast<AcqBest*>(best), results, step_two, center2, step2, prev_input_power);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }

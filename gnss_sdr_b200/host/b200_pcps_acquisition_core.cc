@@ -63,6 +63,8 @@ Pcps_Acquisition_Core::Pcps_Acquisition_Core(const Acq_Conf_Core& conf_)
 {
     // :113-114
     d_threshold = conf_.pfa > 0.0 ? compute_threshold(conf_.pfa, d_effective_fft_size, d_num_doppler_bins, conf_.bit_transition_flag ? 1 : conf_.max_dwells) : conf_.threshold;
+    // :117
+    d_threshold_step_two = conf_.pfa2 > 0.0 ? compute_threshold(conf_.pfa2, d_effective_fft_size, conf_.num_doppler_bins_step2, conf_.bit_transition_flag ? 1 : conf_.max_dwells) : conf_.threshold;
     b200_engine* eng = shared_engine();
     if (eng == nullptr) return;
     b200_acq_conf c{};
@@ -126,6 +128,7 @@ void Pcps_Acquisition_Core::init()
     d_input_power = 0.0F;
     d_num_noncoherent_integrations_counter = 0U;
     d_state = 1;
+    d_step_two = false;
 }
 
 
@@ -147,12 +150,15 @@ int Pcps_Acquisition_Core::acquisition_core(const std::complex<float>* in, uint6
     const uint32_t slot = 0;
     b200_acq_result r{};
     // doppler_grid + compute_statistics (:680-682) on the device
-    if (b200_acq_search(d_acq, reinterpret_cast<const b200_cf32*>(in), &slot, 1, d_num_noncoherent_integrations_counter, &r) != B200_OK)
+    const int rc = d_step_two ? b200_acq_search_step_two(d_acq, reinterpret_cast<const b200_cf32*>(in), slot, d_num_noncoherent_integrations_counter, d_input_power, &r)
+                              : b200_acq_search(d_acq, reinterpret_cast<const b200_cf32*>(in), &slot, 1, d_num_noncoherent_integrations_counter, &r);
+    if (rc != B200_OK)
         {
             // a GPU failure surfaces as a negative acquisition, never as exit()
             d_num_noncoherent_integrations_counter = 0;
             d_active = false;
             d_state = 0;
+            d_step_two = false;
             return 2;
         }
     AcquisitionResult result;
@@ -160,46 +166,59 @@ int Pcps_Acquisition_Core::acquisition_core(const std::complex<float>* in, uint6
     result.doppler = r.doppler;
     result.test_statistics = r.test_statistics;
     result.sample_count = sample_count;
-    d_input_power = r.input_power;
+    if (!d_step_two) d_input_power = r.input_power;  // the second step keeps the first step's value (:428-438)
     update_synchro(result);  // :686
+    if (d_step_two && d_gnss_synchro != nullptr) d_gnss_synchro->Acq_doppler_step = static_cast<uint32_t>(d_acq_parameters.doppler_step2);  // :598-601
 
     int event = 0;
-    // :688-715, make_2_steps == false
+    // handle_threshold_reached (:605-636)
+    auto threshold_reached = [&]() {
+        d_state = 0;
+        if (d_acq_parameters.make_2_steps)
+            {
+                if (d_step_two)
+                    {
+                        result.positive_acq = true;
+                        d_active = false;
+                        event = 1;
+                    }
+                else
+                    {
+                        d_doppler_center_step_two = static_cast<float>(result.doppler);
+                        b200_acq_set_step_two(d_acq, d_doppler_center_step_two, d_acq_parameters.doppler_step2, d_acq_parameters.num_doppler_bins_step2);
+                        d_num_noncoherent_integrations_counter = 0;
+                    }
+                d_step_two = !d_step_two;
+            }
+        else
+            {
+                result.positive_acq = true;
+                d_active = false;
+                event = 1;
+            }
+    };
+    // handle_integration_done (:639-645)
+    auto integration_done = [&]() {
+        if (d_state != 0) event = 2;
+        d_active = false;
+        d_state = 0;
+        d_step_two = false;
+    };
+    const float th = get_threshold();
     if (!d_acq_parameters.bit_transition_flag)
         {
-            if (result.test_statistics > d_threshold)
-                {
-                    d_state = 0;
-                    result.positive_acq = true;
-                    d_active = false;
-                    event = 1;
-                }
+            if (result.test_statistics > th)
+                threshold_reached();
             else
-                {
-                    d_state = 1;
-                }
-            if (d_num_noncoherent_integrations_counter == d_acq_parameters.max_dwells)
-                {
-                    if (d_state != 0) event = 2;
-                    d_active = false;
-                    d_state = 0;
-                }
+                d_state = 1;
+            if (d_num_noncoherent_integrations_counter == d_acq_parameters.max_dwells) integration_done();
         }
     else
         {
             if (result.test_statistics > d_threshold)
-                {
-                    d_state = 0;
-                    result.positive_acq = true;
-                    d_active = false;
-                    event = 1;
-                }
+                threshold_reached();
             else
-                {
-                    if (d_state != 0) event = 2;
-                    d_active = false;
-                    d_state = 0;
-                }
+                integration_done();
         }
     // :717-725
     if ((d_num_noncoherent_integrations_counter == d_acq_parameters.max_dwells) || result.positive_acq || d_acq_parameters.bit_transition_flag)

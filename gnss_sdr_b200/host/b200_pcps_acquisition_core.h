@@ -40,6 +40,10 @@ struct Acq_Conf_Core
     float threshold{0.0F};
     bool bit_transition_flag{false};
     bool use_CFAR_algorithm_flag{true};
+    bool make_2_steps{false};             // acq_conf.h:74
+    float doppler_step2{125.0F};          // :50
+    uint32_t num_doppler_bins_step2{4U};  // :62
+    float pfa2{0.0F};
     bool dump{false};  // keeps the magnitude grid on the device so read_grid() works
 };
 
@@ -77,7 +81,7 @@ public:
     void set_local_code(std::complex<float>* code);
     void set_doppler_center(int32_t doppler_center);
     void set_threshold(float threshold) { d_threshold = threshold; }
-    float get_threshold() const { return d_threshold; }
+    float get_threshold() const { return d_step_two ? d_threshold_step_two : d_threshold; }  // :731-734
     void set_active(bool active);
     void init();  // pcps_acquisition::init (:196-215): reset counters and synchro fields
     uint32_t mag() const { return 0; }
@@ -102,6 +106,9 @@ private:
     b200_acq* d_acq{nullptr};
     Acq_Synchro* d_gnss_synchro{nullptr};
     float d_threshold{0.0F};
+    float d_threshold_step_two{0.0F};
+    float d_doppler_center_step_two{0.0F};
+    bool d_step_two{false};
     int32_t d_doppler_center{0};
     uint32_t d_num_noncoherent_integrations_counter{0};
     int d_state{0};

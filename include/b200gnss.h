@@ -190,6 +190,15 @@ extern "C"
      * results[i] belongs to slots[i].  Synchronous (input H2D, kernels, results D2H). */
     int b200_acq_search(b200_acq* a, const b200_cf32* in_host, const uint32_t* slots, uint32_t n_slots,
         uint32_t dwell_counter, b200_acq_result* results_host);
+    /* Two-step acquisition (Acq_Conf::make_2_steps, pcps_acquisition.cc:294-301,:609-625): after a
+     * positive first step the block re-searches num_doppler_bins_step2 bins spaced doppler_step2 around
+     * the step-one Doppler on the NEXT buffer of samples.  set_step_two = d_doppler_center_step_two +
+     * update_grid_doppler_wipeoffs_step2(); search_step_two = doppler_grid + compute_statistics with
+     * d_step_two == true (Doppler from the float formula :436/:480, CFAR input power carried over from
+     * step one :428-438).  One PRN slot per call. */
+    int b200_acq_set_step_two(b200_acq* a, float doppler_center_step_two, float doppler_step2, uint32_t num_doppler_bins_step2);
+    int b200_acq_search_step_two(b200_acq* a, const b200_cf32* in_host, uint32_t slot, uint32_t dwell_counter,
+        float prev_input_power, b200_acq_result* result_host);
     /* same with the input already on the device and results left on the device (asynchronous) */
     int b200_acq_search_dev(b200_acq* a, const b200_cf32* in_dev, const uint32_t* slots_host, uint32_t n_slots,
         uint32_t dwell_counter, b200_acq_result* results_dev);

@@ -47,6 +47,10 @@ class AcqConf:
     threshold: float = 0.0
     bit_transition_flag: bool = False
     use_CFAR_algorithm_flag: bool = True
+    make_2_steps: bool = False
+    doppler_step2: float = 125.0
+    num_doppler_bins_step2: int = 4
+    pfa2: float = 0.0
 
     def __post_init__(self):
         # pcps_acquisition.cc:107-113
@@ -83,6 +87,11 @@ class PcpsAcquisitionOracle:
         self.threshold = (compute_threshold(conf.pfa, conf.effective_fft_size, conf.num_doppler_bins,
                                             1 if conf.bit_transition_flag else conf.max_dwells)
                           if conf.pfa > 0.0 else conf.threshold)
+        self.threshold_step_two = (compute_threshold(conf.pfa2, conf.effective_fft_size, conf.num_doppler_bins_step2,
+                                                     1 if conf.bit_transition_flag else conf.max_dwells)
+                                   if conf.pfa2 > 0.0 else conf.threshold)
+        self.step_two = False
+        self.doppler_center_step_two = np.float32(0.0)
         self.magnitude_grid = np.zeros((conf.num_doppler_bins, conf.fft_size), np.float32)
         self.num_noncoherent_integrations_counter = 0
         self.input_power = np.float32(0.0)
@@ -99,6 +108,16 @@ class PcpsAcquisitionOracle:
                                                C.c_int32(self.doppler_center), C.c_int32(c.doppler_step),
                                                C.c_int32(self.doppler_bias), C.c_int64(c.fs_in))
         self.grid_doppler_wipeoffs = out
+
+    # pcps_acquisition.cc:294-301
+    def update_grid_doppler_wipeoffs_step2(self):
+        c = self.c
+        out = np.empty((c.num_doppler_bins_step2, c.fft_size), np.complex64)
+        self.o.port.lib.port_acq_wipeoff_grid_step2(C.c_int(0 if self.sincos_variant == "generic" else 1),
+                                                    C.c_void_p(out.ctypes.data), C.c_uint(c.fft_size),
+                                                    C.c_uint(c.num_doppler_bins_step2), C.c_float(float(self.doppler_center_step_two)),
+                                                    C.c_float(c.doppler_step2), C.c_int64(c.fs_in))
+        self.grid_doppler_wipeoffs_step_two = out
 
     def set_doppler_center(self, center: int):
         self.doppler_center = int(center)
@@ -123,16 +142,18 @@ class PcpsAcquisitionOracle:
         c = self.c
         off = c.effective_fft_size if c.bit_transition_flag else 0
         # volk_32fc_x2_multiply_32fc (float32 complex multiply), all bins at once
-        x = (inp[None, :] * self.grid_doppler_wipeoffs).astype(np.complex64)
+        wipe = self.grid_doppler_wipeoffs_step_two if self.step_two else self.grid_doppler_wipeoffs
+        nb = wipe.shape[0]
+        x = (inp[None, :] * wipe).astype(np.complex64)
         X = sfft.fft(x, axis=1, workers=self.workers)
         Y = (X * self.fft_codes[None, :]).astype(np.complex64)
         y = sfft.ifft(Y, axis=1, norm="forward", workers=self.workers)   # unnormalised backward transform
         y = y[:, off:off + c.effective_fft_size]
         mag = (y.real.astype(np.float32) ** 2 + y.imag.astype(np.float32) ** 2).astype(np.float32)
         if self.num_noncoherent_integrations_counter == 1:
-            self.magnitude_grid[:, :c.effective_fft_size] = mag
+            self.magnitude_grid[:nb, :c.effective_fft_size] = mag
         else:
-            self.magnitude_grid[:, :c.effective_fft_size] += mag
+            self.magnitude_grid[:nb, :c.effective_fft_size] += mag
 
     def _grid_max(self):
         """the arg-max scan shared by both statistics (:417-426 / :464-473): per-bin first
@@ -141,7 +162,8 @@ class PcpsAcquisitionOracle:
         grid_maximum = np.float32(0.0)
         index_doppler = 0
         index_time = 0
-        g = self.magnitude_grid[:, :c.effective_fft_size]
+        nb = c.num_doppler_bins_step2 if self.step_two else c.num_doppler_bins
+        g = self.magnitude_grid[:nb, :c.effective_fft_size]
         idx = np.argmax(g, axis=1)     # numpy argmax returns the FIRST maximum, as the generic kernel
         for i in range(g.shape[0]):
             v = g[i, idx[i]]
@@ -151,17 +173,25 @@ class PcpsAcquisitionOracle:
                 index_time = int(idx[i])
         return grid_maximum, index_doppler, index_time
 
+    def _doppler_step_two(self, index_doppler):
+        # (:436 / :480) static_cast<int32_t>(center2 + (float(idx) - float(floor(bins2/2.0))) * step2)
+        c = self.c
+        off = np.float32(np.float32(index_doppler) - np.float32(math.floor(c.num_doppler_bins_step2 / 2.0))) * np.float32(c.doppler_step2)
+        return int(np.float32(self.doppler_center_step_two) + np.float32(off))
+
     # pcps_acquisition.cc:409-449
     def max_to_input_power_statistic(self):
         c = self.c
         grid_maximum, index_doppler, index_time = self._grid_max()
-        index_opp = (index_doppler + c.num_doppler_bins // 2) % c.num_doppler_bins
-        row = self.magnitude_grid[index_opp, :c.effective_fft_size]
-        acc = np.float32(0.0)
-        # std::accumulate with a float init: strictly sequential float32 sum
-        acc = np.float32(_seq_sum_f32(row))
-        self.input_power = np.float32(float(acc) / c.effective_fft_size / 2.0 / self.num_noncoherent_integrations_counter)
-        doppler = -int(c.doppler_max) + self.doppler_center + c.doppler_step * int(index_doppler)
+        if not self.step_two:
+            index_opp = (index_doppler + c.num_doppler_bins // 2) % c.num_doppler_bins
+            row = self.magnitude_grid[index_opp, :c.effective_fft_size]
+            # std::accumulate with a float init: strictly sequential float32 sum
+            acc = np.float32(_seq_sum_f32(row))
+            self.input_power = np.float32(float(np.float32(acc / np.float32(c.effective_fft_size))) / 2.0 / self.num_noncoherent_integrations_counter)
+            doppler = -int(c.doppler_max) + self.doppler_center + c.doppler_step * int(index_doppler)
+        else:
+            doppler = self._doppler_step_two(index_doppler)
         if self.input_power < np.finfo(np.float32).eps:
             stat = np.float32(0.0)
         else:
@@ -173,7 +203,10 @@ class PcpsAcquisitionOracle:
     def first_vs_second_peak_statistic(self):
         c = self.c
         first_peak, index_doppler, index_time = self._grid_max()
-        doppler = -int(c.doppler_max) + self.doppler_center + c.doppler_step * int(index_doppler)
+        if not self.step_two:
+            doppler = -int(c.doppler_max) + self.doppler_center + c.doppler_step * int(index_doppler)
+        else:
+            doppler = self._doppler_step_two(index_doppler)
         n = c.effective_fft_size
         ex1 = index_time - c.samples_per_chip
         ex2 = index_time + c.samples_per_chip
@@ -206,7 +239,22 @@ class PcpsAcquisitionOracle:
         # update_synchro :580-584
         res["acq_delay_samples"] = float(np.fmod(np.float32(res["index_time"]), np.float32(c.samples_per_code)))
         res["acq_doppler_hz"] = float(res["doppler"])
-        res["positive"] = bool(res["test_statistics"] > self.threshold)
+        th = self.threshold_step_two if self.step_two else self.threshold
+        above = bool(res["test_statistics"] > th)
+        res["step_two"] = self.step_two
+        res["positive"] = above
+        if above and c.make_2_steps:
+            # handle_threshold_reached (:605-626)
+            if self.step_two:
+                res["positive"] = True
+            else:
+                res["positive"] = False
+                self.doppler_center_step_two = np.float32(res["doppler"])
+                self.update_grid_doppler_wipeoffs_step2()
+                self.num_noncoherent_integrations_counter = 0
+            self.step_two = not self.step_two
+        elif self.num_noncoherent_integrations_counter == c.max_dwells:
+            self.step_two = False   # handle_integration_done (:639-645)
         if res["positive"] or self.num_noncoherent_integrations_counter == c.max_dwells or c.bit_transition_flag:
             self.num_noncoherent_integrations_counter = 0
         return res

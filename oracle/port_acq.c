@@ -181,3 +181,23 @@ float port_seq_sum_f32(const float* src, unsigned int n)
     for (unsigned int i = 0; i < n; i++) acc += src[i];
     return acc;
 }
+
+/* pcps_acquisition.cc:294-301 update_grid_doppler_wipeoffs_step2: float Doppler offsets around the
+ * step-one estimate, doppler = (float(idx) - float(floor(bins2/2.0))) * step2, carrier frequency
+ * center2 + doppler (no FDMA bias in this branch upstream). */
+int port_acq_wipeoff_grid_step2(int variant, float* out_iq, unsigned int n, unsigned int bins2, float center2, float step2, int64_t fs_in)
+{
+    for (unsigned int d = 0; d < bins2; d++)
+        {
+            const float doppler = ((float)d - (float)floor(bins2 / 2.0)) * step2;
+            const float freq = center2 + doppler;
+            const float phase_step_rad = (float)6.283185307179586 * freq / (float)fs_in;
+            float ph = 0.0f;
+            float* row = out_iq + (size_t)2 * n * d;
+            if (variant == 0)
+                port_sincos_generic(row, -phase_step_rad, &ph, n);
+            else
+                port_sincos_avx2(row, -phase_step_rad, &ph, n);
+        }
+    return 0;
+}

@@ -257,3 +257,31 @@ def test_acq_error_paths(capi, engine):
     with pytest.raises(capi.B200Error):   # dwell accumulation without a grid
         acq.search(np.zeros(4000, np.complex64), [0], dwell_counter=2)
     acq.close()
+
+
+def test_two_step_acquisition(capi, engine, oracle):
+    """make_2_steps (pcps_acquisition.cc:294-301,:605-626): the second step searches 4 bins of 125 Hz
+    around the first step's Doppler on the next buffer, keeps the first step's input power, and uses the
+    float Doppler formula."""
+    from oracle.acq_np import AcqConf, PcpsAcquisitionOracle
+    fs, prn = 4e6, 8
+    iq, svs = _signal(oracle, [prn], fs, 8000, seed=88, cn0=47.0)
+    conf = AcqConf(fs_in=int(fs), samples_per_ms=4000.0, samples_per_code=4000.0, samples_per_chip=3, doppler_max=5000,
+                   doppler_step=500, pfa=0.001, pfa2=0.001, make_2_steps=True, doppler_step2=125.0, num_doppler_bins_step2=4)
+    o = PcpsAcquisitionOracle(conf)
+    code = oracle.port.gps_ca_code_complex_sampled(prn, int(fs))
+    o.set_local_code(code)
+    w1 = o.acquisition_core(iq[:4000])
+    assert not w1["positive"] and o.step_two          # first step passed the threshold, second pending
+    w2 = o.acquisition_core(iq[4000:8000])
+    assert w2["positive"] and w2["step_two"]
+    acq = capi.PcpsAcquisition(engine, fs_in=int(fs), samples_per_ms=4000.0, samples_per_chip=3, doppler_max=5000, doppler_step=500)
+    acq.set_local_code(0, code)
+    g1 = acq.search(iq[:4000], [0])[0]
+    assert (int(g1["index_time"]), int(g1["doppler"])) == (w1["index_time"], w1["doppler"])
+    acq.set_step_two(float(g1["doppler"]), 125.0, 4)
+    g2 = acq.search_step_two(iq[4000:8000], 0, float(g1["input_power"]))
+    assert (int(g2["index_time"]), int(g2["index_doppler"]), int(g2["doppler"])) == (w2["index_time"], w2["index_doppler"], w2["doppler"])
+    assert abs(g2["test_statistics"] - w2["test_statistics"]) / w2["test_statistics"] < 1e-4
+    assert abs(w2["doppler"] - svs[0]["doppler"]) < abs(w1["doppler"] - svs[0]["doppler"]) + 63   # refined (within half a fine bin)
+    acq.close()
