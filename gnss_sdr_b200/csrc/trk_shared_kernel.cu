@@ -25,7 +25,13 @@ namespace b200
 {
 constexpr int kShK = 8;          // items (consumer warps) per CTA
 constexpr int kShTile = 512;     // samples per tile (4 KB)
-constexpr int kShStages = 4;
+#ifndef SH_STAGES
+#define SH_STAGES 4
+#endif
+#ifndef SH_MINB
+#define SH_MINB 3
+#endif
+constexpr int kShStages = SH_STAGES;
 constexpr int kShTblCap = 1152;  // floats per warp-private extended code table
 constexpr int kShThreads = (kShK + 1) * 32;
 constexpr int kShReseed = 64;    // 64-sample steps between exact phasor re-seeds (4096 samples)
@@ -170,7 +176,7 @@ __device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int b
 }
 
 template <int TAPS>
-__global__ void __launch_bounds__(kShThreads, 3) trk_shared_kernel(const b200_trk_item* __restrict__ items, int n_items,
+__global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b200_trk_item* __restrict__ items, int n_items,
     const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, float2* __restrict__ out, int out_stride)
 {
     extern __shared__ __align__(128) unsigned char sh_raw[];
