@@ -563,14 +563,14 @@ def main():
     peak, peak_src = measured_peak_gbs()
     launch_ms = float(np.mean(per_launch_ms))
     achieved = ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE / (launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "trk_correlate_kernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "trk_shared_kernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "algorithmic_bytes_per_launch": ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE,
                 "launch_ms": launch_ms, "peak_source": peak_src,
-                "note": "algorithmic bytes = 8 B per channel-sample (SURVEY 8d); the 32 channels share one IQ stream, so DRAM "
-                        "traffic (the `traffic` field, from ncu) is ~1/32 of that: the stream is read from HBM once and the "
-                        "algorithmic bytes are served L2->SM at ~6.7-6.9 TB/s (ncu l1tex__m_xbar2l1tex_read_bytes = 6.43 GB per "
-                        "launch), the chip's L2 fabric cap; frac > 1 against the HBM copy peak is therefore possible, see DESIGN.md"}
+                "note": "algorithmic bytes = 8 B per channel-sample (SURVEY 8d) = what 32 independent per-channel correlators read; "
+                        "the 32 channels share one IQ stream, so DRAM traffic (`traffic`, from ncu) is the 200 MB stream read once and "
+                        "the shared-window kernel stages each tile once per 8 items (L2->SM 0.87 GB per launch): frac > 1 against the HBM "
+                        "copy peak is expected; the kernel is bound by FP32 instruction issue (ncu: issue 68 %, FMA pipe 67 %), see DESIGN.md 4.2"}
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_baseline()
