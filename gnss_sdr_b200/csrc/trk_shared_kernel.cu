@@ -32,7 +32,7 @@ constexpr int kShTile = 512;     // samples per tile (4 KB)
 #define SH_MINB 3
 #endif
 constexpr int kShStages = SH_STAGES;
-constexpr int kShTblCap = 1152;  // floats per warp-private extended code table
+constexpr int kShWin = 256;      // floats of the warp-private code-replica window (refilled per tile)
 constexpr int kShThreads = (kShK + 1) * 32;
 constexpr int kShReseed = 64;    // 64-sample steps between exact phasor re-seeds (4096 samples)
 
@@ -41,7 +41,7 @@ namespace
 struct __align__(128) ShSmem
 {
     float2 tiles[kShStages][kShTile];
-    float tbl[kShK][kShTblCap];
+    float win[kShK][kShWin];
     unsigned long long full[kShStages];
     unsigned long long empty[kShStages];
     unsigned long long item_start[kShK];  // offset of the item's first sample in the band (band-relative)
@@ -120,9 +120,9 @@ __device__ void warp_correlate_general(const b200_trk_item& it, const ChanDesc& 
 // (2l, 2l+1) of every step.  fa/fb (sample index within the epoch, as floats) and the running phasors
 // are lane state that continues seamlessly from tile to tile (tiles are contiguous).
 // MASKED = the tile sticks out of [0, body): samples outside contribute zero and evaluate the chip
-// index at n = 0 / 1 (inside the table).
+// index of the nearest sample inside (always within the code window).
 template <int TAPS, bool MASKED>
-__device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int body, float step, const float2 (&aux2)[TAPS],
+__device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, float vlo, float vhi, float step, const float2 (&aux2)[TAPS],
     unsigned int tbl_off, float2 Dr2, float2 Di2, float& fa, float& fb, float2& zr, float2& zi, float2 (&are)[TAPS], float2 (&aim)[TAPS])
 {
     const int lane = threadIdx.x & 31;
@@ -136,19 +136,12 @@ __device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, int b
             float2 xa = make_float2(v.x, v.y), xb = make_float2(v.z, v.w);
             if (MASKED)
                 {
-                    const float bodyf = static_cast<float>(body);
-                    const bool va = (fa >= 0.0f) && (fa < bodyf);   // sample indices are exact in float (< 2^24)
-                    const bool vb = (fb >= 0.0f) && (fb < bodyf);
-                    if (!va)
-                        {
-                            xa = make_float2(0.f, 0.f);
-                            ua = 0.0f;
-                        }
-                    if (!vb)
-                        {
-                            xb = make_float2(0.f, 0.f);
-                            ub = 1.0f;
-                        }
+                    // [vlo, vhi] = the tile's samples that belong to the epoch (indices are exact in float);
+                    // the others contribute zero and look the chip of the nearest valid sample up
+                    if (fa < vlo || fa > vhi) xa = make_float2(0.f, 0.f);
+                    if (fb < vlo || fb > vhi) xb = make_float2(0.f, 0.f);
+                    ua = fminf(fmaxf(fa, vlo), vhi);
+                    ub = fminf(fmaxf(fb, vlo), vhi);
                 }
             float2 wr2, wi2;
             wr2.x = fmaf(xa.x, zr.x, -xa.y * zi.x);
@@ -302,46 +295,23 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
             const float rem = it.rem_code_phase_chips;
             T0 = turns_from_rad(-static_cast<double>(it.rem_carrier_phase_rad));
             DT = turns_from_rad(-static_cast<double>(it.phase_step_rad));
-            // chip-index range (monotone in n inside each association)
-            long long lo = 0x7fffffff, hi = -0x7fffffff - 1LL;
-            const float nl_avx = static_cast<float>(max(body - 1, 0));
-            const float n_last = static_cast<float>(it.n - 1);
-            const float n_body = static_cast<float>(body);
+            float smin = ch->shifts[0], smax = ch->shifts[0];
 #pragma unroll
             for (int t = 0; t < TAPS; t++)
                 {
                     const float sh = ch->shifts[t];
                     const float a2 = __fsub_rn(sh, rem);
                     aux2[t] = make_float2(a2, a2);
-                    int v[6];
-                    v[0] = chip_index_avx(step, 0.f, a2);
-                    v[1] = chip_index_avx(step, nl_avx, a2);
-                    v[2] = chip_index_generic(step, n_body, sh, rem);
-                    v[3] = chip_index_generic(step, n_last, sh, rem);
-                    v[4] = chip_index_generic(step, 0.f, sh, rem);
-                    v[5] = chip_index_avx(step, 1.f, a2);
-#pragma unroll
-                    for (int q = 0; q < 6; q++)
-                        {
-                            lo = min(lo, static_cast<long long>(v[q]));
-                            hi = max(hi, static_cast<long long>(v[q]));
-                        }
+                    smin = fminf(smin, sh);
+                    smax = fmaxf(smax, sh);
                 }
-            const long long span = hi - lo + 5;
-            table_path = sm.share && !ch->high_dyn && span <= kShTblCap && lo > -4000000LL && hi < 4000000LL;
+            // The code replica is staged per TILE: a tile spans 512*step chips (+ the tap spread), so a
+            // 256-entry window per warp serves any code length (1023-chip C/A, 8184-value E1, 10230-chip L5).
+            const float span_bound = ceilf(fabsf(step) * static_cast<float>(kShTile)) + ceilf(smax - smin) + 6.0f;
+            table_path = sm.share && !ch->high_dyn && span_bound <= static_cast<float>(kShWin) && fabsf(step) * static_cast<float>(it.n) < 4.0e6f &&
+                         fabsf(smax) < 1.0e5f && fabsf(smin) < 1.0e5f && fabsf(rem) < 1.0e6f;
             if (table_path)
                 {
-                    const int base_i = static_cast<int>(lo - 2);
-                    const int L = ch->code_len;
-                    int r = mod_pos(base_i + lane, L);
-                    const int stride = 32 % L;
-                    for (int j = lane; j < static_cast<int>(span); j += 32)
-                        {
-                            sm.tbl[warp][j] = ch->code[r];
-                            r += stride;
-                            if (r >= L) r -= L;
-                        }
-                    asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.tbl[warp][0])), "r"(4u * (static_cast<unsigned int>(base_i) + 0x4B400000u)));
                     a_i = static_cast<int>(sm.item_start[warp] - hull_start);
                     t_first = a_i / kShTile;
                     t_last = (a_i + body + kShTile - 1) / kShTile;
@@ -360,7 +330,6 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
                     zr = zr2;
                     zi = zi2;
                 }
-            __syncwarp();
         }
 
     float2 are[TAPS], aim[TAPS];
@@ -380,10 +349,37 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
                 {
                     const int n_tile0 = t * kShTile - a_i;
                     const bool interior = (n_tile0 >= 0) && (n_tile0 + kShTile <= body);
+                    // samples of this tile that belong to the epoch, and the chips they touch
+                    const int n_lo = max(n_tile0, 0), n_hi = min(n_tile0 + kShTile, body) - 1;
+                    const float vlo = static_cast<float>(n_lo), vhi = static_cast<float>(n_hi);
+                    int wlo = 0x7fffffff, whi = -0x7fffffff - 1;
+#pragma unroll
+                    for (int q = 0; q < TAPS; q++)
+                        {
+                            const int i0 = chip_index_avx(step, vlo, aux2[q].x);
+                            const int i1 = chip_index_avx(step, vhi, aux2[q].x);
+                            wlo = min(wlo, min(i0, i1));
+                            whi = max(whi, max(i0, i1));
+                        }
+                    const int wb = wlo - 1;
+                    const int wspan = min(whi - wlo + 3, kShWin);   // <= kShWin by the span_bound test
+                    {
+                        const int L = ch->code_len;
+                        int r = mod_pos(wb + lane, L);
+                        const int stride = 32 % L;
+                        for (int j = lane; j < wspan; j += 32)
+                            {
+                                sm.win[warp][j] = __ldg(ch->code + r);
+                                r += stride;
+                                if (r >= L) r -= L;
+                            }
+                    }
+                    asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.win[warp][0])), "r"(4u * (static_cast<unsigned int>(wb) + 0x4B400000u)));
+                    __syncwarp();
                     if (interior)
-                        warp_tile<TAPS, false>(&sm.tiles[s][0], body, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
+                        warp_tile<TAPS, false>(&sm.tiles[s][0], vlo, vhi, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
                     else
-                        warp_tile<TAPS, true>(&sm.tiles[s][0], body, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
+                        warp_tile<TAPS, true>(&sm.tiles[s][0], vlo, vhi, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
                     if (++tiles_in_group == kShReseed / 8)
                         {
                             // re-seed: the group seed advances by G = exp(j DT 64*kShReseed) and replaces the
@@ -423,7 +419,7 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
                             for (int t = 0; t < TAPS; t++)
                                 {
                                     const int idx = chip_index_generic(step, static_cast<float>(n), ch->shifts[t], it.rem_code_phase_chips);
-                                    const float c = lds_f32((static_cast<unsigned int>(idx + 0x4B400000) << 2) + tbl_off);
+                                    const float c = __ldg(ch->code + mod_pos(idx, ch->code_len));
                                     acc[t].x = fmaf(wr, c, acc[t].x);
                                     acc[t].y = fmaf(wi, c, acc[t].y);
                                 }
@@ -484,6 +480,6 @@ int launch_trk_shared(const b200_trk_item* items, int n_items, const ChanDesc* c
     return B200_OK;
 }
 
-int trk_shared_max_code_len() { return kShTblCap - kTrkTablePad; }
+int trk_shared_max_code_len() { return 0x7fffffff; }  // the per-tile code window serves any table length
 
 }  // namespace b200

@@ -427,3 +427,67 @@ def test_integer_sample_ingestion_bitexact(capi, engine, oracle, dtype):
         res[name] = e.trk_batch(items, 3)
     assert np.array_equal(res["float"], res["int"])
     assert np.all(np.abs(res["int"]) > 0)
+
+
+@pytest.mark.parametrize("L,taps_shifts,step,n", [
+    (1023, [-0.5, 0.0, 0.5], 0.04092, 25000),
+    (8184, [-1.2, -0.3, 0.0, 0.3, 1.2], 0.08184, 20000),      # Galileo E1 sinBOC table, 5 taps
+    (10230, [-0.5, 0.0, 0.5], 0.2046, 12000),                   # L5-sized table
+    (1023, [0.0], 0.2557, 4001),                                # 1 tap, ragged length
+])
+def test_shared_window_groups_staggered_integer_exact(capi, oracle, L, taps_shifts, step, n):
+    """The shared-window kernel (groups of 8 items served from one TMA-staged copy of the samples):
+    epochs of different channels start at different, odd/even sample offsets (as in a real receiver,
+    where every channel is aligned to its own code period), item count not a multiple of 8, different
+    code tables and code phases per channel.  Integer data => results must be EXACT.  Run with the
+    shared kernel forced on and forced off: both must equal the integer oracle."""
+    import os
+    rng = np.random.default_rng(L + n)
+    n_ch, n_ep = 11, 3
+    total = n * (n_ep + 1) + 4096
+    x_int = rng.integers(-7, 8, total)
+    starts = np.sort(rng.integers(0, n, n_ch))                  # per-channel epoch alignment
+    codes = [(((np.arange(L) * (7919 + 2 * c)) % 31) - 15) for c in range(n_ch)]
+    rems = rng.uniform(-3, 3, n_ch).astype(np.float32)
+    want = {}
+    for c in range(n_ch):
+        _, idx = oracle.port.resampler(1, codes[c].astype(np.float32), float(rems[c]), step, taps_shifts, n, return_idx=True)
+        for k in range(n_ep):
+            s0 = int(starts[c]) + k * n
+            want[(k, c)] = int_oracle(x_int[s0:s0 + n], codes[c], idx)
+    results = {}
+    for mode in ("1", "0"):
+        os.environ["B200_TRK_SHARED"] = mode
+        e = capi.Engine(0)
+        e.iq_create(0, total)
+        first = e.iq_push(0, x_int.astype(np.complex64))
+        cids = []
+        for c in range(n_ch):
+            cid = e.channel_create(0, len(taps_shifts))
+            e.channel_set_code(cid, codes[c].astype(np.float32), taps_shifts)
+            cids.append(cid)
+        items = np.zeros(n_ch * n_ep, capi.TRK_ITEM_DTYPE)
+        order = []
+        for k in range(n_ep):
+            for c in range(n_ch):
+                it = items[len(order)]
+                it["channel"] = cids[c]
+                it["n"] = n
+                it["sample_index"] = first + int(starts[c]) + k * n
+                it["rem_code_phase_chips"] = rems[c]
+                it["code_phase_step_chips"] = step
+                order.append((k, c))
+        # device-pointer entry point with slices = 1 is where the engine picks the shared kernel
+        import torch
+        items_t = torch.from_numpy(items.view(np.uint8)).cuda()
+        out_t = torch.zeros(len(order), len(taps_shifts), 2, dtype=torch.float32, device="cuda")
+        e.trk_batch_dev(items_t.data_ptr(), len(order), out_t.data_ptr(), len(taps_shifts), 1)
+        e.sync()
+        got = out_t.cpu().numpy()
+        results[mode] = got
+        for i, key in enumerate(order):
+            assert np.array_equal(got[i, :, 0].astype(np.int64), want[key]), (mode, key)
+            assert np.all(got[i, :, 1] == 0)
+        e.close()
+    os.environ.pop("B200_TRK_SHARED", None)
+    assert np.array_equal(results["0"], results["1"])
