@@ -32,7 +32,8 @@ constexpr int kShTile = 512;     // samples per tile (4 KB)
 #define SH_MINB 3
 #endif
 constexpr int kShStages = SH_STAGES;
-constexpr int kShWin = 256;      // floats of the warp-private code-replica window (refilled per tile)
+constexpr int kShTblCap = 1152;  // floats of warp-private code storage: whole-epoch table when it fits ...
+constexpr int kShWin = 256;      // ... else two 256-entry windows (double-buffered, refilled per tile with cp.async)
 constexpr int kShThreads = (kShK + 1) * 32;
 constexpr int kShReseed = 64;    // 64-sample steps between exact phasor re-seeds (4096 samples)
 
@@ -41,7 +42,7 @@ namespace
 struct __align__(128) ShSmem
 {
     float2 tiles[kShStages][kShTile];
-    float win[kShK][kShWin];
+    float tbl[kShK][kShTblCap];
     unsigned long long full[kShStages];
     unsigned long long empty[kShStages];
     unsigned long long item_start[kShK];  // offset of the item's first sample in the band (band-relative)
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
 #pragma unroll
     for (int t = 0; t < TAPS; t++) acc[t] = make_float2(0.f, 0.f);
 
-    bool table_path = false;
+    bool table_path = false, whole_table = false;
     int body = 0, a_i = 0, t_first = 0, t_last = 0;
     float step = 0.f;
     unsigned int tbl_off = 0;
@@ -312,6 +313,37 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
                          fabsf(smax) < 1.0e5f && fabsf(smin) < 1.0e5f && fabsf(rem) < 1.0e6f;
             if (table_path)
                 {
+                    // whole-epoch table when the epoch's chip range fits the warp's storage (C/A at any rate):
+                    // filled once, no per-tile work.  Range from the epoch ends (index monotone in n).
+                    {
+                        int elo = 0x7fffffff, ehi = -0x7fffffff - 1;
+                        const float nl = static_cast<float>(max(body - 1, 0));
+#pragma unroll
+                        for (int q = 0; q < TAPS; q++)
+                            {
+                                const int i0 = chip_index_avx(step, 0.f, aux2[q].x);
+                                const int i1 = chip_index_avx(step, nl, aux2[q].x);
+                                elo = min(elo, min(i0, i1));
+                                ehi = max(ehi, max(i0, i1));
+                            }
+                        whole_table = (static_cast<long long>(ehi) - elo + 3) <= kShTblCap;
+                        if (whole_table)
+                            {
+                                const int wb = elo - 1;
+                                const int wspan = ehi - elo + 3;
+                                const int L = ch->code_len;
+                                int r = mod_pos(wb + lane, L);
+                                const int stride = 32 % L;
+                                for (int j = lane; j < wspan; j += 32)
+                                    {
+                                        sm.tbl[warp][j] = __ldg(ch->code + r);
+                                        r += stride;
+                                        if (r >= L) r -= L;
+                                    }
+                                asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.tbl[warp][0])), "r"(4u * (static_cast<unsigned int>(wb) + 0x4B400000u)));
+                                __syncwarp();
+                            }
+                    }
                     a_i = static_cast<int>(sm.item_start[warp] - hull_start);
                     t_first = a_i / kShTile;
                     t_last = (a_i + body + kShTile - 1) / kShTile;
@@ -336,6 +368,7 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
 #pragma unroll
     for (int t = 0; t < TAPS; t++) are[t] = aim[t] = make_float2(0.f, 0.f);
     int tiles_in_group = 0;
+    int next_wb = 0;
     float fa = static_cast<float>(t_first * kShTile + 2 * lane - a_i), fb = fa + 1.0f;
     for (int t = 0; t < n_tiles; t++)
         {
@@ -349,33 +382,47 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
                 {
                     const int n_tile0 = t * kShTile - a_i;
                     const bool interior = (n_tile0 >= 0) && (n_tile0 + kShTile <= body);
-                    // samples of this tile that belong to the epoch, and the chips they touch
+                    // samples of this tile that belong to the epoch
                     const int n_lo = max(n_tile0, 0), n_hi = min(n_tile0 + kShTile, body) - 1;
                     const float vlo = static_cast<float>(n_lo), vhi = static_cast<float>(n_hi);
-                    int wlo = 0x7fffffff, whi = -0x7fffffff - 1;
-#pragma unroll
-                    for (int q = 0; q < TAPS; q++)
+                    if (!whole_table)
                         {
-                            const int i0 = chip_index_avx(step, vlo, aux2[q].x);
-                            const int i1 = chip_index_avx(step, vhi, aux2[q].x);
-                            wlo = min(wlo, min(i0, i1));
-                            whi = max(whi, max(i0, i1));
+                            // sliding code window: the replica values this tile touches, staged with cp.async
+                            // (LDGSTS, no registers) one tile AHEAD so the L2 latency hides behind the
+                            // correlation of the current tile.  window(t) lives in half (t & 1) of tbl[warp].
+                            auto stage_window = [&](int tt) {
+                                const int m0 = tt * kShTile - a_i;
+                                const float lo_f = static_cast<float>(max(m0, 0)), hi_f = static_cast<float>(min(m0 + kShTile, body) - 1);
+                                int wlo = 0x7fffffff, whi = -0x7fffffff - 1;
+#pragma unroll
+                                for (int q = 0; q < TAPS; q++)
+                                    {
+                                        const int i0 = chip_index_avx(step, lo_f, aux2[q].x);
+                                        const int i1 = chip_index_avx(step, hi_f, aux2[q].x);
+                                        wlo = min(wlo, min(i0, i1));
+                                        whi = max(whi, max(i0, i1));
+                                    }
+                                const int wb = wlo - 1;
+                                const int wspan = min(whi - wlo + 3, kShWin);  // <= kShWin by the span_bound test
+                                const int L = ch->code_len;
+                                int r = mod_pos(wb + lane, L);
+                                const int stride = 32 % L;
+                                float* dst = &sm.tbl[warp][(tt & 1) * kShWin];
+                                for (int j = lane; j < wspan; j += 32)
+                                    {
+                                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + j)), "l"(ch->code + r) : "memory");
+                                        r += stride;
+                                        if (r >= L) r -= L;
+                                    }
+                                return wb;
+                            };
+                            if (t == t_first) next_wb = stage_window(t);
+                            const int wb = next_wb;
+                            asm volatile("cp.async.wait_all;" ::: "memory");
+                            __syncwarp();
+                            if (t + 1 < t_last) next_wb = stage_window(t + 1);
+                            asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.tbl[warp][(t & 1) * kShWin])), "r"(4u * (static_cast<unsigned int>(wb) + 0x4B400000u)));
                         }
-                    const int wb = wlo - 1;
-                    const int wspan = min(whi - wlo + 3, kShWin);   // <= kShWin by the span_bound test
-                    {
-                        const int L = ch->code_len;
-                        int r = mod_pos(wb + lane, L);
-                        const int stride = 32 % L;
-                        for (int j = lane; j < wspan; j += 32)
-                            {
-                                sm.win[warp][j] = __ldg(ch->code + r);
-                                r += stride;
-                                if (r >= L) r -= L;
-                            }
-                    }
-                    asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.win[warp][0])), "r"(4u * (static_cast<unsigned int>(wb) + 0x4B400000u)));
-                    __syncwarp();
                     if (interior)
                         warp_tile<TAPS, false>(&sm.tiles[s][0], vlo, vhi, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
                     else
