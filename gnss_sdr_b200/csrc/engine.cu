@@ -443,9 +443,9 @@ extern "C"
                 const char* env = std::getenv("B200_TRK_SHARED");
                 e->shared_mode = env ? std::atoi(env) : 2;  // 2 = automatic
             }
-        const bool shared_legal = (e->taps_uniform == 1 || e->taps_uniform == 3 || e->taps_uniform == 5) && !e->any_high_dyn &&
-                                  e->max_code_len <= trk_shared_max_code_len() && slices == 1;
-        const bool use_shared = shared_legal && (e->shared_mode == 1 || (e->shared_mode == 2 && n_items >= 1024));
+        const bool shared_legal = (e->taps_uniform == 1 || e->taps_uniform == 3 || e->taps_uniform == 5) && !e->any_high_dyn && slices == 1;
+        const bool use_shared = shared_legal && (e->shared_mode == 1 || (e->shared_mode == 2 && n_items >= 1024 &&
+                                                                            e->max_code_len <= trk_shared_max_code_len()));
         if (use_shared)
             rc = launch_trk_shared(items_dev, n_items, e->chans_dev, e->bands_dev, reinterpret_cast<float2*>(out_dev), out_stride,
                 e->taps_uniform, e->stream);
