@@ -39,6 +39,8 @@ struct b200_acq
     float2* code_stage{nullptr};
     float* grid{nullptr};      // slots x bins x ne (optional)
     float2* wipe2{nullptr};    // step-two wipe-offs (bins2 x n)
+    float2* Z{nullptr};        // two-level FFT only: rows x fft_size inverse-transformed blocks
+    AcqRowStat* partial{nullptr};
     float center2{0.f}, step2{0.f};
     uint32_t bins2{0};
     AcqRowStat* rowstat{nullptr};
@@ -89,7 +91,7 @@ int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32
     int rc = acq_launch_fwd(in_dev, static_cast<int>(c.consumed_samples), wipe, a->X, bins, a->plan, a->tw, st);
     if (rc) return rc;
     rc = acq_launch_corr(a->X, a->codes, a->slot_list, static_cast<int>(n_slots), bins, a->plan, a->tw, off, ne, a->rowstat, a->grid,
-        dwell_counter > 1 ? 1 : 0, 0, nullptr, 0, nullptr, st);
+        dwell_counter > 1 ? 1 : 0, 0, nullptr, 0, nullptr, a->Z, a->partial, st);
     if (rc) return rc;
     rc = acq_launch_stats(a->rowstat, static_cast<int>(n_slots), bins, ne, c.doppler_max, a->doppler_center, c.doppler_step,
         dwell_counter, c.use_cfar, a->best, results_dev, step_two, a->center2, a->step2, prev_input_power, st);
@@ -98,7 +100,7 @@ int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32
     if (!c.use_cfar)
         {
             rc = acq_launch_corr(a->X, a->codes, a->slot_list, static_cast<int>(n_slots), bins, a->plan, a->tw, off, ne, a->rowstat,
-                a->grid, 0, 1, a->best, static_cast<int>(c.samples_per_chip), a->second_peak, st);
+                a->grid, 0, 1, a->best, static_cast<int>(c.samples_per_chip), a->second_peak, a->Z, a->partial, st);
             if (rc) return rc;
             rc = acq_launch_finish_second_peak(a->second_peak, static_cast<int>(n_slots), results_dev, st);
             if (rc) return rc;
@@ -131,7 +133,7 @@ extern "C"
         int rc = acq_plan_make(static_cast<int>(c.fft_size), &pl);
         if (rc)
             {
-                set_error("fft_size %u unsupported: must be <= %d and factor into 2,3,5,7", c.fft_size, kAcqMaxSmemPoints);
+                set_error("fft_size %u unsupported: prime factors must be 2,3,5,7 and fft_size <= 8 x %d", c.fft_size, kAcqMaxSmemPoints);
                 return rc;
             }
         B200_CUDA_TRY(cudaSetDevice(e->device));
@@ -165,6 +167,18 @@ extern "C"
         B200_CUDA_TRY(cudaMalloc(&a->results_dev, sizeof(b200_acq_result) * slots));
         B200_CUDA_TRY(cudaMallocHost(&a->results_pin, sizeof(b200_acq_result) * slots));
         B200_CUDA_TRY(cudaMallocHost(&a->slot_pin, sizeof(int) * slots));
+        if (pl.n1 > 1)
+            {
+                const size_t rows = bins * slots;
+                cudaError_t zerr = cudaMalloc(&a->Z, sizeof(float2) * n * rows);
+                if (zerr != cudaSuccess)
+                    {
+                        set_error("two-level FFT workspace (%zu bytes): %s", sizeof(float2) * n * rows, cudaGetErrorString(zerr));
+                        b200_acq_destroy(a);
+                        return B200_ERR_NOMEM;
+                    }
+                B200_CUDA_TRY(cudaMalloc(&a->partial, sizeof(AcqRowStat) * rows * acq_final_chunks(pl)));
+            }
         if (c.max_dwells > 1 || c.keep_grid)
             {
                 cudaError_t err = cudaMalloc(&a->grid, sizeof(float) * ne * bins * slots);
@@ -309,6 +323,8 @@ extern "C"
         cudaFree(a->tw);
         cudaFree(a->wipe);
         cudaFree(a->wipe2);
+        cudaFree(a->Z);
+        cudaFree(a->partial);
         cudaFree(a->X);
         cudaFree(a->codes);
         cudaFree(a->in_dev);

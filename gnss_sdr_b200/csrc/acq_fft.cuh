@@ -30,6 +30,11 @@ struct FftPlan
     int radix[kAcqMaxStages];          // forward DIF order; product = n
     unsigned int mdiv[kAcqMaxStages];  // floor(2^32 / m) + 1 for the stage's m = M / radix (exact i / m for i < 2^16)
     int tw_off[kAcqMaxStages];         // start of the stage's compact twiddle table: exp(-2 pi j k / M), k < m
+    // Sizes above kAcqMaxSmemPoints: n_total = n1 * n.  One radix-n1 stage runs through global memory (L2),
+    // the remaining stages are the in-shared-memory plan above on each of the n1 blocks of n points.
+    int n1;       // 1 = whole transform in shared memory
+    int n_total;  // transform size seen by the caller
+    int tw_goff;  // twiddles of the global stage: exp(-2 pi j k / n_total), k < n
 };
 
 __device__ __forceinline__ int fast_div(int i, int m, unsigned int magic)
@@ -284,6 +289,21 @@ __device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, c
         }
     __syncthreads();
     fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw + pl.tw_off[0], last);
+}
+
+
+// inverse DIT over all stages in place (two-level path: natural order within the block afterwards)
+__device__ __forceinline__ void fft_inverse_smem_inplace(float2* s, const FftPlan& pl, const float2* tw)
+{
+    StoreSink st_sink;
+    int M = 1;
+    for (int st = pl.n_stages - 1; st >= 0; st--)
+        {
+            M *= pl.radix[st];
+            __syncthreads();
+            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
+        }
+    __syncthreads();
 }
 
 }  // namespace b200

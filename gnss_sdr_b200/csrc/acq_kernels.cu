@@ -20,6 +20,8 @@
 #include "acq_fft.cuh"
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace b200
 {
 struct AcqRowStat
@@ -368,6 +370,242 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* 
         }
 }
 
+// ---- two-level transforms (fft_size > kAcqMaxSmemPoints): n_total = n1 * n ----------------------------------
+// Forward: one radix-n1 DIF stage through global memory (block length n_total, sub-length n), then the
+// in-shared-memory plan on each of the n1 blocks.  Inverse: the blocks first, then the radix-n1 DIT stage,
+// whose natural-order outputs feed the statistics directly.  Layout stays "digit reversed" end to end.
+__device__ __forceinline__ float2 acq_source(const float2* __restrict__ in, const float2* __restrict__ wipe, int i, int consumed,
+    int layout, int n_total)
+{
+    // wipe != nullptr: signal * wipe-off, zero-padded beyond consumed (acquisition_core :657-664, :531)
+    // wipe == nullptr: local code placed by `layout` (set_local_code :230-246)
+    float2 v = make_float2(0.f, 0.f);
+    if (wipe != nullptr)
+        {
+            if (i < consumed)
+                {
+                    const float2 a = in[i];
+                    const float2 b = wipe[i];
+                    v.x = __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+                    v.y = __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
+                }
+            return v;
+        }
+    if (layout == 0)
+        {
+            if (i < consumed) v = in[i];
+        }
+    else if (layout == 1)
+        {
+            const int off = n_total / 2;
+            if (i >= off) v = in[i - off];
+        }
+    else
+        {
+            const int off = n_total - consumed;
+            if (i >= off) v = in[i - off];
+        }
+    return v;
+}
+
+template <int R>
+__global__ void acq_global_fwd_stage(const float2* __restrict__ in, int consumed, int layout, const float2* __restrict__ wipe,
+    float2* __restrict__ X, FftPlan pl, const float2* __restrict__ tw)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n2 = pl.n;
+    if (j >= n2) return;
+    const int d = blockIdx.y;
+    const float2* w = wipe ? wipe + static_cast<size_t>(d) * pl.n_total : nullptr;
+    float2 v[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) v[q] = acq_source(in, w, j + q * n2, consumed, layout, pl.n_total);
+    Bfly<R>::fwd(v);
+    const float2 w1 = __ldg(tw + pl.tw_goff + j);
+    float2 wp = w1;
+    float2* o = X + static_cast<size_t>(d) * pl.n_total;
+    o[j] = v[0];
+#pragma unroll
+    for (int q = 1; q < R; q++)
+        {
+            o[q * n2 + j] = cmul(v[q], wp);
+            if (q + 1 < R) wp = cmul(wp, w1);
+        }
+}
+
+// forward in-smem FFT of block p of row d, in place; conj_out for the local code
+__global__ void __launch_bounds__(kAcqThreads, 1) acq_block_fft_kernel(float2* __restrict__ X, FftPlan pl, const float2* __restrict__ tw, int conj_out)
+{
+    extern __shared__ __align__(16) float2 s[];
+    const int n = pl.n;
+    float2* blk = X + static_cast<size_t>(blockIdx.y) * pl.n_total + static_cast<size_t>(blockIdx.x) * n;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = blk[i];
+    fft_forward_smem(s, pl, tw);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) blk[i] = conj_out ? make_float2(s[i].x, -s[i].y) : s[i];
+}
+
+// rows: mode 0 -> r = slot_pos * bins + bin ; mode 1 -> r = slot_pos (bin from best[])
+__global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_block_kernel(const float2* __restrict__ X, const float2* __restrict__ codes,
+    const int* __restrict__ slot_list, int bins, FftPlan pl, const float2* __restrict__ tw, float2* __restrict__ Z, int mode,
+    const AcqBest* __restrict__ best)
+{
+    extern __shared__ __align__(16) float2 s[];
+    const int n = pl.n;
+    const int p = blockIdx.x;
+    const int r = blockIdx.y;
+    int slot_pos, bin;
+    if (mode == 0)
+        {
+            slot_pos = r / bins;
+            bin = r - slot_pos * bins;
+        }
+    else
+        {
+            slot_pos = r;
+            bin = static_cast<int>(best[r].index_doppler);
+        }
+    const int slot = slot_list[slot_pos];
+    const float2* x = X + static_cast<size_t>(bin) * pl.n_total + static_cast<size_t>(p) * n;
+    const float2* c = codes + static_cast<size_t>(slot) * pl.n_total + static_cast<size_t>(p) * n;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const float2 a = __ldg(x + i);
+            const float2 b = __ldg(c + i);
+            s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+        }
+    fft_inverse_smem_inplace(s, pl, tw);
+    float2* z = Z + static_cast<size_t>(r) * pl.n_total + static_cast<size_t>(p) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = s[i];
+}
+
+// final radix-n1 DIT stage + |.|^2 + statistics; grid (chunks, rows); partial[r * chunks + chunk]
+template <int R>
+__global__ void __launch_bounds__(256) acq_global_final_stage(const float2* __restrict__ Z, FftPlan pl, const float2* __restrict__ tw,
+    const int* __restrict__ slot_list, int bins, int off, int ne, float* __restrict__ grid, int accumulate, int mode,
+    const AcqBest* __restrict__ best, int samples_per_chip, AcqRowStat* __restrict__ partial)
+{
+    __shared__ float red_v[8];
+    __shared__ unsigned int red_i[8];
+    __shared__ float red_s[8];
+    const int r = blockIdx.y;
+    const int n2 = pl.n;
+    int slot_pos, bin;
+    RowSink sink;
+    sink.off = off;
+    sink.ne = ne;
+    sink.ex1 = -1;
+    sink.ex2 = -1;
+    sink.grid = nullptr;
+    sink.accumulate = accumulate;
+    if (mode == 0)
+        {
+            slot_pos = r / bins;
+            bin = r - slot_pos * bins;
+        }
+    else
+        {
+            slot_pos = r;
+            bin = static_cast<int>(best[r].index_doppler);
+            int e1 = static_cast<int>(best[r].index_time) - samples_per_chip;
+            int e2 = static_cast<int>(best[r].index_time) + samples_per_chip;
+            if (e1 < 0)
+                e1 = ne + e1;
+            else if (e2 >= ne)
+                e2 = e2 - ne;
+            sink.ex1 = e1;
+            sink.ex2 = e2;
+        }
+    if (grid != nullptr && mode == 0) sink.grid = grid + (static_cast<size_t>(slot_list[slot_pos]) * bins + bin) * ne;
+    sink.best = -1.0f;
+    sink.best_t = 0xffffffffu;
+    sink.sum = 0.0f;
+    const float2* z = Z + static_cast<size_t>(r) * pl.n_total;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += gridDim.x * blockDim.x)
+        {
+            float2 v[R];
+#pragma unroll
+            for (int q = 0; q < R; q++) v[q] = z[q * n2 + j];
+            const float2 w1 = __ldg(tw + pl.tw_goff + j);
+            float2 wp = w1;
+#pragma unroll
+            for (int q = 1; q < R; q++)
+                {
+                    v[q] = cmul_conj(v[q], wp);
+                    if (q + 1 < R) wp = cmul(wp, w1);
+                }
+#pragma unroll
+            for (int q = 0; q < R; q++) v[q] = swap_ri(v[q]);
+            Bfly<R>::fwd(v);
+#pragma unroll
+            for (int q = 0; q < R; q++) sink(nullptr, j + q * n2, swap_ri(v[q]));
+        }
+    float bv = sink.best;
+    unsigned int bi = sink.best_t;
+    float sm = sink.sum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const unsigned int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            if (ov > bv || (ov == bv && oi < bi))
+                {
+                    bv = ov;
+                    bi = oi;
+                }
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        {
+            red_v[warp] = bv;
+            red_i[warp] = bi;
+            red_s[warp] = sm;
+        }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        {
+            for (int w = 1; w < 8; w++)
+                {
+                    if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi))
+                        {
+                            bv = red_v[w];
+                            bi = red_i[w];
+                        }
+                    sm += red_s[w];
+                }
+            AcqRowStat st;
+            st.max = bv;
+            st.argmax = bi;
+            st.sum = sm;
+            st.pad = 0.f;
+            partial[static_cast<size_t>(r) * gridDim.x + blockIdx.x] = st;
+        }
+}
+
+__global__ void acq_row_reduce_kernel(const AcqRowStat* __restrict__ partial, int chunks, int rows, AcqRowStat* __restrict__ rowstat,
+    float* __restrict__ second_peak, int mode)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    AcqRowStat a = partial[static_cast<size_t>(r) * chunks];
+    for (int k = 1; k < chunks; k++)
+        {
+            const AcqRowStat b = partial[static_cast<size_t>(r) * chunks + k];
+            if (b.max > a.max || (b.max == a.max && b.argmax < a.argmax))
+                {
+                    a.max = b.max;
+                    a.argmax = b.argmax;
+                }
+            a.sum += b.sum;
+        }
+    if (mode == 0)
+        rowstat[r] = a;
+    else
+        second_peak[r] = a.max;
+}
+
 // ---- statistics ---------------------------------------------------------------------------------------
 // one thread per searched PRN (bins <= a few hundred): pcps_acquisition.cc:417-449 / :464-482
 __global__ void acq_stats_kernel(const AcqRowStat* __restrict__ rowstat, int n_slots, int bins, int ne, int doppler_max,
@@ -444,6 +682,15 @@ __global__ void acq_twiddle_kernel(float2* __restrict__ tw, FftPlan pl)
                 }
             M = m;
         }
+    if (pl.n1 > 1)
+        {
+            for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < pl.n; k += gridDim.x * blockDim.x)
+                {
+                    double s, c;
+                    sincospi(-2.0 * static_cast<double>(k) / static_cast<double>(pl.n_total), &s, &c);
+                    tw[pl.tw_goff + k] = make_float2(static_cast<float>(c), static_cast<float>(s));
+                }
+        }
 }
 
 bool g_attr_done = false;
@@ -454,13 +701,50 @@ int set_attrs()
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_code_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_block_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     g_attr_done = true;
     return B200_OK;
 }
 }  // namespace
 
 // ---- launchers (called from acq_engine.cu) --------------------------------------------------------------
-int acq_plan_make(int n, FftPlan* pl)
+static int acq_plan_make_smem(int n, FftPlan* pl);
+
+int acq_plan_make(int n_total, FftPlan* pl)
+{
+    if (n_total < 2) return B200_ERR_RANGE;
+    if (n_total <= kAcqMaxSmemPoints)
+        {
+            const int rc = acq_plan_make_smem(n_total, pl);
+            pl->n1 = 1;
+            pl->n_total = n_total;
+            pl->tw_goff = 0;
+            return rc;
+        }
+    // two-level: smallest supported radix n1 that brings the blocks into shared memory
+    const int cand[6] = {2, 3, 4, 5, 7, 8};
+    for (int n1 : cand)
+        {
+            if (n_total % n1) continue;
+            const int n2 = n_total / n1;
+            if (n2 > kAcqMaxSmemPoints) continue;
+            if (acq_plan_make_smem(n2, pl) != B200_OK) continue;
+            pl->n1 = n1;
+            pl->n_total = n_total;
+            int off = 0, M = n2;
+            for (int st = 0; st < pl->n_stages; st++)
+                {
+                    M /= pl->radix[st];
+                    off += M;
+                }
+            pl->tw_goff = off;  // after the per-stage tables; n2 entries follow
+            return B200_OK;
+        }
+    return B200_ERR_RANGE;
+}
+
+static int acq_plan_make_smem(int n, FftPlan* pl)
 {
     if (n < 2 || n > kAcqMaxSmemPoints) return B200_ERR_RANGE;
     int rem = n;
@@ -519,11 +803,38 @@ int acq_launch_wipeoff(float2* wipe, int n, int bins, int doppler_max, int doppl
     return B200_OK;
 }
 
+template <typename F>
+static int dispatch_radix(int r, F&& f)
+{
+    switch (r)
+        {
+        case 2: f(std::integral_constant<int, 2>{}); return B200_OK;
+        case 3: f(std::integral_constant<int, 3>{}); return B200_OK;
+        case 4: f(std::integral_constant<int, 4>{}); return B200_OK;
+        case 5: f(std::integral_constant<int, 5>{}); return B200_OK;
+        case 7: f(std::integral_constant<int, 7>{}); return B200_OK;
+        case 8: f(std::integral_constant<int, 8>{}); return B200_OK;
+        default: return B200_ERR_RANGE;
+        }
+}
+
+int acq_final_chunks(const FftPlan& pl) { return pl.n1 > 1 ? (pl.n + 1023) / 1024 : 0; }
+
 int acq_launch_code_fft(const float2* code, int consumed, int layout, float2* out, const FftPlan& pl, const float2* tw, cudaStream_t st)
 {
     int rc = set_attrs();
     if (rc) return rc;
-    acq_code_fft_kernel<<<1, kAcqThreads, pl.n * sizeof(float2), st>>>(code, consumed, layout, out, pl, tw);
+    if (pl.n1 == 1)
+        {
+            acq_code_fft_kernel<<<1, kAcqThreads, pl.n * sizeof(float2), st>>>(code, consumed, layout, out, pl, tw);
+        }
+    else
+        {
+            const dim3 g((pl.n + 255) / 256, 1);
+            rc = dispatch_radix(pl.n1, [&](auto R) { acq_global_fwd_stage<decltype(R)::value><<<g, 256, 0, st>>>(code, consumed, layout, nullptr, out, pl, tw); });
+            if (rc) return rc;
+            acq_block_fft_kernel<<<dim3(pl.n1, 1), kAcqThreads, pl.n * sizeof(float2), st>>>(out, pl, tw, 1);
+        }
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }
@@ -532,20 +843,46 @@ int acq_launch_fwd(const float2* in, int consumed, const float2* wipe, float2* X
 {
     int rc = set_attrs();
     if (rc) return rc;
-    acq_fwd_kernel<<<bins, kAcqThreads, pl.n * sizeof(float2), st>>>(in, consumed, wipe, X, pl, tw);
+    if (pl.n1 == 1)
+        {
+            acq_fwd_kernel<<<bins, kAcqThreads, pl.n * sizeof(float2), st>>>(in, consumed, wipe, X, pl, tw);
+        }
+    else
+        {
+            const dim3 g((pl.n + 255) / 256, bins);
+            rc = dispatch_radix(pl.n1, [&](auto R) { acq_global_fwd_stage<decltype(R)::value><<<g, 256, 0, st>>>(in, consumed, 0, wipe, X, pl, tw); });
+            if (rc) return rc;
+            acq_block_fft_kernel<<<dim3(pl.n1, bins), kAcqThreads, pl.n * sizeof(float2), st>>>(X, pl, tw, 0);
+        }
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }
 
 int acq_launch_corr(const float2* X, const float2* codes, const int* slot_list, int n_slots, int bins, const FftPlan& pl,
     const float2* tw, int off, int ne, AcqRowStat* rowstat, float* grid, int accumulate, int mode, const void* best,
-    int samples_per_chip, float* second_peak, cudaStream_t st)
+    int samples_per_chip, float* second_peak, float2* Z, AcqRowStat* partial, cudaStream_t st)
 {
     int rc = set_attrs();
     if (rc) return rc;
-    const int grid_dim = (mode == 0) ? n_slots * bins : n_slots;
-    acq_corr_kernel<<<grid_dim, kAcqThreads, pl.n * sizeof(float2), st>>>(X, codes, slot_list, bins, pl, tw, off, ne, rowstat,
-        grid, accumulate, mode, static_cast<const AcqBest*>(best), samples_per_chip, second_peak);
+    const int rows = (mode == 0) ? n_slots * bins : n_slots;
+    if (pl.n1 == 1 || (mode == 1 && grid != nullptr))
+        {
+            const size_t smem = (pl.n1 == 1) ? pl.n * sizeof(float2) : 16;
+            acq_corr_kernel<<<rows, kAcqThreads, smem, st>>>(X, codes, slot_list, bins, pl, tw, off, ne, rowstat,
+                grid, accumulate, mode, static_cast<const AcqBest*>(best), samples_per_chip, second_peak);
+        }
+    else
+        {
+            acq_corr_block_kernel<<<dim3(pl.n1, rows), kAcqThreads, pl.n * sizeof(float2), st>>>(X, codes, slot_list, bins, pl, tw, Z, mode,
+                static_cast<const AcqBest*>(best));
+            const int chunks = acq_final_chunks(pl);
+            rc = dispatch_radix(pl.n1, [&](auto R) {
+                acq_global_final_stage<decltype(R)::value><<<dim3(chunks, rows), 256, 0, st>>>(Z, pl, tw, slot_list, bins, off, ne, grid, accumulate,
+                    mode, static_cast<const AcqBest*>(best), samples_per_chip, partial);
+            });
+            if (rc) return rc;
+            acq_row_reduce_kernel<<<(rows + 127) / 128, 128, 0, st>>>(partial, chunks, rows, rowstat, second_peak, mode);
+        }
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }

@@ -84,7 +84,8 @@ int acq_launch_code_fft(const float2* code, int consumed, int layout, float2* ou
 int acq_launch_fwd(const float2* in, int consumed, const float2* wipe, float2* X, int bins, const FftPlan& pl, const float2* tw, cudaStream_t st);
 int acq_launch_corr(const float2* X, const float2* codes, const int* slot_list, int n_slots, int bins, const FftPlan& pl,
     const float2* tw, int off, int ne, AcqRowStat* rowstat, float* grid, int accumulate, int mode, const void* best,
-    int samples_per_chip, float* second_peak, cudaStream_t st);
+    int samples_per_chip, float* second_peak, float2* Z, AcqRowStat* partial, cudaStream_t st);
+int acq_final_chunks(const FftPlan& pl);
 int acq_launch_stats(const AcqRowStat* rowstat, int n_slots, int bins, int ne, int doppler_max, int doppler_center,
     int doppler_step, unsigned int dwell_counter, int use_cfar, void* best, b200_acq_result* results, int step_two, float center2,
     float step2, float prev_input_power, cudaStream_t st);

@@ -248,8 +248,8 @@ def test_fft_round_trip_property_all_supported_radices(capi, engine, oracle):
 def test_acq_error_paths(capi, engine):
     with pytest.raises(capi.B200Error):   # 16368 = 2^4*3*11*31: unsupported primes
         capi.PcpsAcquisition(engine, fs_in=16368000, samples_per_ms=16368.0, samples_per_chip=16, doppler_max=5000, doppler_step=250)
-    with pytest.raises(capi.B200Error):   # too large for the single-CTA path
-        capi.PcpsAcquisition(engine, fs_in=50000000, samples_per_ms=50000.0, samples_per_chip=48, doppler_max=5000, doppler_step=250)
+    with pytest.raises(capi.B200Error):   # beyond 8 x 27648 points
+        capi.PcpsAcquisition(engine, fs_in=300000000, samples_per_ms=300000.0, samples_per_chip=290, doppler_max=1000, doppler_step=500)
     acq = capi.PcpsAcquisition(engine, fs_in=4000000, samples_per_ms=4000.0, samples_per_chip=3, doppler_max=5000, doppler_step=250)
     with pytest.raises(capi.B200Error):   # search before set_local_code
         acq.search(np.zeros(4000, np.complex64), [0])
@@ -284,4 +284,38 @@ def test_two_step_acquisition(capi, engine, oracle):
     assert (int(g2["index_time"]), int(g2["index_doppler"]), int(g2["doppler"])) == (w2["index_time"], w2["index_doppler"], w2["doppler"])
     assert abs(g2["test_statistics"] - w2["test_statistics"]) / w2["test_statistics"] < 1e-4
     assert abs(w2["doppler"] - svs[0]["doppler"]) < abs(w1["doppler"] - svs[0]["doppler"]) + 63   # refined (within half a fine bin)
+    acq.close()
+
+
+@pytest.mark.parametrize("fs,sampled_ms,dmax,dstep,cfar", [
+    (50e6, 1, 5000, 500, True),       # N = 50000  = 2 x 25000
+    (25e6, 4, 2000, 250, True),       # N = 100000 = 4 x 25000   (4 ms coherent)
+    (50e6, 4, 1000, 250, False),      # N = 200000 = 8 x 25000   (Galileo E1 size at 50 Msps), first/second peak
+    (8e6, 4, 2000, 500, True),        # N = 32000  = 2 x 16000
+    (8e6, 7, 1000, 500, True),        # N = 56000  = 7 x 8000 -> radix-7 global stage
+])
+def test_two_level_fft_sizes(capi, engine, oracle, fs, sampled_ms, dmax, dstep, cfar):
+    """fft_size above the single-CTA limit: one radix-n1 stage through global memory + in-shared-memory
+    blocks.  Same contract as the small sizes: exact indices, statistics within 1e-4, grid within 2e-5."""
+    spms = fs / 1000.0
+    n = int(spms) * sampled_ms
+    spchip = int(fs / 1.023e6)
+    prn = 7
+    iq, svs = _signal(oracle, [7, 21], fs, n, seed=int(fs / 1e3) + sampled_ms, cn0=42.0)
+    o = _oracle_acq(oracle, fs, spms, spchip, dmax, dstep, prn, iq, cfar=cfar, sampled_ms=sampled_ms, ms_per_code=sampled_ms)
+    want = o.acquisition_core(iq)
+    acq = capi.PcpsAcquisition(engine, fs_in=int(fs), samples_per_ms=spms, samples_per_chip=spchip, doppler_max=dmax,
+                               doppler_step=dstep, use_CFAR_algorithm_flag=cfar, sampled_ms=sampled_ms, ms_per_code=sampled_ms,
+                               keep_grid=True)
+    assert acq.conf.fft_size == n
+    acq.set_local_code(0, np.tile(oracle.port.gps_ca_code_complex_sampled(prn, int(fs)), sampled_ms))
+    got = acq.search(iq, [0])[0]
+    assert int(got["index_time"]) == want["index_time"]
+    assert int(got["index_doppler"]) == want["index_doppler"]
+    assert abs(got["grid_maximum"] - want["grid_maximum"]) / want["grid_maximum"] < 1e-4
+    assert abs(got["test_statistics"] - want["test_statistics"]) / want["test_statistics"] < 1e-4
+    g = acq.read_grid(0)
+    ref_g = o.magnitude_grid[:, :acq.conf.effective_fft_size]
+    assert np.max(np.abs(g - ref_g)) / ref_g.max() < 2e-5
+    assert abs(want["doppler"] - svs[0]["doppler"]) <= 666
     acq.close()
