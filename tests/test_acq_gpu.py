@@ -310,7 +310,10 @@ def test_two_level_fft_sizes(capi, engine, oracle, fs, sampled_ms, dmax, dstep, 
     assert acq.conf.fft_size == n
     acq.set_local_code(0, np.tile(oracle.port.gps_ca_code_complex_sampled(prn, int(fs)), sampled_ms))
     got = acq.search(iq, [0])[0]
-    assert int(got["index_time"]) == want["index_time"]
+    # with sampled_ms code periods in the buffer the correlation has sampled_ms mathematically equal peaks one
+    # code period apart; which one wins is rounding noise, and update_synchro folds it away
+    # (Acq_delay_samples = fmod(index_time, samples_per_code), pcps_acquisition.cc:582)
+    assert int(got["index_time"]) % int(spms) == want["index_time"] % int(spms)
     assert int(got["index_doppler"]) == want["index_doppler"]
     assert abs(got["grid_maximum"] - want["grid_maximum"]) / want["grid_maximum"] < 1e-4
     assert abs(got["test_statistics"] - want["test_statistics"]) / want["test_statistics"] < 1e-4
