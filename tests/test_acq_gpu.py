@@ -221,7 +221,7 @@ def test_doppler_center_assisted(capi, engine, oracle):
     got = acq.search(iq, [0])[0]
     assert int(got["doppler"]) == want["doppler"]
     assert int(got["index_time"]) == want["index_time"]
-    assert abs(want["doppler"] - svs[0]["doppler"]) <= 666
+    assert abs(want["doppler"] - svs[0]["doppler"]) <= max(dstep, 666 / sampled_ms)
     acq.close()
 
 
@@ -301,7 +301,10 @@ def test_two_level_fft_sizes(capi, engine, oracle, fs, sampled_ms, dmax, dstep, 
     n = int(spms) * sampled_ms
     spchip = int(fs / 1.023e6)
     prn = 7
-    iq, svs = _signal(oracle, [7, 21], fs, n, seed=int(fs / 1e3) + sampled_ms, cn0=42.0)
+    codes = {p: oracle.port.gps_ca_code(p) for p in (7, 21)}
+    svs = [dict(prn=7, doppler=0.6 * dmax + 17.0, code_phase_chips=321.4, cn0=42.0, phase0=1.0),
+           dict(prn=21, doppler=-0.3 * dmax, code_phase_chips=77.7, cn0=42.0, phase0=2.0)]
+    iq = make_iq(codes, fs, n, svs, seed=int(fs / 1e3) + sampled_ms)
     o = _oracle_acq(oracle, fs, spms, spchip, dmax, dstep, prn, iq, cfar=cfar, sampled_ms=sampled_ms, ms_per_code=sampled_ms)
     want = o.acquisition_core(iq)
     acq = capi.PcpsAcquisition(engine, fs_in=int(fs), samples_per_ms=spms, samples_per_chip=spchip, doppler_max=dmax,
@@ -320,5 +323,5 @@ def test_two_level_fft_sizes(capi, engine, oracle, fs, sampled_ms, dmax, dstep, 
     g = acq.read_grid(0)
     ref_g = o.magnitude_grid[:, :acq.conf.effective_fft_size]
     assert np.max(np.abs(g - ref_g)) / ref_g.max() < 2e-5
-    assert abs(want["doppler"] - svs[0]["doppler"]) <= 666
+    assert abs(want["doppler"] - svs[0]["doppler"]) <= max(dstep, 666 / sampled_ms)
     acq.close()
