@@ -302,7 +302,7 @@ def test_two_level_fft_sizes(capi, engine, oracle, fs, sampled_ms, dmax, dstep, 
     spchip = int(fs / 1.023e6)
     prn = 7
     codes = {p: oracle.port.gps_ca_code(p) for p in (7, 21)}
-    svs = [dict(prn=7, doppler=0.6 * dmax + 17.0, code_phase_chips=321.4, cn0=42.0, phase0=1.0),
+    svs = [dict(prn=7, doppler=dstep * round(0.6 * dmax / dstep) + 10.0, code_phase_chips=321.4, cn0=42.0, phase0=1.0),
            dict(prn=21, doppler=-0.3 * dmax, code_phase_chips=77.7, cn0=42.0, phase0=2.0)]
     iq = make_iq(codes, fs, n, svs, seed=int(fs / 1e3) + sampled_ms)
     o = _oracle_acq(oracle, fs, spms, spchip, dmax, dstep, prn, iq, cfar=cfar, sampled_ms=sampled_ms, ms_per_code=sampled_ms)
