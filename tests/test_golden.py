@@ -64,7 +64,11 @@ def test_gpu_matches_reference_golden_taps(oracle, case):
     eng.close()
     want = G[f"{name}/a_avx"]
     assert np.all(np.abs(got - want) / np.abs(want) < 1e-3)                       # the reference's SIMD-vs-generic bound
-    assert np.max(np.abs(got - want)) <= 3 * np.max(np.abs(G[f"{name}/generic"] - want)) + 2e-5 * np.max(np.abs(want))
+    if not hd:
+        # and not further from the reference's SIMD result than ~ the reference's own generic kernel is
+        # (the high-dynamics rotator has only a generic, cpowf-based implementation whose float phase is
+        # itself ~1e-4 off, so that comparison is meaningless there)
+        assert np.max(np.abs(got - want)) <= 3 * np.max(np.abs(G[f"{name}/generic"] - want)) + 2e-5 * np.max(np.abs(want))
 
 
 @pytest.mark.gpu
