@@ -1,0 +1,76 @@
+"""BASELINE configs[0]: GPS L1 C/A, 1 channel, 4 Msps: PCPS acquisition hands (code delay, Doppler) to a
+DLL/PLL tracking loop.  The SAME host loop (tests/trk_loop.py, a restatement of the reference's scalar loop
+math) runs once over the reference's CPU correlator and once over the B200 correlator, started from the
+B200 acquisition result; both must lock and stay together."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from gnss_synth import GPS_L1_FREQ, make_iq  # noqa: E402
+from trk_loop import run_tracking  # noqa: E402
+
+
+def test_acquisition_to_tracking_chain(oracle):
+    import gnss_sdr_b200.capi as capi
+    fs, prn, doppler, delay = 4e6, 1, 1680.0, 524
+    n = int(fs * 2.3)
+    code = oracle.port.gps_ca_code(prn)
+    spc = fs / 1.023e6
+    sv = dict(prn=prn, doppler=doppler, code_phase_chips=(-(delay) / spc) % 1023, cn0=47.0, phase0=0.4)
+    iq = make_iq({prn: code}, fs, n, [sv], seed=1)
+
+    eng = capi.Engine(0)
+    # ---- acquisition (the reference test's configuration: doppler_max 5000, step 100 would be 100 bins; 250 here)
+    acq = capi.PcpsAcquisition(eng, fs_in=int(fs), samples_per_ms=4000.0, samples_per_chip=3, doppler_max=5000, doppler_step=250)
+    acq.set_local_code(0, oracle.port.gps_ca_code_complex_sampled(prn, int(fs)))
+    r = acq.search(iq[:4000], [0])[0]
+    acq.close()
+    acq_delay = float(np.fmod(np.float32(r["index_time"]), np.float32(4000.0)))
+    assert abs(acq_delay - delay) <= 2 and abs(int(r["doppler"]) - doppler) <= 250
+
+    shifts = [-0.5, 0.0, 0.5]
+    # ---- tracking over the B200 correlator
+    mc = capi.Multicorrelator(eng, 4096, 3)
+    mc.set_high_dynamics_resampler(False)
+    mc.set_local_code_and_taps(code, shifts)
+
+    def corr_gpu(block, rem_carr, dphi, rem_code, step, nn):
+        return mc.Carrier_wipeoff_multicorrelator_resampler(block, rem_carr, dphi, 0.0, rem_code, step, 0.0, nn)
+
+    n_ep = 2000
+    g = run_tracking(corr_gpu, iq, fs, acq_delay, float(r["doppler"]), n_ep)
+    mc.free()
+    eng.close()
+
+    # ---- the same loop over the reference's own correlator
+    if oracle.ref is not None:
+        oracle.ref.select_arch("a_avx")
+        h = oracle.ref.mc_create(4096, 3, high_dyn=False)
+        oracle.ref.mc_set_code(h, code, shifts)
+
+        def corr_cpu(block, rem_carr, dphi, rem_code, step, nn):
+            return oracle.ref.mc_correlate(h, block, 3, rem_carr, dphi, 0.0, rem_code, step, 0.0, nn)
+    else:
+        def corr_cpu(block, rem_carr, dphi, rem_code, step, nn):
+            return oracle.port.multicorrelator(1, block, code, shifts, rem_carr, dphi, rem_code, step, nn)
+    c = run_tracking(corr_cpu, iq, fs, acq_delay, float(r["doppler"]), n_ep)
+    if oracle.ref is not None:
+        oracle.ref.mc_destroy(h)
+
+    assert len(g["P"]) == len(c["P"]) == n_ep
+    # lock: after pull-in the Doppler estimate sits on the truth, the prompt is on the I axis and strong
+    tail = slice(1200, None)   # the 3rd-order PLL needs ~0.8 s to pull a 70 Hz acquisition error in
+    assert abs(np.mean(g["doppler"][tail]) - doppler) < 2.0
+    assert np.std(g["doppler"][tail]) < 6.0
+    snr = np.abs(np.mean(g["P"][tail].real)) / np.std(g["P"][tail].imag)
+    assert snr > 8.0
+    assert np.mean(np.abs(g["code_err"][tail])) < 0.08
+    # the two loops consumed the same samples and produced the same prompts to float accuracy
+    assert np.array_equal(g["pos"], c["pos"])
+    rel = np.abs(g["P"] - c["P"]) / np.abs(c["P"])
+    assert np.max(rel) < 2e-3, np.max(rel)
+    assert np.max(np.abs(g["doppler"] - c["doppler"])) < 0.05
+    # truth check of the code tracking: sample positions advance by the true code period
+    true_len = 1023 / (1.023e6 * (1 + doppler / GPS_L1_FREQ)) * fs
+    assert abs((g["pos"][-1] - g["pos"][1200]) / (n_ep - 1 - 1200) - true_len) < 0.01
