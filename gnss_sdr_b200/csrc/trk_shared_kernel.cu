@@ -122,17 +122,35 @@ __device__ void warp_correlate_general(const b200_trk_item& it, const ChanDesc& 
 // are lane state that continues seamlessly from tile to tile (tiles are contiguous).
 // MASKED = the tile sticks out of [0, body): samples outside contribute zero and evaluate the chip
 // index of the nearest sample inside (always within the code window).
-template <int TAPS, bool MASKED>
-__device__ __forceinline__ void warp_tile(const float2* __restrict__ tile, float vlo, float vhi, float step, const float2 (&aux2)[TAPS],
+// where a warp gets the tile's samples from: the CTA's shared ring (normal case) ...
+struct SmemTileLoader
+{
+    const float4* p;  // tile + lane
+    __device__ __forceinline__ float4 operator()(int k) const { return p[32 * k]; }
+};
+// ... or straight from the band store, when the group's items cannot share a window (different bands,
+// epochs far apart): same arithmetic, the samples just come through L2 per item as in trk_kernels.cu.
+struct GlobalTileLoader
+{
+    const float2* base;
+    unsigned long long mask, off, limit;  // off = band offset of the tile's first sample + 2*lane (even)
+    __device__ __forceinline__ float4 operator()(int k) const
+    {
+        const unsigned long long o = off + 64ULL * static_cast<unsigned long long>(k);
+        if (mask == ~0ULL && o + 2ULL > limit) return make_float4(0.f, 0.f, 0.f, 0.f);  // linear band: stay inside
+        return ldg_stream16(base + (o & mask));
+    }
+};
+
+template <int TAPS, bool MASKED, class Loader>
+__device__ __forceinline__ void warp_tile(const Loader& load, float vlo, float vhi, float step, const float2 (&aux2)[TAPS],
     unsigned int tbl_off, float2 Dr2, float2 Di2, float& fa, float& fb, float2& zr, float2& zi, float2 (&are)[TAPS], float2 (&aim)[TAPS])
 {
-    const int lane = threadIdx.x & 31;
     const float2 magic2 = make_float2(12582912.0f, 12582912.0f);
-    const float4* p = reinterpret_cast<const float4*>(tile) + lane;
 #pragma unroll
     for (int k = 0; k < kShTile / 64; k++)
         {
-            const float4 v = p[32 * k];
+            const float4 v = load(k);
             float ua = fa, ub = fb;
             float2 xa = make_float2(v.x, v.y), xb = make_float2(v.z, v.w);
             if (MASKED)
@@ -283,6 +301,7 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
     for (int t = 0; t < TAPS; t++) acc[t] = make_float2(0.f, 0.f);
 
     bool table_path = false, whole_table = false;
+    unsigned long long my_hull = 0;
     int body = 0, a_i = 0, t_first = 0, t_last = 0;
     float step = 0.f;
     unsigned int tbl_off = 0;
@@ -309,7 +328,7 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
             // The code replica is staged per TILE: a tile spans 512*step chips (+ the tap spread), so a
             // 256-entry window per warp serves any code length (1023-chip C/A, 8184-value E1, 10230-chip L5).
             const float span_bound = ceilf(fabsf(step) * static_cast<float>(kShTile)) + ceilf(smax - smin) + 6.0f;
-            table_path = sm.share && !ch->high_dyn && span_bound <= static_cast<float>(kShWin) && fabsf(step) * static_cast<float>(it.n) < 4.0e6f &&
+            table_path = !ch->high_dyn && span_bound <= static_cast<float>(kShWin) && fabsf(step) * static_cast<float>(it.n) < 4.0e6f &&
                          fabsf(smax) < 1.0e5f && fabsf(smin) < 1.0e5f && fabsf(rem) < 1.0e6f;
             if (table_path)
                 {
@@ -344,7 +363,10 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
                                 __syncwarp();
                             }
                     }
-                    a_i = static_cast<int>(sm.item_start[warp] - hull_start);
+                    // tiles are counted from the group's hull when the window is shared, else from this item's
+                    // own (even-aligned) start
+                    my_hull = sm.share ? hull_start : (sm.item_start[warp] & ~1ULL);
+                    a_i = static_cast<int>(sm.item_start[warp] - my_hull);
                     t_first = a_i / kShTile;
                     t_last = (a_i + body + kShTile - 1) / kShTile;
                     const float2 D = phasor_from_turns(DT * 64ULL);
@@ -370,6 +392,70 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
     int tiles_in_group = 0;
     int next_wb = 0;
     float fa = static_cast<float>(t_first * kShTile + 2 * lane - a_i), fb = fa + 1.0f;
+    // one tile of this warp's epoch; `load` says where the samples come from
+    auto process_tile = [&](int t, const auto& load) {
+        const int n_tile0 = t * kShTile - a_i;
+        const bool interior = (n_tile0 >= 0) && (n_tile0 + kShTile <= body);
+        // samples of this tile that belong to the epoch
+        const int n_lo = max(n_tile0, 0), n_hi = min(n_tile0 + kShTile, body) - 1;
+        const float vlo = static_cast<float>(n_lo), vhi = static_cast<float>(n_hi);
+        if (!whole_table)
+            {
+                // sliding code window: the replica values this tile touches, staged with cp.async
+                // (LDGSTS, no registers) one tile AHEAD so the L2 latency hides behind the
+                // correlation of the current tile.  window(t) lives in half (t & 1) of tbl[warp].
+                auto stage_window = [&](int tt) {
+                    const int m0 = tt * kShTile - a_i;
+                    const float lo_f = static_cast<float>(max(m0, 0)), hi_f = static_cast<float>(min(m0 + kShTile, body) - 1);
+                    int wlo = 0x7fffffff, whi = -0x7fffffff - 1;
+#pragma unroll
+                    for (int q = 0; q < TAPS; q++)
+                        {
+                            const int i0 = chip_index_avx(step, lo_f, aux2[q].x);
+                            const int i1 = chip_index_avx(step, hi_f, aux2[q].x);
+                            wlo = min(wlo, min(i0, i1));
+                            whi = max(whi, max(i0, i1));
+                        }
+                    const int wb = wlo - 1;
+                    const int wspan = min(whi - wlo + 3, kShWin);  // <= kShWin by the span_bound test
+                    const int L = ch->code_len;
+                    int r = mod_pos(wb + lane, L);
+                    const int stride = 32 % L;
+                    float* dst = &sm.tbl[warp][(tt & 1) * kShWin];
+                    for (int j = lane; j < wspan; j += 32)
+                        {
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + j)), "l"(ch->code + r) : "memory");
+                            r += stride;
+                            if (r >= L) r -= L;
+                        }
+                    return wb;
+                };
+                if (t == t_first) next_wb = stage_window(t);
+                const int wb = next_wb;
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+                if (t + 1 < t_last) next_wb = stage_window(t + 1);
+                asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.tbl[warp][(t & 1) * kShWin])), "r"(4u * (static_cast<unsigned int>(wb) + 0x4B400000u)));
+            }
+        if (interior)
+            warp_tile<TAPS, false>(load, vlo, vhi, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
+        else
+            warp_tile<TAPS, true>(load, vlo, vhi, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
+        if (++tiles_in_group == kShReseed / 8)
+            {
+                // re-seed: the group seed advances by G = exp(j DT 64*kShReseed) and replaces the
+                // running phasor (bounds the drift of the 64 recurrence steps in between)
+                const float2 t2 = __fmul2_rn(zi2, Gi2);
+                const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
+                zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
+                zr2 = ngr;
+                zr = zr2;
+                zi = zi2;
+                tiles_in_group = 0;
+            }
+        __syncwarp();
+    };
+
     for (int t = 0; t < n_tiles; t++)
         {
             const int s = t % kShStages;
@@ -380,68 +466,19 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
             mbar_wait(&sm.full[s], par);
             if (table_path && t >= t_first && t < t_last)
                 {
-                    const int n_tile0 = t * kShTile - a_i;
-                    const bool interior = (n_tile0 >= 0) && (n_tile0 + kShTile <= body);
-                    // samples of this tile that belong to the epoch
-                    const int n_lo = max(n_tile0, 0), n_hi = min(n_tile0 + kShTile, body) - 1;
-                    const float vlo = static_cast<float>(n_lo), vhi = static_cast<float>(n_hi);
-                    if (!whole_table)
-                        {
-                            // sliding code window: the replica values this tile touches, staged with cp.async
-                            // (LDGSTS, no registers) one tile AHEAD so the L2 latency hides behind the
-                            // correlation of the current tile.  window(t) lives in half (t & 1) of tbl[warp].
-                            auto stage_window = [&](int tt) {
-                                const int m0 = tt * kShTile - a_i;
-                                const float lo_f = static_cast<float>(max(m0, 0)), hi_f = static_cast<float>(min(m0 + kShTile, body) - 1);
-                                int wlo = 0x7fffffff, whi = -0x7fffffff - 1;
-#pragma unroll
-                                for (int q = 0; q < TAPS; q++)
-                                    {
-                                        const int i0 = chip_index_avx(step, lo_f, aux2[q].x);
-                                        const int i1 = chip_index_avx(step, hi_f, aux2[q].x);
-                                        wlo = min(wlo, min(i0, i1));
-                                        whi = max(whi, max(i0, i1));
-                                    }
-                                const int wb = wlo - 1;
-                                const int wspan = min(whi - wlo + 3, kShWin);  // <= kShWin by the span_bound test
-                                const int L = ch->code_len;
-                                int r = mod_pos(wb + lane, L);
-                                const int stride = 32 % L;
-                                float* dst = &sm.tbl[warp][(tt & 1) * kShWin];
-                                for (int j = lane; j < wspan; j += 32)
-                                    {
-                                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + j)), "l"(ch->code + r) : "memory");
-                                        r += stride;
-                                        if (r >= L) r -= L;
-                                    }
-                                return wb;
-                            };
-                            if (t == t_first) next_wb = stage_window(t);
-                            const int wb = next_wb;
-                            asm volatile("cp.async.wait_all;" ::: "memory");
-                            __syncwarp();
-                            if (t + 1 < t_last) next_wb = stage_window(t + 1);
-                            asm("sub.u32 %0, %1, %2;" : "=r"(tbl_off) : "r"(smem_u32(&sm.tbl[warp][(t & 1) * kShWin])), "r"(4u * (static_cast<unsigned int>(wb) + 0x4B400000u)));
-                        }
-                    if (interior)
-                        warp_tile<TAPS, false>(&sm.tiles[s][0], vlo, vhi, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
-                    else
-                        warp_tile<TAPS, true>(&sm.tiles[s][0], vlo, vhi, step, aux2, tbl_off, Dr2, Di2, fa, fb, zr, zi, are, aim);
-                    if (++tiles_in_group == kShReseed / 8)
-                        {
-                            // re-seed: the group seed advances by G = exp(j DT 64*kShReseed) and replaces the
-                            // running phasor (bounds the drift of the 64 recurrence steps in between)
-                            const float2 t2 = __fmul2_rn(zi2, Gi2);
-                            const float2 ngr = __ffma2_rn(zr2, Gr2, make_float2(-t2.x, -t2.y));
-                            zi2 = __ffma2_rn(zr2, Gi2, __fmul2_rn(zi2, Gr2));
-                            zr2 = ngr;
-                            zr = zr2;
-                            zi = zi2;
-                            tiles_in_group = 0;
-                        }
-                    __syncwarp();
+                    const SmemTileLoader ld{reinterpret_cast<const float4*>(&sm.tiles[s][0]) + lane};
+                    process_tile(t, ld);
                 }
             if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+    if (!sm.share && table_path)
+        {
+            // no shared window for this group: stream this item's own tiles from the band store
+            for (int t = t_first; t < t_last; t++)
+                {
+                    const GlobalTileLoader ld{bd.base, bd.mask, my_hull + static_cast<unsigned long long>(t) * kShTile + 2ULL * lane, bd.limit};
+                    process_tile(t, ld);
+                }
         }
     if (have_item && it.n > 0)
         {

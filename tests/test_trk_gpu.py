@@ -491,3 +491,52 @@ def test_shared_window_groups_staggered_integer_exact(capi, oracle, L, taps_shif
         e.close()
     os.environ.pop("B200_TRK_SHARED", None)
     assert np.array_equal(results["0"], results["1"])
+
+
+def test_shared_kernel_groups_that_cannot_share(capi, oracle):
+    """Groups of 8 items whose sample ranges are far apart (channel-major order: 8 consecutive epochs of one
+    channel) or that sit on different bands cannot share a window; each warp then streams its own samples
+    with the same arithmetic.  Integer-exact."""
+    import os
+    import torch
+    n, L, shifts, step = 6000, 1023, [-0.5, 0.0, 0.5], 0.1705
+    rng = np.random.default_rng(4242)
+    n_ch, n_ep = 4, 9
+    total = n * n_ep + 1001
+    xs = [rng.integers(-7, 8, total) for _ in range(2)]           # two bands
+    codes = [(((np.arange(L) * (7919 + 2 * c)) % 31) - 15) for c in range(n_ch)]
+    os.environ["B200_TRK_SHARED"] = "1"
+    e = capi.Engine(0)
+    firsts = []
+    for b in range(2):
+        e.iq_create(b, total)
+        firsts.append(e.iq_push(b, xs[b].astype(np.complex64)))
+    cids = []
+    for c in range(n_ch):
+        cid = e.channel_create(c % 2, 3)                          # channels alternate between the bands
+        e.channel_set_code(cid, codes[c].astype(np.float32), shifts)
+        cids.append(cid)
+    items = np.zeros(n_ch * n_ep, capi.TRK_ITEM_DTYPE)
+    order = []
+    for c in range(n_ch):                                         # channel-major: consecutive epochs of one channel
+        for k in range(n_ep):
+            it = items[len(order)]
+            it["channel"] = cids[c]
+            it["n"] = n
+            it["sample_index"] = firsts[c % 2] + 37 * c + k * n + (k % 2)
+            it["rem_code_phase_chips"] = 0.3 + c
+            it["code_phase_step_chips"] = step
+            order.append((c, k))
+    items_t = torch.from_numpy(items.view(np.uint8)).cuda()
+    out_t = torch.zeros(len(order), 3, 2, dtype=torch.float32, device="cuda")
+    e.trk_batch_dev(items_t.data_ptr(), len(order), out_t.data_ptr(), 3, 1)
+    e.sync()
+    got = out_t.cpu().numpy()
+    e.close()
+    os.environ.pop("B200_TRK_SHARED", None)
+    for i, (c, k) in enumerate(order):
+        _, idx = oracle.port.resampler(1, codes[c].astype(np.float32), 0.3 + c, step, shifts, n, return_idx=True)
+        s0 = 37 * c + k * n + (k % 2)
+        want = int_oracle(xs[c % 2][s0:s0 + n], codes[c], idx)
+        assert np.array_equal(got[i, :, 0].astype(np.int64), want), (c, k)
+        assert np.all(got[i, :, 1] == 0)
