@@ -46,7 +46,9 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False, ext
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         obj = obj if not out else obj[:-2] + "_" + os.path.basename(out) + ".o"
-        cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
+        # *_nofma.cu: host-parity arithmetic (DLL/PLL loop) - every multiply and add rounds separately
+        per_file = ["--fmad=false"] if src.endswith("_nofma.cu") else []
+        cmd = [NVCC] + FLAGS + per_file + list(extra) + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -104,6 +104,57 @@ _SIGS.update({
     "b200_acq_destroy": ([_vp], C.c_int),
 })
 
+
+
+class TrkLoopConf(C.Structure):
+    """b200_trk_loop_conf: Dll_Pll_Conf / dll_pll_veml_tracking members the device loop needs."""
+    _fields_ = [
+        ("fs_in", C.c_double), ("code_chip_rate", C.c_double), ("signal_carrier_freq", C.c_double),
+        ("code_period", C.c_double), ("carrier_lock_th", C.c_double),
+        ("code_length_chips", C.c_uint32), ("vector_length", C.c_uint32), ("pull_in_time_s", C.c_uint32),
+        ("bit_synchronization_time_limit_s", C.c_uint32), ("prn", C.c_uint32),
+        ("code_samples_per_chip", C.c_int32), ("pll_filter_order", C.c_int32), ("dll_filter_order", C.c_int32),
+        ("cn0_samples", C.c_int32), ("cn0_min", C.c_int32), ("max_code_lock_fail", C.c_int32),
+        ("max_carrier_lock_fail", C.c_int32), ("cn0_smoother_samples", C.c_int32),
+        ("carrier_lock_test_smoother_samples", C.c_int32), ("veml", C.c_int32), ("cloop", C.c_int32),
+        ("carrier_aiding", C.c_int32), ("enable_fll_pull_in", C.c_int32), ("enable_fll_steady_state", C.c_int32),
+        ("pll_bw_hz", C.c_float), ("dll_bw_hz", C.c_float), ("fll_bw_hz", C.c_float),
+        ("early_late_space_chips", C.c_float), ("slope", C.c_float), ("y_intercept", C.c_float),
+        ("cn0_smoother_alpha", C.c_float), ("carrier_lock_test_smoother_alpha", C.c_float),
+    ]
+
+
+class TrkLoopStatus(C.Structure):
+    _fields_ = [
+        ("state", C.c_int32), ("loss_of_lock", C.c_int32), ("sample_counter", C.c_uint64), ("epochs", C.c_uint64),
+        ("carrier_doppler_hz", C.c_double), ("code_freq_chips", C.c_double), ("rem_code_phase_samples", C.c_double),
+        ("acc_carrier_phase_rad", C.c_double), ("CN0_SNV_dB_Hz", C.c_double), ("carrier_lock_test", C.c_double),
+    ]
+
+
+# b200_trk_dump_record: one epoch of the reference's tracking dump file (108 bytes, unpadded)
+TRK_DUMP_RECORD_DTYPE = np.dtype([
+    ("abs_VE", "<f4"), ("abs_E", "<f4"), ("abs_P", "<f4"), ("abs_L", "<f4"), ("abs_VL", "<f4"),
+    ("prompt_I", "<f4"), ("prompt_Q", "<f4"), ("PRN_start_sample_count", "<u8"),
+    ("acc_carrier_phase_rad", "<f4"), ("carrier_doppler_hz", "<f4"), ("carrier_doppler_rate_hz_s", "<f4"),
+    ("code_freq_chips", "<f4"), ("code_freq_rate_chips", "<f4"), ("carr_error_hz", "<f4"),
+    ("carr_error_filt_hz", "<f4"), ("code_error_chips", "<f4"), ("code_error_filt_chips", "<f4"),
+    ("CN0_SNV_dB_Hz", "<f4"), ("carrier_lock_test", "<f4"), ("aux1", "<f4"), ("aux2", "<f8"),
+    ("PRN", "<u4"), ("TOW_ms", "<u8"), ("WN", "<u4"),
+])
+assert TRK_DUMP_RECORD_DTYPE.itemsize == 108 and C.sizeof(TrkLoopConf) == 152
+
+_SIGS.update({
+    "b200_trk_loop_create": ([_vp, C.c_int, C.POINTER(TrkLoopConf), C.POINTER(C.c_int)], C.c_int),
+    "b200_trk_loop_start": ([_vp, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint64], C.c_int),
+    "b200_trk_loop_run": ([_vp, C.c_int, _vp, _vp], C.c_int),
+    "b200_trk_loop_peek_items": ([_vp, _vp], C.c_int),
+    "b200_trk_loop_set_mode": ([_vp, C.c_int], C.c_int),
+    "b200_trk_loop_step_taps": ([_vp, _vp, _vp, _vp], C.c_int),
+    "b200_trk_loop_status_get": ([_vp, C.c_int, C.POINTER(TrkLoopStatus)], C.c_int),
+    "b200_trk_dump_write": ([C.c_char_p, _vp, C.c_int, C.c_int], C.c_int),
+})
+
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
@@ -226,6 +277,56 @@ class Engine:
 
     def trk_batch_dev(self, items_dev_ptr: int, n_items: int, out_dev_ptr: int, out_stride: int, slices: int = 1):
         _chk(lib.b200_trk_batch_dev(self.h, items_dev_ptr, n_items, out_dev_ptr, out_stride, slices), "b200_trk_batch_dev")
+
+    # free-running DLL/PLL loops on the device
+    def loop_create(self, channel: int, conf: TrkLoopConf) -> int:
+        lid = C.c_int(-1)
+        _chk(lib.b200_trk_loop_create(self.h, channel, C.byref(conf), C.byref(lid)), "b200_trk_loop_create")
+        self._n_loops = getattr(self, "_n_loops", 0) + 1
+        return lid.value
+
+    def loop_start(self, loop_id: int, acq_delay_samples: float, acq_doppler_hz: float, acq_samplestamp: int, nitems_read: int):
+        _chk(lib.b200_trk_loop_start(self.h, loop_id, acq_delay_samples, acq_doppler_hz, acq_samplestamp, nitems_read),
+             "b200_trk_loop_start")
+
+    def loop_run(self, max_epochs: int):
+        """-> (records[n_loops, max_epochs] of TRK_DUMP_RECORD_DTYPE, n_records[n_loops])"""
+        n = getattr(self, "_n_loops", 0)
+        rec = np.zeros((n, max_epochs), TRK_DUMP_RECORD_DTYPE)
+        cnt = np.zeros(n, np.int32)
+        _chk(lib.b200_trk_loop_run(self.h, max_epochs, rec.ctypes.data, cnt.ctypes.data), "b200_trk_loop_run")
+        return rec, cnt
+
+    def loop_set_mode(self, mode: int):
+        _chk(lib.b200_trk_loop_set_mode(self.h, mode), "b200_trk_loop_set_mode")
+
+    def loop_peek_items(self) -> np.ndarray:
+        n = getattr(self, "_n_loops", 0)
+        items = np.zeros(n, TRK_ITEM_DTYPE)
+        _chk(lib.b200_trk_loop_peek_items(self.h, items.ctypes.data), "b200_trk_loop_peek_items")
+        return items
+
+    def loop_step_taps(self, taps: np.ndarray):
+        """taps complex64[n_loops, 8] -> (records[n_loops], logged[n_loops])"""
+        n = getattr(self, "_n_loops", 0)
+        t = np.zeros((n, B200_MAX_TAPS), np.complex64)
+        taps = np.asarray(taps, np.complex64).reshape(n, -1)
+        t[:, :taps.shape[1]] = taps
+        rec = np.zeros(n, TRK_DUMP_RECORD_DTYPE)
+        logged = np.zeros(n, np.int32)
+        _chk(lib.b200_trk_loop_step_taps(self.h, t.ctypes.data, rec.ctypes.data, logged.ctypes.data), "b200_trk_loop_step_taps")
+        return rec, logged
+
+    def loop_status(self, loop_id: int) -> TrkLoopStatus:
+        s = TrkLoopStatus()
+        _chk(lib.b200_trk_loop_status_get(self.h, loop_id, C.byref(s)), "b200_trk_loop_status_get")
+        return s
+
+
+def trk_dump_write(filename: str, records: np.ndarray, append: bool = False):
+    """Write records in the reference's tracking dump format (dll_pll_veml_tracking.cc:1599-1694)."""
+    records = np.ascontiguousarray(records, TRK_DUMP_RECORD_DTYPE)
+    _chk(lib.b200_trk_dump_write(filename.encode(), records.ctypes.data, records.size, int(append)), "b200_trk_dump_write")
 
 
 class Multicorrelator:

@@ -31,7 +31,7 @@ const char* get_error() { return g_err; }
 
 using namespace b200;
 
-namespace
+namespace b200
 {
 int upload_tables(b200_engine* e)
 {
@@ -191,6 +191,7 @@ extern "C"
         if (e->out_pin) cudaFreeHost(e->out_pin);
         if (e->partial) cudaFree(e->partial);
         if (e->counters) cudaFree(e->counters);
+        loops_free(e);
         for (auto& sl : e->slots)
             {
                 if (sl.items_dev) cudaFree(sl.items_dev);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "loop.cuh"
 
 #include <mutex>
 #include <vector>
@@ -83,5 +84,23 @@ struct b200_engine
     static constexpr int kSlots = 16;
     Slot slots[kSlots];
     uint64_t next_ticket{1};
+    // free-running DLL/PLL loops (loop_engine.cu)
+    std::vector<b200::LoopDev> loops;  // host mirror: configuration and start-of-tracking state
+    b200::LoopDev* loops_dev{nullptr};
+    int loops_dev_cap{0};
+    b200_trk_item* loop_items_dev{nullptr};
+    float2* loop_taps_dev{nullptr};
+    int* loop_nrec_dev{nullptr};
+    unsigned int* loop_rec_dev{nullptr};
+    size_t loop_rec_cap{0};  // 32-bit words
+    int loop_mode{-1};       // 0 persistent kernel (default), 1 one launch pair per epoch with slices = 1, 2 same with automatic slices
 };
+
+namespace b200
+{
+// engine.cu
+int upload_tables(b200_engine* e);
+int ensure_partials(b200_engine* e, int n_items, int slices);
+void loops_free(b200_engine* e);  // loop_engine.cu
+}  // namespace b200
 

@@ -140,6 +140,126 @@ extern "C"
      * correlation (SMs) overlap.  These are the trk_submit / trk_wait of SURVEY 8b. */
     int b200_trk_submit(b200_engine* e, const b200_trk_item* items_host, int n_items, int out_stride, uint64_t* ticket);
     int b200_trk_wait(b200_engine* e, uint64_t ticket, b200_cf32* out_host);
+    /* ---- tracking: free-running DLL/PLL loops on the device -------------------- */
+    /* One loop = the per-epoch cycle of one dll_pll_veml_tracking block in its tracking state
+     * (src/algorithms/tracking/gnuradio_blocks/dll_pll_veml_tracking.cc, general_work case 1 = pull-in
+     * alignment :1948-1980 and case 2 :1982-2015: do_correlation_step :1232-1257,
+     * cn0_and_tracking_lock_status :1167-1224, run_dll_pll :1260-1347, update_tracking_vars :1409-1483,
+     * log_data :1599-1694), evaluated on the device between correlator launches, so that epoch k+1's
+     * NCO commands never visit the host.  Types follow the reference member by member (float where it
+     * is float, double where it is double).  Bit synchronisation, the secondary-code search, extended
+     * integration (states 3/4) and telemetry stay with the host, which reads the per-epoch records.
+     * Field names are Dll_Pll_Conf's (src/algorithms/tracking/libs/dll_pll_conf.h:32-89) or the
+     * block's own members (dll_pll_veml_tracking.h:128-222). */
+    typedef struct b200_trk_loop_conf
+    {
+        double fs_in;
+        double code_chip_rate;       /* d_code_chip_rate */
+        double signal_carrier_freq;  /* d_signal_carrier_freq */
+        double code_period;          /* d_code_period [s] */
+        double carrier_lock_th;
+        uint32_t code_length_chips;  /* d_code_length_chips */
+        uint32_t vector_length;      /* samples correlated per epoch (adapter: round(fs/(rate/length))) */
+        uint32_t pull_in_time_s;
+        uint32_t bit_synchronization_time_limit_s; /* fail-safe of :2001-2006; 0xFFFFFFFF disables it */
+        uint32_t prn;
+        int32_t code_samples_per_chip; /* d_code_samples_per_chip: 1, or 2 for Galileo E1 sinBOC */
+        int32_t pll_filter_order;      /* 2 or 3 */
+        int32_t dll_filter_order;      /* 1..3 */
+        int32_t cn0_samples;           /* <= 64 */
+        int32_t cn0_min;
+        int32_t max_code_lock_fail;
+        int32_t max_carrier_lock_fail;
+        int32_t cn0_smoother_samples;
+        int32_t carrier_lock_test_smoother_samples;
+        int32_t veml;                  /* d_veml: 5 taps VE,E,P,L,VL instead of 3 taps E,P,L */
+        int32_t cloop;                 /* d_cloop: Costas discriminator (true unless a pilot is tracked) */
+        int32_t carrier_aiding;
+        int32_t enable_fll_pull_in;
+        int32_t enable_fll_steady_state;
+        float pll_bw_hz;
+        float dll_bw_hz;
+        float fll_bw_hz;
+        float early_late_space_chips;  /* becomes Dll_Pll_Conf::spc in state 2 (:1993) */
+        float slope;
+        float y_intercept;
+        float cn0_smoother_alpha;
+        float carrier_lock_test_smoother_alpha;
+    } b200_trk_loop_conf; /* 152 bytes */
+
+    /* One tracking dump record, byte for byte what log_data() writes per epoch
+     * (dll_pll_veml_tracking.cc:1599-1694; read back by
+     * tests/unit-tests/signal-processing-blocks/libs/tracking_dump_reader.cc:22-50).  108 bytes,
+     * unpadded: the u64 and the double sit on 4-byte boundaries. */
+#pragma pack(push, 1)
+    typedef struct b200_trk_dump_record
+    {
+        float abs_VE, abs_E, abs_P, abs_L, abs_VL;
+        float prompt_I, prompt_Q;
+        uint64_t PRN_start_sample_count; /* nitems_read + d_current_prn_length_samples */
+        float acc_carrier_phase_rad;
+        float carrier_doppler_hz;
+        float carrier_doppler_rate_hz_s;
+        float code_freq_chips;
+        float code_freq_rate_chips;
+        float carr_error_hz;
+        float carr_error_filt_hz;
+        float code_error_chips;
+        float code_error_filt_chips;
+        float CN0_SNV_dB_Hz;
+        float carrier_lock_test;
+        float aux1; /* d_rem_code_phase_samples */
+        double aux2;
+        uint32_t PRN;
+        uint64_t TOW_ms;
+        uint32_t WN;
+    } b200_trk_dump_record;
+#pragma pack(pop)
+
+    /* Loop status word returned by b200_trk_loop_status */
+    typedef struct b200_trk_loop_status
+    {
+        int32_t state;              /* d_state: 0 standby (never started / loss of lock), 1 pull-in, 2 tracking */
+        int32_t loss_of_lock;       /* 1 if the last cycle raised the reference's "events" message 3 */
+        uint64_t sample_counter;    /* nitems_read(0): absolute index of the next epoch's first sample */
+        uint64_t epochs;            /* valid DLL/PLL cycles (= records written) since start */
+        double carrier_doppler_hz;
+        double code_freq_chips;
+        double rem_code_phase_samples;
+        double acc_carrier_phase_rad;
+        double CN0_SNV_dB_Hz;
+        double carrier_lock_test;
+    } b200_trk_loop_status;
+
+    /* Create a loop over tracking channel `channel` (b200_trk_channel_create + b200_trk_channel_set_code
+     * with the E,P,L / VE,E,P,L,VL shifts of start_tracking :1041-1054).  Filter coefficients are derived
+     * here as Tracking_loop_filter::update_coefficients (tracking_loop_filter.cc:86-186) and
+     * Tracking_FLL_PLL_filter::set_params (tracking_FLL_PLL_filter.cc:23-54) do. */
+    int b200_trk_loop_create(b200_engine* e, int channel, const b200_trk_loop_conf* conf, int* loop_id);
+    /* start_tracking() (:791-1078): take the acquisition result; nitems_read = absolute index of the
+     * first sample the tracking block would see next (state 1 then skips to the PRN start). */
+    int b200_trk_loop_start(b200_engine* e, int loop_id, double acq_delay_samples, double acq_doppler_hz,
+        uint64_t acq_samplestamp_samples, uint64_t nitems_read);
+    /* Run up to max_epochs cycles of every started loop: per epoch one correlator launch over all loops
+     * and one loop-update launch; a loop whose next vector_length samples are not in its band yet stalls.
+     * records_host: n_loops x max_epochs records (loop-major); n_records_host[loop] = cycles logged.
+     * Either output may be NULL. */
+    int b200_trk_loop_run(b200_engine* e, int max_epochs, b200_trk_dump_record* records_host, int* n_records_host);
+    /* How b200_trk_loop_run schedules the work: 0 (default) one persistent kernel, one CTA per loop, free-running
+     * for max_epochs cycles with no launch per epoch; 1 a correlator launch + a loop-update launch per epoch with
+     * one CTA per loop (bit-identical records to mode 0); 2 the same with each epoch split over several CTAs
+     * (lowest latency for a handful of channels).  Env B200_LOOP_MODE sets the initial value. */
+    int b200_trk_loop_set_mode(b200_engine* e, int mode);
+    /* Prepare (if not already pending) and return the next work item of every loop: the seven scalars
+     * do_correlation_step would pass, for hosts that correlate elsewhere.  n == 0 marks a loop in standby. */
+    int b200_trk_loop_peek_items(b200_engine* e, b200_trk_item* items_host);
+    /* One cycle with caller-supplied correlator outputs (taps_host: n_loops x taps of the loop's channel,
+     * loop-major, stride = 8): the loop arithmetic alone, for hosts that correlate elsewhere and for tests. */
+    int b200_trk_loop_step_taps(b200_engine* e, const b200_cf32* taps_host, b200_trk_dump_record* records_host, int* logged_host);
+    int b200_trk_loop_status_get(b200_engine* e, int loop_id, b200_trk_loop_status* out);
+    /* Append records to a tracking dump file in the reference's format (d_dump_file, :1599-1694). */
+    int b200_trk_dump_write(const char* filename, const b200_trk_dump_record* records, int n_records, int append);
+
     /* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
     int b200_engine_launch_count(b200_engine* e, uint64_t* n);
 

@@ -8,6 +8,9 @@ Inputs are regenerated from seeds by the tests (tests/gnss_synth.py, numpy defau
 fixtures hold only parameters and the reference's outputs:
   trk_ref_golden.npz   Cpu_Multicorrelator_Real_Codes (a_avx kernels, high_dyn false/true) taps,
                        and generic-kernel taps, for the shapes in CASES
+  loop_ref_golden.npz  per-epoch item scalars and 108-byte dump records of the DLL/PLL cycle evaluated with the
+                       reference's own Tracking_loop_filter / Tracking_FLL_PLL_filter / Exponential_Smoother /
+                       discriminator / lock-detector code (oracle/ref_loop.cc) for seeded correlator outputs
   acq_ref_golden.npz   volk_gnsssdr_s32f_sincos_32fc a_avx2 wipe-off rows (bit patterns) for a few
                        Doppler bins, and volk_gnsssdr_32f_index_max_32u results
 """
@@ -28,6 +31,15 @@ CASES = [
     ("gps_25msps_ragged", 103, 25e6, 25003, 1023, 19, [-0.5, 0.0, 0.5], 4711.0, 12.9, 1.0, False),
     ("e1_50msps", 104, 50e6, 200000, 8184, None, [-1.2, -0.3, 0.0, 0.3, 1.2], -1234.5, 1000.25, 2.0, False),
     ("gps_25msps_hd", 105, 25e6, 25000, 1023, 9, [-0.5, 0.0, 0.5], 2500.0, 600.1, 1.0, True),
+]
+
+
+# DLL/PLL loop fixture: (name, conf overrides, epochs); taps = loop_harness.synthetic_taps(epochs, taps, LOOP_SEED)
+LOOP_SEED = 77
+LOOP_CASES = [
+    ("gps_default", dict(), 600),
+    ("pll2_dll1_fll", dict(pll_filter_order=2, dll_filter_order=1, enable_fll_pull_in=1, pull_in_time_s=1), 600),
+    ("veml_e1", dict(veml=1, code_samples_per_chip=2, early_late_space_chips=0.15, dll_filter_order=3), 600),
 ]
 
 
@@ -77,6 +89,26 @@ def main():
             acq[f"sincos/{int(fs)}/{int(f)}/tail"] = bits[-128:].copy()
             acq[f"sincos/{int(fs)}/{int(f)}/xor_sum"] = np.array([np.bitwise_xor.reduce(bits), np.sum(bits.astype(np.uint64)) & 0xFFFFFFFFFFFF], np.uint64)
     np.savez(os.path.join(HERE, "acq_ref_golden.npz"), **acq)
+    # DLL/PLL loop: records and item scalars produced by the reference's own loop-filter / discriminator /
+    # lock-detector / smoother objects (oracle/_ref/liboracle_ref_loop.so) for seeded correlator outputs
+    from oracle import loop as ol
+    import loop_harness as lh
+    lp = {}
+    for name, kw, n_ep in LOOP_CASES:
+        conf = ol.default_conf(fs_in=4e6, **kw)
+        R = ol.RefLoop(conf)
+        R.start(524.3, 1680.0, 1000, 9000)
+        taps = lh.synthetic_taps(n_ep, 5 if conf.veml else 3, seed=LOOP_SEED)
+        recs, items = [], []
+        for k in range(n_ep):
+            s, n, p6 = R.prepare()
+            items.append(np.concatenate([[s, n], p6.view(np.uint32)]).astype(np.uint64))
+            ok, r = R.update(taps[k])
+            assert ok
+            recs.append(r)
+        lp[f"{name}/records"] = np.frombuffer(np.array(recs, ol.DUMP_RECORD_DTYPE).tobytes(), np.uint8)
+        lp[f"{name}/items"] = np.array(items, np.uint64)
+    np.savez_compressed(os.path.join(HERE, "loop_ref_golden.npz"), **lp)
     print("wrote", os.listdir(HERE))
 
 
