@@ -273,7 +273,7 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
     return out
 
 
-def bench_closed_loop(capi, eng, svs, cids, n_epochs=990, repeats=3):
+def bench_closed_loop(capi, eng, svs, cids, n_epochs=990, repeats=3, replicas=1, with_launch_mode=True):
     """Free-running DLL/PLL on the device: the 32 channels of the C2 band tracked in closed loop,
     correlator launch and loop-update launch alternating on the engine stream, no host round trip per epoch.
     Timed with the engine's CUDA events around b200_trk_loop_run (includes the D2H of the dump records)."""
@@ -287,6 +287,11 @@ def bench_closed_loop(capi, eng, svs, cids, n_epochs=990, repeats=3):
     conf.veml, conf.cloop, conf.carrier_aiding, conf.enable_fll_pull_in, conf.enable_fll_steady_state = 0, 1, 1, 0, 0
     conf.pll_bw_hz, conf.dll_bw_hz, conf.fll_bw_hz, conf.early_late_space_chips = 35.0, 2.0, 35.0, 0.5
     conf.slope, conf.y_intercept, conf.cn0_smoother_alpha, conf.carrier_lock_test_smoother_alpha = 1.0, 1.0, 0.002, 0.002
+    # replicas > 1: several independent loops per satellite (own state, different acquisition Doppler errors) to
+    # show how closed-loop throughput scales with the number of channels resident on the GPU
+    base = getattr(eng, "_n_loops", 0)
+    svs = [dict(sv, acq_err=20.0 - 7.0 * r) for r in range(replicas) for sv in svs]
+    cids = list(cids) * replicas
     lids = []
     for sv, cid in zip(svs, cids):
         conf.prn = sv["prn"]
@@ -298,7 +303,7 @@ def bench_closed_loop(capi, eng, svs, cids, n_epochs=990, repeats=3):
             for sv, lid in zip(svs, lids):
                 rate = CA_RATE * (1.0 + sv["doppler"] / GPS_L1_FREQ)
                 delay = ((1023.0 - sv["code_phase_chips"]) % 1023.0) / (rate / FS)      # sample of the first PRN start
-                eng.loop_start(lid, delay, sv["doppler"] + 20.0, 0, 0)                  # acquisition-grade Doppler
+                eng.loop_start(lid, delay, sv["doppler"] + sv["acq_err"], 0, 0)         # acquisition-grade Doppler
             l0 = eng.launch_count()
             eng.timer_start()
             rec, cnt = eng.loop_run(n_epochs)
@@ -308,9 +313,10 @@ def bench_closed_loop(capi, eng, svs, cids, n_epochs=990, repeats=3):
                 best = (ms, rec, cnt, launches)
         return best
 
-    per_launch = run_mode(2)
+    per_launch = run_mode(2) if with_launch_mode else None
     best = run_mode(0)
     ms, rec, cnt, launches = best
+    rec, cnt = rec[base:], cnt[base:]          # loops created by earlier calls on this engine are in standby
     tail = rec[:, n_epochs - 200:n_epochs - 5]
     dopp_err = np.array([abs(float(np.mean(tail[i]["carrier_doppler_hz"])) - svs[i]["doppler"]) for i in range(len(svs))])
     locked = int(np.sum((dopp_err < 3.0) & (cnt >= n_epochs - 2)))
@@ -320,7 +326,8 @@ def bench_closed_loop(capi, eng, svs, cids, n_epochs=990, repeats=3):
             "realtime_factor": n_epochs * 1e-3 / (ms * 1e-3), "us_per_epoch": ms * 1e3 / n_epochs,
             "gpu_launches": int(launches), "channels_locked": locked, "max_doppler_error_hz": float(np.max(dopp_err)),
             "mean_cn0_dbhz": float(np.mean(tail["CN0_SNV_dB_Hz"])),
-            "per_epoch_launch_mode": {"ms": per_launch[0], "gpu_launches": int(per_launch[3]), "us_per_epoch": per_launch[0] * 1e3 / n_epochs},
+            "per_epoch_launch_mode": ({"ms": per_launch[0], "gpu_launches": int(per_launch[3]), "us_per_epoch": per_launch[0] * 1e3 / n_epochs}
+                                      if per_launch else None),
             "note": "persistent kernel: one CTA per channel free-runs prepare -> correlate -> discriminators, loop filters, NCO, "
                     "lock detectors, dump record, epoch after epoch with no launch and no host round trip; epoch k+1 depends on "
                     "epoch k, so each channel is latency-bound and throughput scales with the channel count up to the number of "
@@ -613,6 +620,7 @@ def main():
     if not args.no_loop and rank == 0:
         try:
             closed = bench_closed_loop(capi, eng, svs, cids)
+            closed["x8_channels"] = bench_closed_loop(capi, eng, svs, cids, replicas=8, with_launch_mode=False)
         except Exception as ex:
             closed = {"error": repr(ex)}
 
