@@ -47,7 +47,7 @@ def assert_records_match(got, want, what=""):
         assert not bad.any(), (what, f, int(np.argmax(bad)), g[bad][:3], w[bad][:3])
 
 
-def make_engine_with_loops(capi, oracle, confs, fs, band_samples=None, prns=None):
+def make_engine_with_loops(capi, oracle, confs, fs, band_samples=None, prns=None, tables=None):
     e = capi.Engine()
     if band_samples is not None:
         e.iq_create(0, len(band_samples) + 16)
@@ -59,9 +59,12 @@ def make_engine_with_loops(capi, oracle, confs, fs, band_samples=None, prns=None
         spc = c.code_samples_per_chip
         els, vels = c.early_late_space_chips, 0.5
         shifts = ([-vels * spc, -els * spc, 0.0, els * spc, vels * spc] if c.veml else [-els * spc, 0.0, els * spc])
-        code = oracle.port.gps_ca_code(prns[i] if prns else 1 + i)
-        if spc == 2:
-            code = np.repeat(code, 2)
+        if tables is not None:
+            code = tables[i]
+        else:
+            code = oracle.port.gps_ca_code(prns[i] if prns else 1 + i)
+            if spc == 2:
+                code = np.repeat(code, 2)
         ch = e.channel_create(0, taps)
         e.channel_set_code(ch, code, shifts)
         ids.append(e.loop_create(ch, conf_to_capi(capi, c)))
@@ -244,6 +247,47 @@ def test_persistent_kernel_and_per_epoch_launches_agree_bit_for_bit(oracle):
         e.close()
     assert np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
     assert out[0][0].tobytes() == out[1][0].tobytes()
+
+
+def test_galileo_e1_like_veml_loop_with_4ms_epochs(oracle):
+    """Galileo-E1-shaped loop: sinBOC(1,1) table with 2 samples per chip (8184 values), 4 ms code period
+    (vector_length 16000 at 4 Msps), five taps VE,E,P,L,VL with the VEML discriminator, C/N0 smoother initialised
+    over cn0_smoother_samples / 4 estimates.  Persistent kernel vs the oracle closed loop."""
+    from gnss_sdr_b200 import capi
+    fs, doppler, cn0 = 4e6, -1540.0, 45.0
+    rng = np.random.default_rng(17)
+    primary = (2 * rng.integers(0, 2, 4092) - 1).astype(np.int32)
+    table = oracle.port.sinboc11(primary)
+    L = len(table)
+    rate = 1.023e6 * 2.0 * (1.0 + doppler / 1575.42e6)           # table entries per second
+    cp = 2711.0                                                      # table entries at sample 0
+    delay = ((L - cp) % L) / (rate / fs)
+    n = int(fs * 2.0)
+    iq = gs.make_iq({1: table}, fs, n, [dict(prn=1, doppler=doppler, code_phase_chips=cp, cn0=cn0)], seed=23, chips_per_table_chip=2.0)
+    conf = ol.default_conf(fs_in=fs, prn=1, code_length_chips=4092, code_period=0.004, vector_length=16000, code_samples_per_chip=2,
+                           veml=1, early_late_space_chips=0.15, pull_in_time_s=1)
+    e, ids = make_engine_with_loops(capi, oracle, [conf], fs, band_samples=iq, tables=[table])
+    e.iq_push(0, iq)
+    e.loop_start(ids[0], delay + 0.2, doppler + 25.0, 0, 0)
+    n_ep = 490
+    rec, cnt = e.loop_run(n_ep)
+    assert cnt[0] == n_ep
+    o = ol.PortLoop(conf)
+    o.start(delay + 0.2, doppler + 25.0, 0, 0)
+    shifts = [-0.5 * 2, -0.15 * 2, 0.0, 0.15 * 2, 0.5 * 2]
+    want = lh.run_closed_loop(o, lh.PortCorrelator(oracle.port, table, shifts), iq, n_ep)
+    got = rec[0]
+    assert len(want) == n_ep
+    tail = slice(n_ep - 100, n_ep)
+    assert abs(np.mean(got["carrier_doppler_hz"][tail]) - doppler) < 1.0
+    assert abs(np.mean(got["CN0_SNV_dB_Hz"][tail]) - cn0) < 1.5
+    assert np.all(got["abs_P"][tail] > got["abs_E"][tail]) and np.all(got["abs_P"][tail] > got["abs_L"][tail])
+    assert np.max(np.abs(got["carrier_doppler_hz"] - want["carrier_doppler_hz"])) < 0.7
+    assert np.max(np.abs(got["aux1"] - want["aux1"])) < 5e-2
+    d = np.diff(got["PRN_start_sample_count"].astype(np.int64))
+    assert set(np.unique(d)) <= {15999, 16000, 16001}
+    assert np.max(np.abs(got["PRN_start_sample_count"].astype(np.int64) - want["PRN_start_sample_count"].astype(np.int64))) <= 1
+    e.close()
 
 
 def test_loops_stall_on_missing_samples_and_resume(oracle):
