@@ -35,6 +35,12 @@ struct FftPlan
     int n1;       // 1 = whole transform in shared memory
     int n_total;  // transform size seen by the caller
     int tw_goff;  // twiddles of the global stage: exp(-2 pi j k / n_total), k < n
+    // Storage order of spectra in global memory (single-level plans with >= 2 stages): the digit-reversed
+    // position p = b * perm_r + q (perm_r = radix of the last forward stage, q < perm_r) lives at
+    // q * perm_nb + b.  The last forward stage then stores, and the first inverse stage loads, with
+    // consecutive threads on consecutive addresses, so neither needs a pass through shared memory.
+    int perm_r;   // 1 = natural digit-reversed order (no fusion)
+    int perm_nb;  // n / perm_r
 };
 
 __device__ __forceinline__ int fast_div(int i, int m, unsigned int magic)
@@ -246,6 +252,80 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
         }
 }
 
+// Last forward (DIF) stage, block length R, no twiddles: shared memory -> global in the permuted storage order
+// (see FftPlan::perm_r).  CONJ stores the conjugate (local-code spectrum, volk_32fc_conjugate_32fc).
+template <int R, bool CONJ>
+__device__ __forceinline__ void fft_last_fwd_stage_to_global(const float2* __restrict__ s, float2* __restrict__ out, int nb)
+{
+#pragma unroll 2
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        {
+            float2 v[R];
+#pragma unroll
+            for (int q = 0; q < R; q++) v[q] = s[i * R + q];
+            Bfly<R>::fwd(v);
+#pragma unroll
+            for (int q = 0; q < R; q++) out[q * nb + i] = CONJ ? make_float2(v[q].x, -v[q].y) : v[q];
+        }
+}
+
+template <bool CONJ>
+__device__ __forceinline__ void fft_last_fwd_stage_to_global_dispatch(int radix, const float2* s, float2* out, int nb)
+{
+    switch (radix)
+        {
+        case 2: fft_last_fwd_stage_to_global<2, CONJ>(s, out, nb); break;
+        case 3: fft_last_fwd_stage_to_global<3, CONJ>(s, out, nb); break;
+        case 4: fft_last_fwd_stage_to_global<4, CONJ>(s, out, nb); break;
+        case 5: fft_last_fwd_stage_to_global<5, CONJ>(s, out, nb); break;
+        case 7: fft_last_fwd_stage_to_global<7, CONJ>(s, out, nb); break;
+        default: fft_last_fwd_stage_to_global<8, CONJ>(s, out, nb); break;
+        }
+}
+
+// First inverse (DIT) stage, block length R, no twiddles: the point-wise product X . C
+// (volk_32fc_x2_multiply_32fc, separately rounded like the element-wise kernel) is formed from the two
+// permuted-order spectra in global memory and goes through the butterfly into shared memory.
+template <int R>
+__device__ __forceinline__ void fft_first_inv_stage_from_global(const float2* __restrict__ x, const float2* __restrict__ c,
+    float2* __restrict__ s, int nb)
+{
+#pragma unroll 2
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        {
+            float2 a[R], b[R], v[R];
+#pragma unroll
+            for (int q = 0; q < R; q++)
+                {
+                    a[q] = __ldg(x + q * nb + i);
+                    b[q] = __ldg(c + q * nb + i);
+                }
+#pragma unroll
+            for (int q = 0; q < R; q++)
+                {
+                    const float re = __fsub_rn(__fmul_rn(a[q].x, b[q].x), __fmul_rn(a[q].y, b[q].y));
+                    const float im = __fadd_rn(__fmul_rn(a[q].x, b[q].y), __fmul_rn(a[q].y, b[q].x));
+                    v[q] = make_float2(im, re);  // swap_ri: inverse = swap . forward . swap
+                }
+            Bfly<R>::fwd(v);
+#pragma unroll
+            for (int q = 0; q < R; q++) s[i * R + q] = swap_ri(v[q]);
+        }
+}
+
+__device__ __forceinline__ void fft_first_inv_stage_from_global_dispatch(int radix, const float2* x, const float2* c, float2* s, int nb)
+{
+    switch (radix)
+        {
+        case 2: fft_first_inv_stage_from_global<2>(x, c, s, nb); break;
+        case 3: fft_first_inv_stage_from_global<3>(x, c, s, nb); break;
+        case 4: fft_first_inv_stage_from_global<4>(x, c, s, nb); break;
+        case 5: fft_first_inv_stage_from_global<5>(x, c, s, nb); break;
+        case 7: fft_first_inv_stage_from_global<7>(x, c, s, nb); break;
+        default: fft_first_inv_stage_from_global<8>(x, c, s, nb); break;
+        }
+}
+
 template <bool INV, class Sink>
 __device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, int M, unsigned int magic, const float2* tw, Sink& sink)
 {
@@ -257,6 +337,31 @@ __device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, 
         case 5: fft_stage<5, INV>(s, n, M, magic, tw, sink); break;
         case 7: fft_stage<7, INV>(s, n, M, magic, tw, sink); break;
         default: fft_stage<8, INV>(s, n, M, magic, tw, sink); break;
+        }
+}
+
+// forward DIF, spectrum written to global memory in the plan's storage order: all stages in shared memory and
+// a copy when perm_r == 1, else the last stage streams straight to global.  CONJ: store the conjugate.
+template <bool CONJ>
+__device__ __forceinline__ void fft_forward_to_global(float2* s, const FftPlan& pl, const float2* tw, float2* __restrict__ out)
+{
+    StoreSink st_sink;
+    int M = pl.n;
+    const int n_smem_stages = (pl.perm_r > 1) ? pl.n_stages - 1 : pl.n_stages;
+    for (int st = 0; st < n_smem_stages; st++)
+        {
+            __syncthreads();
+            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
+            M /= pl.radix[st];
+        }
+    __syncthreads();
+    if (pl.perm_r > 1)
+        {
+            fft_last_fwd_stage_to_global_dispatch<CONJ>(pl.perm_r, s, out, pl.perm_nb);
+        }
+    else
+        {
+            for (int i = threadIdx.x; i < pl.n; i += blockDim.x) out[i] = CONJ ? make_float2(s[i].x, -s[i].y) : s[i];
         }
 }
 
@@ -291,6 +396,24 @@ __device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, c
     fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw + pl.tw_off[0], last);
 }
 
+
+// inverse DIT of the product of two spectra held in global memory in the plan's storage order (perm_r > 1):
+// first stage from global, stages n_stages-2 .. 1 in place, stage 0 through `last`.
+template <class Sink>
+__device__ __forceinline__ void fft_inverse_from_global(const float2* x, const float2* c, float2* s, const FftPlan& pl, const float2* tw, Sink& last)
+{
+    StoreSink st_sink;
+    fft_first_inv_stage_from_global_dispatch(pl.perm_r, x, c, s, pl.perm_nb);
+    int M = pl.perm_r;
+    for (int st = pl.n_stages - 2; st >= 1; st--)
+        {
+            M *= pl.radix[st];
+            __syncthreads();
+            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
+        }
+    __syncthreads();
+    fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw + pl.tw_off[0], last);
+}
 
 // inverse DIT over all stages in place (two-level path: natural order within the block afterwards)
 __device__ __forceinline__ void fft_inverse_smem_inplace(float2* s, const FftPlan& pl, const float2* tw)

@@ -160,9 +160,8 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_code_fft_kernel(const floa
                 }
             s[i] = v;
         }
-    fft_forward_smem(s, pl, tw);
-    // volk_32fc_conjugate_32fc (:250)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = make_float2(s[i].x, -s[i].y);
+    // forward FFT, then volk_32fc_conjugate_32fc (:250) fused into the store
+    fft_forward_to_global<true>(s, pl, tw, out);
 }
 
 // ---- forward: wipe-off + FFT, one CTA per Doppler bin ------------------------------------------------
@@ -187,9 +186,7 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_fwd_kernel(const float2* _
                 }
             s[i] = v;
         }
-    fft_forward_smem(s, pl, tw);
-    float2* o = X + static_cast<size_t>(d) * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = s[i];
+    fft_forward_to_global<false>(s, pl, tw, X + static_cast<size_t>(d) * n);
 }
 
 // ---- correlation rows ---------------------------------------------------------------------------------
@@ -308,6 +305,13 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* 
         {
             const float2* x = X + static_cast<size_t>(bin) * n;
             const float2* c = codes + static_cast<size_t>(slot) * n;
+            if (pl.perm_r > 1)
+                {
+                    // product (volk_32fc_x2_multiply_32fc, :538) and first inverse stage straight from global memory
+                    fft_inverse_from_global(x, c, s, pl, tw, sink);
+                }
+            else
+                {
 #pragma unroll 4
             for (int i = threadIdx.x; i < n; i += blockDim.x)
                 {
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* 
                     s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
                 }
             fft_inverse_smem(s, pl, tw, sink);
+                }
         }
 
     // CTA reduction with "first maximum" tie-break
@@ -720,6 +725,11 @@ int acq_plan_make(int n_total, FftPlan* pl)
             pl->n1 = 1;
             pl->n_total = n_total;
             pl->tw_goff = 0;
+            if (rc == B200_OK && pl->n_stages >= 2)
+                {
+                    pl->perm_r = pl->radix[pl->n_stages - 1];
+                    pl->perm_nb = pl->n / pl->perm_r;
+                }
             return rc;
         }
     // two-level: smallest supported radix n1 that brings the blocks into shared memory
@@ -758,6 +768,8 @@ static int acq_plan_make_smem(int n, FftPlan* pl)
             }
     if (rem != 1) return B200_ERR_RANGE;  // unsupported prime factor
     pl->n = n;
+    pl->perm_r = 1;
+    pl->perm_nb = n;
     int k = 0;
     // Powers of two first (large sub-block stride m, conflict-free stride-1 accesses), odd radices
     // last: in the final stages consecutive threads are R*m apart and an ODD stride spreads over
