@@ -20,6 +20,7 @@
 namespace b200
 {
 constexpr int kAcqThreads = 1024;
+constexpr int kAcqThreads25 = 512;  // plans with radix-25 stages: 25 values per thread need 128 registers
 constexpr int kAcqMaxStages = 16;
 constexpr int kAcqMaxSmemPoints = 27648;  // 216 KB of float2
 
@@ -41,6 +42,7 @@ struct FftPlan
     // consecutive threads on consecutive addresses, so neither needs a pass through shared memory.
     int perm_r;   // 1 = natural digit-reversed order (no fusion)
     int perm_nb;  // n / perm_r
+    int threads;  // CTA size the plan was made for: kAcqThreads, or kAcqThreads25 when it has radix-25 stages
 };
 
 __device__ __forceinline__ int fast_div(int i, int m, unsigned int magic)
@@ -184,7 +186,100 @@ struct Bfly<8>
     }
 };
 
+// 25 = 5 x 5 (Cooley-Tukey inside the registers of one thread): input n = 5 n1 + n2, output k = k1 + 5 k2,
+// X[k1 + 5 k2] = sum_n2 W5^(n2 k2) W25^(n2 k1) sum_n1 x[5 n1 + n2] W5^(n1 k1).  Two shared-memory passes of a
+// radix-5 pair become one.
+template <>
+struct Bfly<25>
+{
+    static __device__ __forceinline__ float2 mulw(float2 a, float c, float sn)  // a * (c - j sn)
+    {
+        return make_float2(fmaf(a.x, c, a.y * sn), fmaf(a.y, c, -a.x * sn));
+    }
+    static __device__ __forceinline__ void fwd(float2 (&v)[25])
+    {
+        // W25^m = cos(2 pi m/25) - j sin(2 pi m/25), m = n2 * k1
+        const float c1 = 0.96858316112863108f, s1 = 0.24868988716485479f;
+        const float c2 = 0.87630668004386358f, s2 = 0.48175367410171532f;
+        const float c3 = 0.72896862742141155f, s3 = 0.68454710592868862f;
+        const float c4 = 0.53582679497899655f, s4 = 0.84432792550201508f;
+        const float c6 = 0.06279051952931353f, s6 = 0.99802672842827156f;
+        const float c8 = -0.42577929156507272f, s8 = 0.90482705246601947f;
+        const float c9 = -0.63742398974868975f, s9 = 0.77051324277578925f;
+        const float c12 = -0.99211470131447783f, s12 = 0.12533323356430454f;
+        const float c16 = -0.63742398974868952f, s16 = -0.77051324277578936f;
+        float2 t[5];
+#pragma unroll
+        for (int n2 = 0; n2 < 5; n2++)
+            {
+#pragma unroll
+                for (int n1 = 0; n1 < 5; n1++) t[n1] = v[5 * n1 + n2];
+                Bfly<5>::fwd(t);
+#pragma unroll
+                for (int k1 = 0; k1 < 5; k1++) v[5 * k1 + n2] = t[k1];  // A[k1][n2]
+            }
+        v[5 * 1 + 1] = mulw(v[5 * 1 + 1], c1, s1);
+        v[5 * 1 + 2] = mulw(v[5 * 1 + 2], c2, s2);
+        v[5 * 1 + 3] = mulw(v[5 * 1 + 3], c3, s3);
+        v[5 * 1 + 4] = mulw(v[5 * 1 + 4], c4, s4);
+        v[5 * 2 + 1] = mulw(v[5 * 2 + 1], c2, s2);
+        v[5 * 2 + 2] = mulw(v[5 * 2 + 2], c4, s4);
+        v[5 * 2 + 3] = mulw(v[5 * 2 + 3], c6, s6);
+        v[5 * 2 + 4] = mulw(v[5 * 2 + 4], c8, s8);
+        v[5 * 3 + 1] = mulw(v[5 * 3 + 1], c3, s3);
+        v[5 * 3 + 2] = mulw(v[5 * 3 + 2], c6, s6);
+        v[5 * 3 + 3] = mulw(v[5 * 3 + 3], c9, s9);
+        v[5 * 3 + 4] = mulw(v[5 * 3 + 4], c12, s12);
+        v[5 * 4 + 1] = mulw(v[5 * 4 + 1], c4, s4);
+        v[5 * 4 + 2] = mulw(v[5 * 4 + 2], c8, s8);
+        v[5 * 4 + 3] = mulw(v[5 * 4 + 3], c12, s12);
+        v[5 * 4 + 4] = mulw(v[5 * 4 + 4], c16, s16);
+        float2 o[25];
+#pragma unroll
+        for (int k1 = 0; k1 < 5; k1++)
+            {
+#pragma unroll
+                for (int n2 = 0; n2 < 5; n2++) t[n2] = v[5 * k1 + n2];
+                Bfly<5>::fwd(t);
+#pragma unroll
+                for (int k2 = 0; k2 < 5; k2++) o[k1 + 5 * k2] = t[k2];
+            }
+#pragma unroll
+        for (int q = 0; q < 25; q++) v[q] = o[q];
+    }
+};
+
 __device__ __forceinline__ float2 swap_ri(float2 a) { return make_float2(a.y, a.x); }
+
+// w^q for q = 0..R-1 from w^1: a multiply chain for the small radices, a two-level product for radix 25
+// (w^(5a+b) = w^(5a) w^b) so that the dependency depth stays short.
+template <int R>
+__device__ __forceinline__ void twiddle_powers(float2 w1, float2 (&w)[R])
+{
+    w[0] = make_float2(1.f, 0.f);
+    if (R > 1) w[1] = w1;
+    if (R == 25)
+        {
+            w[2] = cmul(w1, w1);
+            w[3] = cmul(w[2], w1);
+            w[4] = cmul(w[2], w[2]);
+            w[5] = cmul(w[4], w1);
+            w[10] = cmul(w[5], w[5]);
+            w[15] = cmul(w[10], w[5]);
+            w[20] = cmul(w[10], w[10]);
+#pragma unroll
+            for (int a = 1; a < 5; a++)
+                {
+#pragma unroll
+                    for (int b = 1; b < 5; b++) w[5 * a + b] = cmul(w[5 * a], w[b]);
+                }
+        }
+    else
+        {
+#pragma unroll
+            for (int q = 2; q < R; q++) w[q] = cmul(w[q - 1], w1);
+        }
+}
 
 // Where a stage puts its outputs.  StoreSink writes them back in place (the normal case); the
 // acquisition kernels pass a sink that consumes the natural-order outputs of the LAST inverse
@@ -203,7 +298,7 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
 {
     const int m = M / R;
     const int nb = n / R;
-#pragma unroll 2
+#pragma unroll(R >= 16 ? 1 : 2)
     for (int i = threadIdx.x; i < nb; i += blockDim.x)
         {
             const int b = fast_div(i, m, magic);
@@ -218,12 +313,22 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
                     if (m > 1)
                         {
                             const float2 w1 = __ldg(tw + j);
-                            float2 w = w1;
-#pragma unroll
-                            for (int q = 1; q < R; q++)
+                            if (R == 25)
                                 {
-                                    v[q] = cmul_conj(v[q], w);
-                                    if (q + 1 < R) w = cmul(w, w1);
+                                    float2 wp[R];
+                                    twiddle_powers<R>(w1, wp);
+#pragma unroll
+                                    for (int q = 1; q < R; q++) v[q] = cmul_conj(v[q], wp[q]);
+                                }
+                            else
+                                {
+                                    float2 w = w1;
+#pragma unroll
+                                    for (int q = 1; q < R; q++)
+                                        {
+                                            v[q] = cmul_conj(v[q], w);
+                                            if (q + 1 < R) w = cmul(w, w1);
+                                        }
                                 }
                         }
 #pragma unroll
@@ -238,12 +343,22 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
                     if (m > 1)
                         {
                             const float2 w1 = __ldg(tw + j);
-                            float2 w = w1;
-#pragma unroll
-                            for (int q = 1; q < R; q++)
+                            if (R == 25)
                                 {
-                                    v[q] = cmul(v[q], w);
-                                    if (q + 1 < R) w = cmul(w, w1);
+                                    float2 wp[R];
+                                    twiddle_powers<R>(w1, wp);
+#pragma unroll
+                                    for (int q = 1; q < R; q++) v[q] = cmul(v[q], wp[q]);
+                                }
+                            else
+                                {
+                                    float2 w = w1;
+#pragma unroll
+                                    for (int q = 1; q < R; q++)
+                                        {
+                                            v[q] = cmul(v[q], w);
+                                            if (q + 1 < R) w = cmul(w, w1);
+                                        }
                                 }
                         }
                 }
@@ -326,9 +441,17 @@ __device__ __forceinline__ void fft_first_inv_stage_from_global_dispatch(int rad
         }
 }
 
-template <bool INV, class Sink>
+template <bool INV, class Sink, bool A25 = false>
 __device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, int M, unsigned int magic, const float2* tw, Sink& sink)
 {
+    if (A25)
+        {
+            if (radix == 25)
+                {
+                    fft_stage<A25 ? 25 : 5, INV>(s, n, M, magic, tw, sink);
+                    return;
+                }
+        }
     switch (radix)
         {
         case 2: fft_stage<2, INV>(s, n, M, magic, tw, sink); break;
@@ -342,7 +465,7 @@ __device__ __forceinline__ void fft_stage_dispatch(int radix, float2* s, int n, 
 
 // forward DIF, spectrum written to global memory in the plan's storage order: all stages in shared memory and
 // a copy when perm_r == 1, else the last stage streams straight to global.  CONJ: store the conjugate.
-template <bool CONJ>
+template <bool CONJ, bool A25 = false>
 __device__ __forceinline__ void fft_forward_to_global(float2* s, const FftPlan& pl, const float2* tw, float2* __restrict__ out)
 {
     StoreSink st_sink;
@@ -351,7 +474,7 @@ __device__ __forceinline__ void fft_forward_to_global(float2* s, const FftPlan& 
     for (int st = 0; st < n_smem_stages; st++)
         {
             __syncthreads();
-            fft_stage_dispatch<false>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
+            fft_stage_dispatch<false, StoreSink, A25>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
             M /= pl.radix[st];
         }
     __syncthreads();
@@ -399,7 +522,7 @@ __device__ __forceinline__ void fft_inverse_smem(float2* s, const FftPlan& pl, c
 
 // inverse DIT of the product of two spectra held in global memory in the plan's storage order (perm_r > 1):
 // first stage from global, stages n_stages-2 .. 1 in place, stage 0 through `last`.
-template <class Sink>
+template <bool A25, class Sink>
 __device__ __forceinline__ void fft_inverse_from_global(const float2* x, const float2* c, float2* s, const FftPlan& pl, const float2* tw, Sink& last)
 {
     StoreSink st_sink;
@@ -409,10 +532,10 @@ __device__ __forceinline__ void fft_inverse_from_global(const float2* x, const f
         {
             M *= pl.radix[st];
             __syncthreads();
-            fft_stage_dispatch<true>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
+            fft_stage_dispatch<true, StoreSink, A25>(pl.radix[st], s, pl.n, M, pl.mdiv[st], tw + pl.tw_off[st], st_sink);
         }
     __syncthreads();
-    fft_stage_dispatch<true>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw + pl.tw_off[0], last);
+    fft_stage_dispatch<true, Sink, A25>(pl.radix[0], s, pl.n, pl.n, pl.mdiv[0], tw + pl.tw_off[0], last);
 }
 
 // inverse DIT over all stages in place (two-level path: natural order within the block afterwards)

@@ -20,6 +20,7 @@
 #include "acq_fft.cuh"
 #include "common.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace b200
@@ -136,7 +137,8 @@ __global__ void acq_wipeoff_kernel(float2* __restrict__ wipe, int n, int bins, i
 // layout 0: code[0..consumed) at the front (sampled_ms == ms_per_code)          (:238-241)
 // layout 1: bit_transition_flag: zeros in the first half, code[0..n/2) in the second (:230-235)
 // layout 2: zero-padded front: code[0..consumed) at [n-consumed, n)               (:243-246)
-__global__ void __launch_bounds__(kAcqThreads, 1) acq_code_fft_kernel(const float2* __restrict__ code, int consumed, int layout,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) acq_code_fft_kernel(const float2* __restrict__ code, int consumed, int layout,
     float2* __restrict__ out, FftPlan pl, const float2* __restrict__ tw)
 {
     extern __shared__ __align__(16) float2 s[];
@@ -161,11 +163,12 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_code_fft_kernel(const floa
             s[i] = v;
         }
     // forward FFT, then volk_32fc_conjugate_32fc (:250) fused into the store
-    fft_forward_to_global<true>(s, pl, tw, out);
+    fft_forward_to_global<true, THREADS == kAcqThreads25>(s, pl, tw, out);
 }
 
 // ---- forward: wipe-off + FFT, one CTA per Doppler bin ------------------------------------------------
-__global__ void __launch_bounds__(kAcqThreads, 1) acq_fwd_kernel(const float2* __restrict__ in, int consumed,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) acq_fwd_kernel(const float2* __restrict__ in, int consumed,
     const float2* __restrict__ wipe, float2* __restrict__ X, FftPlan pl, const float2* __restrict__ tw)
 {
     extern __shared__ __align__(16) float2 s[];
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_fwd_kernel(const float2* _
                 }
             s[i] = v;
         }
-    fft_forward_to_global<false>(s, pl, tw, X + static_cast<size_t>(d) * n);
+    fft_forward_to_global<false, THREADS == kAcqThreads25>(s, pl, tw, X + static_cast<size_t>(d) * n);
 }
 
 // ---- correlation rows ---------------------------------------------------------------------------------
@@ -235,15 +238,16 @@ struct AcqBest
 // mode 0: grid = n_slots * bins rows; row r -> slot_list[r / bins], bin r % bins; writes rowstat.
 // mode 1: grid = n_slots; row = the winning (bin, index_time) in best[]; excluded window of
 //         +-samples_per_chip around the peak; writes second_peak[slot].
-__global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* __restrict__ X, const float2* __restrict__ codes,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) acq_corr_kernel(const float2* __restrict__ X, const float2* __restrict__ codes,
     const int* __restrict__ slot_list, int bins, FftPlan pl, const float2* __restrict__ tw, int off, int ne,
     AcqRowStat* __restrict__ rowstat, float* __restrict__ grid, int accumulate, int mode,
     const AcqBest* __restrict__ best, int samples_per_chip, float* __restrict__ second_peak)
 {
     extern __shared__ __align__(16) float2 s[];
-    __shared__ float red_v[kAcqThreads / 32];
-    __shared__ unsigned int red_i[kAcqThreads / 32];
-    __shared__ float red_s[kAcqThreads / 32];
+    __shared__ float red_v[THREADS / 32];
+    __shared__ unsigned int red_i[THREADS / 32];
+    __shared__ float red_s[THREADS / 32];
     const int n = pl.n;
     int slot_pos, bin;
     RowSink sink;
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* 
             if (pl.perm_r > 1)
                 {
                     // product (volk_32fc_x2_multiply_32fc, :538) and first inverse stage straight from global memory
-                    fft_inverse_from_global(x, c, s, pl, tw, sink);
+                    fft_inverse_from_global<THREADS == kAcqThreads25>(x, c, s, pl, tw, sink);
                 }
             else
                 {
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(kAcqThreads, 1) acq_corr_kernel(const float2* 
     __syncthreads();
     if (threadIdx.x == 0)
         {
-            for (int w = 1; w < kAcqThreads / 32; w++)
+            for (int w = 1; w < THREADS / 32; w++)
                 {
                     if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi))
                         {
@@ -703,9 +707,12 @@ int set_attrs()
 {
     if (g_attr_done) return B200_OK;
     const int bytes = kAcqMaxSmemPoints * static_cast<int>(sizeof(float2));
-    B200_CUDA_TRY(cudaFuncSetAttribute(acq_code_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    B200_CUDA_TRY(cudaFuncSetAttribute(acq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_code_fft_kernel<kAcqThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_fwd_kernel<kAcqThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_kernel<kAcqThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_code_fft_kernel<kAcqThreads25>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_fwd_kernel<kAcqThreads25>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_kernel<kAcqThreads25>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_block_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     g_attr_done = true;
@@ -714,14 +721,18 @@ int set_attrs()
 }  // namespace
 
 // ---- launchers (called from acq_engine.cu) --------------------------------------------------------------
-static int acq_plan_make_smem(int n, FftPlan* pl);
+static int acq_plan_make_smem(int n, FftPlan* pl, bool allow25);
 
 int acq_plan_make(int n_total, FftPlan* pl)
 {
     if (n_total < 2) return B200_ERR_RANGE;
     if (n_total <= kAcqMaxSmemPoints)
         {
-            const int rc = acq_plan_make_smem(n_total, pl);
+            // radix-25 stages (one shared-memory pass instead of two radix-5 passes) on 512-thread CTAs;
+            // B200_ACQ_RADIX25=0 keeps the radix <= 8 plan on 1024 threads
+            const char* env = std::getenv("B200_ACQ_RADIX25");
+            const bool allow25 = env ? std::atoi(env) != 0 : true;
+            const int rc = acq_plan_make_smem(n_total, pl, allow25);
             pl->n1 = 1;
             pl->n_total = n_total;
             pl->tw_goff = 0;
@@ -739,7 +750,7 @@ int acq_plan_make(int n_total, FftPlan* pl)
             if (n_total % n1) continue;
             const int n2 = n_total / n1;
             if (n2 > kAcqMaxSmemPoints) continue;
-            if (acq_plan_make_smem(n2, pl) != B200_OK) continue;
+            if (acq_plan_make_smem(n2, pl, false) != B200_OK) continue;
             pl->n1 = n1;
             pl->n_total = n_total;
             int off = 0, M = n2;
@@ -754,7 +765,7 @@ int acq_plan_make(int n_total, FftPlan* pl)
     return B200_ERR_RANGE;
 }
 
-static int acq_plan_make_smem(int n, FftPlan* pl)
+static int acq_plan_make_smem(int n, FftPlan* pl, bool allow25)
 {
     if (n < 2 || n > kAcqMaxSmemPoints) return B200_ERR_RANGE;
     int rem = n;
@@ -770,6 +781,7 @@ static int acq_plan_make_smem(int n, FftPlan* pl)
     pl->n = n;
     pl->perm_r = 1;
     pl->perm_nb = n;
+    pl->threads = kAcqThreads;
     int k = 0;
     // Powers of two first (large sub-block stride m, conflict-free stride-1 accesses), odd radices
     // last: in the final stages consecutive threads are R*m apart and an ODD stride spreads over
@@ -784,7 +796,23 @@ static int acq_plan_make_smem(int n, FftPlan* pl)
     if (twos == 1) pl->radix[k++] = 2;
     for (int i = 0; i < cnt[3]; i++) pl->radix[k++] = 3;
     for (int i = 0; i < cnt[7]; i++) pl->radix[k++] = 7;
-    for (int i = 0; i < cnt[5]; i++) pl->radix[k++] = 5;
+    int fives = cnt[5];
+    // pairs of 5 become radix-25 stages as long as at least two stages remain (the fused first/last stage
+    // paths take the final radix from the plan and are not instantiated for 25)
+    if (allow25 && fives >= 2 && (k + fives / 2 + (fives & 1)) >= 2 && ((fives & 1) || k >= 1))
+        {
+            const bool odd = (fives & 1) != 0;
+            int pairs = fives / 2;
+            if (!odd)
+                {
+                    // the last stage must be a radix the fused paths support: keep one pair as 5, 5
+                    pairs -= 1;
+                }
+            for (int i = 0; i < pairs; i++) pl->radix[k++] = 25;
+            if (pairs > 0) pl->threads = kAcqThreads25;
+            fives -= 2 * pairs;
+        }
+    for (int i = 0; i < fives; i++) pl->radix[k++] = 5;
     if (k > kAcqMaxStages) return B200_ERR_RANGE;
     pl->n_stages = k;
     int M = n;
@@ -838,7 +866,10 @@ int acq_launch_code_fft(const float2* code, int consumed, int layout, float2* ou
     if (rc) return rc;
     if (pl.n1 == 1)
         {
-            acq_code_fft_kernel<<<1, kAcqThreads, pl.n * sizeof(float2), st>>>(code, consumed, layout, out, pl, tw);
+            if (pl.threads == kAcqThreads25)
+                acq_code_fft_kernel<kAcqThreads25><<<1, kAcqThreads25, pl.n * sizeof(float2), st>>>(code, consumed, layout, out, pl, tw);
+            else
+                acq_code_fft_kernel<kAcqThreads><<<1, kAcqThreads, pl.n * sizeof(float2), st>>>(code, consumed, layout, out, pl, tw);
         }
     else
         {
@@ -857,7 +888,10 @@ int acq_launch_fwd(const float2* in, int consumed, const float2* wipe, float2* X
     if (rc) return rc;
     if (pl.n1 == 1)
         {
-            acq_fwd_kernel<<<bins, kAcqThreads, pl.n * sizeof(float2), st>>>(in, consumed, wipe, X, pl, tw);
+            if (pl.threads == kAcqThreads25)
+                acq_fwd_kernel<kAcqThreads25><<<bins, kAcqThreads25, pl.n * sizeof(float2), st>>>(in, consumed, wipe, X, pl, tw);
+            else
+                acq_fwd_kernel<kAcqThreads><<<bins, kAcqThreads, pl.n * sizeof(float2), st>>>(in, consumed, wipe, X, pl, tw);
         }
     else
         {
@@ -880,8 +914,12 @@ int acq_launch_corr(const float2* X, const float2* codes, const int* slot_list, 
     if (pl.n1 == 1 || (mode == 1 && grid != nullptr))
         {
             const size_t smem = (pl.n1 == 1) ? pl.n * sizeof(float2) : 16;
-            acq_corr_kernel<<<rows, kAcqThreads, smem, st>>>(X, codes, slot_list, bins, pl, tw, off, ne, rowstat,
-                grid, accumulate, mode, static_cast<const AcqBest*>(best), samples_per_chip, second_peak);
+            if (pl.threads == kAcqThreads25)
+                acq_corr_kernel<kAcqThreads25><<<rows, kAcqThreads25, smem, st>>>(X, codes, slot_list, bins, pl, tw, off, ne, rowstat, grid,
+                    accumulate, mode, static_cast<const AcqBest*>(best), samples_per_chip, second_peak);
+            else
+                acq_corr_kernel<kAcqThreads><<<rows, kAcqThreads, smem, st>>>(X, codes, slot_list, bins, pl, tw, off, ne, rowstat, grid,
+                    accumulate, mode, static_cast<const AcqBest*>(best), samples_per_chip, second_peak);
         }
     else
         {
