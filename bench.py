@@ -564,6 +564,22 @@ def main():
                        "then b200_trk_wait: copies overlap correlation"}
         # e2e result must agree with the device-resident run
         e2e["max_rel_diff_vs_value_run"] = float(np.max(np.abs(res - taps)) / np.max(np.abs(taps)))
+        # what the link alone does: the same pinned 200 MB buffer copied host -> device with nothing else going on
+        # (the e2e step cannot be faster than this; it is the PCIe roofline of the cf32 path on this box)
+        scratch = torch.empty((n_iq, 2), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            scratch.copy_(host_iq, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            scratch.copy_(host_iq, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        copy_ms = c0.elapsed_time(c1) / 5
+        e2e["h2d_copy_only"] = {"ms_per_step": copy_ms, "gb_per_s": n_iq * 8 / copy_ms / 1e6,
+                                "value_if_copy_bound": world * ch_samples_step / (copy_ms * 1e-3) / 1e6}
+        del scratch
 
         # ---- same e2e step with 16-bit / 8-bit front-end samples (SURVEY "next" row N3): the raw integers
         # cross PCIe and are converted on the device (b200_iq_push_i16/_i8) instead of on the host.

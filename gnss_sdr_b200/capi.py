@@ -155,6 +155,22 @@ _SIGS.update({
     "b200_trk_dump_write": ([C.c_char_p, _vp, C.c_int, C.c_int], C.c_int),
 })
 
+
+
+class AcqDump(C.Structure):
+    _fields_ = [("acq_grid", _vp), ("acq_grid_narrow", _vp), ("effective_fft_size", C.c_uint32), ("num_doppler_bins", C.c_uint32),
+                ("num_doppler_bins_step2", C.c_uint32), ("doppler_max", C.c_int32), ("doppler_step", C.c_int32),
+                ("positive_acq", C.c_int32), ("num_dwells", C.c_int32), ("prn", C.c_uint32), ("acq_doppler_hz", C.c_float),
+                ("acq_delay_samples", C.c_float), ("test_statistic", C.c_float), ("threshold", C.c_float),
+                ("input_power", C.c_float), ("doppler_step_narrow", C.c_float), ("doppler_grid_narrow_min", C.c_float),
+                ("sample_counter", C.c_uint64)]
+
+
+_SIGS.update({
+    "b200_acq_dump_write": ([C.c_char_p, C.POINTER(AcqDump)], C.c_int),
+    "b200_acq_dump_filename": ([C.c_char_p, C.c_char, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t], C.c_int),
+})
+
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
@@ -449,3 +465,30 @@ class PcpsAcquisition:
             self.close()
         except Exception:
             pass
+
+
+def acq_dump_write(filename: str, grid: np.ndarray, *, doppler_max: int, doppler_step: int, positive_acq: bool, acq_doppler_hz: float,
+                   acq_delay_samples: float, test_statistic: float, threshold: float, input_power: float, sample_counter: int,
+                   prn: int, num_dwells: int, grid_narrow: np.ndarray = None, doppler_step_narrow: float = 0.0,
+                   doppler_grid_narrow_min: float = 0.0):
+    """Write the acquisition dump of pcps_acquisition::dump_results (:354-406) as a Level-5 MAT-file.
+    grid: float32[num_doppler_bins, effective_fft_size] as PcpsAcquisition.read_grid returns it."""
+    grid = np.ascontiguousarray(grid, np.float32)
+    d = AcqDump()
+    d.acq_grid = grid.ctypes.data
+    d.num_doppler_bins, d.effective_fft_size = grid.shape
+    if grid_narrow is not None:
+        grid_narrow = np.ascontiguousarray(grid_narrow, np.float32)
+        d.acq_grid_narrow = grid_narrow.ctypes.data
+        d.num_doppler_bins_step2 = grid_narrow.shape[0]
+    d.doppler_max, d.doppler_step, d.positive_acq, d.num_dwells, d.prn = doppler_max, doppler_step, int(positive_acq), num_dwells, prn
+    d.acq_doppler_hz, d.acq_delay_samples, d.test_statistic, d.threshold = acq_doppler_hz, acq_delay_samples, test_statistic, threshold
+    d.input_power, d.doppler_step_narrow, d.doppler_grid_narrow_min, d.sample_counter = input_power, doppler_step_narrow, doppler_grid_narrow_min, sample_counter
+    _chk(lib.b200_acq_dump_write(filename.encode(), C.byref(d)), "b200_acq_dump_write")
+
+
+def acq_dump_filename(base: str, system: str, signal: str, channel: int, dump_number: int, prn: int) -> str:
+    buf = C.create_string_buffer(1024)
+    _chk(lib.b200_acq_dump_filename(base.encode(), system.encode()[:1], signal.encode(), channel, dump_number, prn, buf, 1024),
+         "b200_acq_dump_filename")
+    return buf.value.decode()

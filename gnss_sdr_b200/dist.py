@@ -86,3 +86,15 @@ def gather_results(local_results: np.ndarray, slots_owned: list, n_slots: int, d
             if sid >= 0:
                 out[sid] = recs[k]
     return out
+
+
+def broadcast_band(block, src: int = 0):
+    """Fan one IQ block (torch tensor, complex samples as float32 pairs, resident on this rank's device) out to
+    every rank: one broadcast over NCCL/NVLink (8 B * fs per second of signal - 0.4 GB/s for a 50 Msps band,
+    SURVEY 8e).  Every rank passes a tensor of the same shape; the source rank's content wins.  Each rank then
+    hands its copy to its engine with b200_iq_attach_dev (or keeps a ring of such blocks) and tracks the
+    channels shard_round_robin gives it.  Returns the tensor."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(block, src=src)
+    return block

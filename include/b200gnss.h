@@ -329,6 +329,37 @@ extern "C"
     int b200_acq_read_wipeoffs(b200_acq* a, b200_cf32* wipe_host);
     int b200_acq_destroy(b200_acq* a);
 
+    /* Acquisition dump: the variables pcps_acquisition::dump_results writes
+     * (pcps_acquisition.cc:354-406), same names, classes and shapes.  The reference writes them through matio
+     * as MAT 7.3 (HDF5); this library writes a Level-5 MAT-file, which matio (hence the reference's
+     * acquisition_dump_reader.cc), MATLAB/Octave and scipy read alike; utils/python/plot_acq_grid.py uses h5py
+     * and needs the 7.3 container.  Host-only. */
+    typedef struct b200_acq_dump
+    {
+        const float* acq_grid;        /* num_doppler_bins x effective_fft_size, as b200_acq_read_grid returns it */
+        const float* acq_grid_narrow; /* make_2_steps only (else NULL): num_doppler_bins_step2 x effective_fft_size */
+        uint32_t effective_fft_size;
+        uint32_t num_doppler_bins;
+        uint32_t num_doppler_bins_step2;
+        int32_t doppler_max;
+        int32_t doppler_step;
+        int32_t positive_acq;
+        int32_t num_dwells;
+        uint32_t prn;
+        float acq_doppler_hz;
+        float acq_delay_samples;
+        float test_statistic;
+        float threshold;
+        float input_power;
+        float doppler_step_narrow;     /* d_acq_parameters.doppler_step2 */
+        float doppler_grid_narrow_min; /* d_doppler_center_step_two - floor(bins2 / 2) * doppler_step2 (:397) */
+        uint64_t sample_counter;
+    } b200_acq_dump;
+    int b200_acq_dump_write(const char* filename, const b200_acq_dump* dump);
+    /* <base>_<System>_<Signal>_ch_<channel>_<dump_number>_sat_<PRN>.mat (:357-370) */
+    int b200_acq_dump_filename(const char* base, char system, const char* signal2, uint32_t channel, uint32_t dump_number,
+        uint32_t prn, char* out, size_t out_size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,10 @@ assert int(prn[0]) == w + 1 and int(d[0]) == int(truth["index_doppler"][w]) and 
 assert peak[0] == truth["grid_maximum"][w]
 full = bd.gather_results(local, owned, n_prn)
 assert np.array_equal(full, truth)
+# band fan-out: rank 0 holds the IQ block, everybody ends up with it
+blk = torch.arange(2 * 4096, dtype=torch.float32).reshape(4096, 2) if rank == 0 else torch.zeros((4096, 2))
+bd.broadcast_band(blk, src=0)
+assert float(blk[-1, 1]) == 2 * 4096 - 1 and float(blk[17, 0]) == 34.0
 dist.barrier()
 if rank == 0:
     print("DIST_OK")
