@@ -400,7 +400,7 @@ def run_reference_arm(args):
         return 0
     vals, times = [], []
     for k in range(args.warmup + args.steps):
-        cb, t = cpu_baseline(budget_s=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        cb, t = cpu_baseline(budget_s=max(0.3, 60.0 / max(1, args.warmup + args.steps)))   # whole arm ~1-2 min for any K
         if k >= args.warmup:
             vals.append(cb["value"])
             times.append(t)
