@@ -167,6 +167,10 @@ class AcqDump(C.Structure):
 
 
 _SIGS.update({
+    "b200_acq_fine_create": ([_vp, C.c_uint32, C.POINTER(_vp)], C.c_int),
+    "b200_acq_fine_estimate": ([_vp, _vp, _vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)], C.c_int),
+    "b200_acq_fine_read_spectrum": ([_vp, _vp], C.c_int),
+    "b200_acq_fine_destroy": ([_vp], C.c_int),
     "b200_acq_dump_write": ([C.c_char_p, C.POINTER(AcqDump)], C.c_int),
     "b200_acq_dump_filename": ([C.c_char_p, C.c_char, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t], C.c_int),
 })
@@ -397,12 +401,12 @@ class PcpsAcquisition:
     def __init__(self, engine: Engine, *, fs_in: int, samples_per_ms: float, samples_per_chip: int, doppler_max: int,
                  doppler_step: int, sampled_ms: int = 1, ms_per_code: int = 1, bit_transition_flag: bool = False,
                  use_CFAR_algorithm_flag: bool = True, max_dwells: int = 1, n_code_slots: int = 1,
-                 keep_grid: bool = False):
+                 keep_grid: bool = False, num_doppler_bins: int = None):
         import math
         consumed = int(sampled_ms * samples_per_ms * (2.0 if bit_transition_flag else 1.0))
         fft_size = consumed if sampled_ms == ms_per_code else consumed * 2
         eff = fft_size // 2 if bit_transition_flag else fft_size
-        bins = int(math.ceil(float(2 * doppler_max) / float(doppler_step)))
+        bins = int(math.ceil(float(2 * doppler_max) / float(doppler_step))) if num_doppler_bins is None else int(num_doppler_bins)
         layout = 1 if bit_transition_flag else (0 if sampled_ms == ms_per_code else 2)
         self.conf = AcqConf(fft_size, eff, consumed, bins, doppler_max, doppler_step, int(fs_in), samples_per_chip,
                             layout, int(bit_transition_flag), int(use_CFAR_algorithm_flag), max_dwells, n_code_slots,
@@ -492,3 +496,37 @@ def acq_dump_filename(base: str, system: str, signal: str, channel: int, dump_nu
     _chk(lib.b200_acq_dump_filename(base.encode(), system.encode()[:1], signal.encode(), channel, dump_number, prn, buf, 1024),
          "b200_acq_dump_filename")
     return buf.value.decode()
+
+
+class AcqFineDoppler:
+    """b200_acq_fine: estimate_Doppler() of pcps_acquisition_fine_doppler_cc on the device."""
+
+    def __init__(self, engine: Engine, fft_size: int):
+        self.h = _vp()
+        self.fft_size = fft_size
+        _chk(lib.b200_acq_fine_create(engine.h, fft_size, C.byref(self.h)), "b200_acq_fine_create")
+
+    def estimate(self, buffer_10ms, code_replica):
+        """-> (tmp_index_freq, peak)"""
+        buf = np.ascontiguousarray(buffer_10ms, np.complex64)
+        code = np.ascontiguousarray(code_replica, np.complex64)
+        assert buf.size == 10 * self.fft_size and code.size == self.fft_size
+        idx, peak = C.c_uint32(0), C.c_float(0)
+        _chk(lib.b200_acq_fine_estimate(self.h, buf.ctypes.data, code.ctypes.data, C.byref(idx), C.byref(peak)), "b200_acq_fine_estimate")
+        return idx.value, peak.value
+
+    def read_spectrum(self) -> np.ndarray:
+        out = np.zeros(80 * self.fft_size, np.float32)
+        _chk(lib.b200_acq_fine_read_spectrum(self.h, out.ctypes.data), "b200_acq_fine_read_spectrum")
+        return out
+
+    def close(self):
+        if self.h:
+            lib.b200_acq_fine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -133,7 +133,7 @@ extern "C"
         int rc = acq_plan_make(static_cast<int>(c.fft_size), &pl);
         if (rc)
             {
-                set_error("fft_size %u unsupported: prime factors must be 2,3,5,7 and fft_size <= 8 x %d", c.fft_size, kAcqMaxSmemPoints);
+                set_error("fft_size %u unsupported: prime factors must be 2,3,5,7 and fft_size <= 10 x %d", c.fft_size, kAcqMaxSmemPoints);
                 return rc;
             }
         B200_CUDA_TRY(cudaSetDevice(e->device));

@@ -186,6 +186,39 @@ struct Bfly<8>
     }
 };
 
+// 10 = 2 x 5: input n = 5 n1 + n2, output k = k1 + 2 k2 (global stage of 10 ms transforms: 10 blocks of 1 ms)
+template <>
+struct Bfly<10>
+{
+    static __device__ __forceinline__ void fwd(float2 (&v)[10])
+    {
+        // W10^m = cos(2 pi m/10) - j sin(2 pi m/10), m = 1..4
+        const float c1 = 0.80901699437494742f, s1 = 0.58778525229247313f;
+        const float c2 = 0.30901699437494742f, s2 = 0.95105651629515357f;
+        const float c3 = -0.30901699437494742f, s3 = 0.95105651629515357f;
+        const float c4 = -0.80901699437494742f, s4 = 0.58778525229247313f;
+        float2 a0[5], a1[5];
+#pragma unroll
+        for (int n2 = 0; n2 < 5; n2++)
+            {
+                a0[n2] = cadd(v[n2], v[5 + n2]);  // k1 = 0
+                a1[n2] = csub(v[n2], v[5 + n2]);  // k1 = 1
+            }
+        a1[1] = make_float2(fmaf(a1[1].x, c1, a1[1].y * s1), fmaf(a1[1].y, c1, -a1[1].x * s1));
+        a1[2] = make_float2(fmaf(a1[2].x, c2, a1[2].y * s2), fmaf(a1[2].y, c2, -a1[2].x * s2));
+        a1[3] = make_float2(fmaf(a1[3].x, c3, a1[3].y * s3), fmaf(a1[3].y, c3, -a1[3].x * s3));
+        a1[4] = make_float2(fmaf(a1[4].x, c4, a1[4].y * s4), fmaf(a1[4].y, c4, -a1[4].x * s4));
+        Bfly<5>::fwd(a0);
+        Bfly<5>::fwd(a1);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; k2++)
+            {
+                v[2 * k2] = a0[k2];
+                v[2 * k2 + 1] = a1[k2];
+            }
+    }
+};
+
 // 25 = 5 x 5 (Cooley-Tukey inside the registers of one thread): input n = 5 n1 + n2, output k = k1 + 5 k2,
 // X[k1 + 5 k2] = sum_n2 W5^(n2 k2) W25^(n2 k1) sum_n1 x[5 n1 + n2] W5^(n1 k1).  Two shared-memory passes of a
 // radix-5 pair become one.

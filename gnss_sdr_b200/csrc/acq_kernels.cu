@@ -744,7 +744,7 @@ int acq_plan_make(int n_total, FftPlan* pl)
             return rc;
         }
     // two-level: smallest supported radix n1 that brings the blocks into shared memory
-    const int cand[6] = {2, 3, 4, 5, 7, 8};
+    const int cand[7] = {2, 3, 4, 5, 7, 8, 10};
     for (int n1 : cand)
         {
             if (n_total % n1) continue;
@@ -854,6 +854,7 @@ static int dispatch_radix(int r, F&& f)
         case 5: f(std::integral_constant<int, 5>{}); return B200_OK;
         case 7: f(std::integral_constant<int, 7>{}); return B200_OK;
         case 8: f(std::integral_constant<int, 8>{}); return B200_OK;
+        case 10: f(std::integral_constant<int, 10>{}); return B200_OK;
         default: return B200_ERR_RANGE;
         }
 }

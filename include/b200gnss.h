@@ -329,6 +329,24 @@ extern "C"
     int b200_acq_read_wipeoffs(b200_acq* a, b200_cf32* wipe_host);
     int b200_acq_destroy(b200_acq* a);
 
+    /* ---- acquisition: fine Doppler estimate of pcps_acquisition_fine_doppler_cc -------- */
+    /* estimate_Doppler() (src/algorithms/acquisition/gnuradio_blocks/pcps_acquisition_fine_doppler_cc.cc:316-389):
+     * 10 ms of samples x 10 replicas of the aligned local code, zero-padded 8x, FFT, first maximum of |X[k]|^2.
+     * The 80 x fft_size transform is computed as eight (10 x fft_size)-point transforms of the code-wiped signal
+     * modulated by eight sub-bin phasors, so the zero padding costs nothing.  fft_size = samples per ms
+     * (prime factors 2,3,5,7; <= 27 648).  code_replica_host: fft_size values of
+     * gps_l1_ca_code_gen_complex_sampled already rotated as :336-340 do.  *index_freq = tmp_index_freq of :357
+     * (0 .. 80 fft_size - 1); the mapping to Hz and the 1 kHz plausibility check (:360-386) are the host's
+     * (b200::Pcps_Acquisition_Fine_Doppler_Core).  The coarse grid of the same block is b200_acq with
+     * use_cfar = 0, max_dwells and doppler_max = doppler_step (its wipe-offs start at -doppler_step, :172). */
+    typedef struct b200_acq_fine b200_acq_fine;
+    int b200_acq_fine_create(b200_engine* e, uint32_t fft_size, b200_acq_fine** out);
+    int b200_acq_fine_estimate(b200_acq_fine* f, const b200_cf32* buffer_10ms_host, const b200_cf32* code_replica_host,
+        uint32_t* index_freq, float* peak);
+    /* |X[k]|^2, k = 0 .. 80 fft_size - 1, of the last estimate (parity tests) */
+    int b200_acq_fine_read_spectrum(b200_acq_fine* f, float* mag_host);
+    int b200_acq_fine_destroy(b200_acq_fine* f);
+
     /* Acquisition dump: the variables pcps_acquisition::dump_results writes
      * (pcps_acquisition.cc:354-406), same names, classes and shapes.  The reference writes them through matio
      * as MAT 7.3 (HDF5); this library writes a Level-5 MAT-file, which matio (hence the reference's
