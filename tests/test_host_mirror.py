@@ -15,6 +15,7 @@ def build():
     cmd = ["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "host", "test_host_mirror.cc"),
            os.path.join(libdir, "host", "b200_multicorrelator_real_codes.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_core.cc"),
+           os.path.join(libdir, "host", "b200_pcps_acquisition_fine_doppler_core.cc"),
            "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(libdir, "host"),
            "-L" + libdir, "-lb200gnss", "-Wl,-rpath," + libdir, "-lpthread", "-o", EXE]
     if os.path.exists(ref):
