@@ -77,6 +77,7 @@ struct b200_engine
         int n_items{0};
         int out_stride{0};
         cudaEvent_t done{nullptr};
+        cudaEvent_t items_ready{nullptr};  // work items have arrived (copy stream)
         bool busy{false};
         uint64_t ticket{0};
         std::vector<int> perm;  // results k belong to the caller's item perm[k] (empty = identity)
