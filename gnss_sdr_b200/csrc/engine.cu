@@ -179,7 +179,11 @@ extern "C"
         for (auto& b : e->bands)
             {
                 if (b.dev) cudaFree(b.dev);
-                if (b.raw_stage) cudaFree(b.raw_stage);
+                for (int k = 0; k < 2; k++)
+                    {
+                        if (b.raw_stage[k]) cudaFree(b.raw_stage[k]);
+                        if (b.raw_free[k]) cudaEventDestroy(b.raw_free[k]);
+                    }
             }
         for (auto& c : e->chans)
             if (c.code_dev) cudaFree(c.code_dev);
@@ -321,24 +325,34 @@ extern "C"
         B200_CUDA_TRY(cudaSetDevice(e->device));
         if (first_index) *first_index = b.write_index;
         const unsigned long long bytes = n * 2ULL * static_cast<unsigned long long>(bytes_per_component);
-        if (bytes > b.raw_cap)
+        const int k = b.raw_next;
+        b.raw_next ^= 1;
+        if (!b.raw_free[k]) B200_CUDA_TRY(cudaEventCreateWithFlags(&b.raw_free[k], cudaEventDisableTiming));
+        if (bytes > b.raw_cap[k])
             {
                 B200_CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
-                if (b.raw_stage) B200_CUDA_TRY(cudaFree(b.raw_stage));
-                b.raw_cap = bytes + bytes / 4 + 256;
-                B200_CUDA_TRY(cudaMalloc(&b.raw_stage, b.raw_cap));
+                B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+                if (b.raw_stage[k]) B200_CUDA_TRY(cudaFree(b.raw_stage[k]));
+                b.raw_cap[k] = bytes + bytes / 4 + 256;
+                B200_CUDA_TRY(cudaMalloc(&b.raw_stage[k], b.raw_cap[k]));
+                B200_CUDA_TRY(cudaEventRecord(b.raw_free[k], e->stream));
             }
         if (n)
             {
-                B200_CUDA_TRY(cudaMemcpyAsync(b.raw_stage, host, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+                // raw integers cross PCIe on the copy stream; the conversion into the float ring runs on the compute
+                // stream (ordered before every later correlator launch), so the copy engine goes straight on to the
+                // next block, which lands in the other staging buffer
+                B200_CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, b.raw_free[k], 0));
+                B200_CUDA_TRY(cudaMemcpyAsync(b.raw_stage[k], host, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+                B200_CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
+                B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
                 int rc = (bytes_per_component == 2)
-                             ? launch_convert_i16(static_cast<const short*>(b.raw_stage), b.dev, b.mask, b.write_index, n, e->copy_stream)
-                             : launch_convert_i8(static_cast<const signed char*>(b.raw_stage), b.dev, b.mask, b.write_index, n, e->copy_stream);
+                             ? launch_convert_i16(static_cast<const short*>(b.raw_stage[k]), b.dev, b.mask, b.write_index, n, e->stream)
+                             : launch_convert_i8(static_cast<const signed char*>(b.raw_stage[k]), b.dev, b.mask, b.write_index, n, e->stream);
                 if (rc) return rc;
                 e->launches++;
+                B200_CUDA_TRY(cudaEventRecord(b.raw_free[k], e->stream));
             }
-        B200_CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
-        B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
         b.write_index += n;
         return B200_OK;
     }

@@ -21,8 +21,12 @@ struct Band
     unsigned long long write_index{0};  // absolute index of the next pushed sample
     bool attached{false};
     bool in_use{false};
-    void* raw_stage{nullptr};           // device staging for integer sample pushes
-    unsigned long long raw_cap{0};      // bytes
+    // device staging for integer sample pushes: two buffers, so that the next raw copy runs while the previous
+    // block is being converted on the compute stream
+    void* raw_stage[2]{nullptr, nullptr};
+    unsigned long long raw_cap[2]{0, 0};  // bytes
+    cudaEvent_t raw_free[2]{nullptr, nullptr};  // conversion that read the buffer has finished
+    int raw_next{0};
 };
 
 struct Channel
