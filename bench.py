@@ -179,12 +179,11 @@ def acq_rows_bytes_flops():
 
 
 def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0, world=1):
-    import oracle
-    from gnss_synth import make_iq
+    from gnss_synth import make_iq, gps_ca_code, gps_ca_code_complex_sampled
     bins, rows, abytes, aflops = acq_rows_bytes_flops()
     rng = np.random.default_rng(4)
     present = [2, 5, 9, 13, 17, 21, 26, 30]
-    codes = {p: oracle.port.gps_ca_code(p) for p in present}
+    codes = {p: gps_ca_code(p) for p in present}
     svs = [dict(prn=p, doppler=float(rng.uniform(-9000, 9000)), code_phase_chips=float(rng.uniform(0, 1023)), cn0=45.0,
                 phase0=float(rng.uniform(0, 6.28))) for p in present]
     iq = make_iq(codes, float(ACQ_FS), ACQ_N, svs, seed=4)
@@ -192,7 +191,7 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
                                doppler_step=ACQ_DSTEP, n_code_slots=ACQ_PRNS)
     assert acq.conf.num_doppler_bins == bins
     for p in range(1, ACQ_PRNS + 1):
-        acq.set_local_code(p - 1, oracle.port.gps_ca_code_complex_sampled(p, ACQ_FS))
+        acq.set_local_code(p - 1, gps_ca_code_complex_sampled(p, ACQ_FS))
     # multi-GPU: the PRN x Doppler grid is sharded by PRN; the only exchange is the peak all-reduce
     from gnss_sdr_b200 import dist as bd
     my_slots = np.array(bd.shard_round_robin(ACQ_PRNS, world, rank), dtype=np.uint32)
@@ -238,8 +237,9 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
         assert int(bprn[0]) == w + 1 and int(bt[0]) == int(res["index_time"][w]), "all-reduced peak != gathered table"
     else:
         res = res_local
-    from oracle.acq_np import compute_threshold
-    th = compute_threshold(0.001, ACQ_N, bins, 1)
+    # compute_threshold (pcps_acquisition.cc:52-56): 2 * gamma_p_inv(2 * dwells, (1 - pfa)^(1 / (N * bins)))
+    from scipy.special import gammaincinv
+    th = 2.0 * float(gammaincinv(2.0, (1.0 - 0.001) ** (1.0 / (ACQ_N * bins))))
     detected = sorted(int(p) for p in range(1, ACQ_PRNS + 1) if res[p - 1]["test_statistics"] > th)
     # e2e: host samples in, host results out, per sweep
     t0 = time.perf_counter()
@@ -444,8 +444,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    import oracle  # only for PRN code tables of the synthetic input (test infrastructure, not timed)
-    codes = {p: oracle.port.gps_ca_code(p) for p in range(1, N_CH + 1)}
+    from gnss_synth import gps_ca_code   # synthetic-input code tables; oracle/ is only touched by the CPU-baseline legs
+    codes = {p: gps_ca_code(p) for p in range(1, N_CH + 1)}
     svs = svs_for_rank(rank)
     n_iq = EPOCH * N_EPOCHS
     iq_dev = synth_iq_device(torch, codes, svs, n_iq + 16, SEED + rank, dev)

@@ -49,3 +49,42 @@ def trk_params_for(sv: dict, fs: float, epoch_len: int, n_epochs: int, table_chi
     rem_code = -code_phase
     return (s.astype(np.uint64), rem_carr.astype(np.float32), np.full(n_epochs, dphi, np.float32),
             rem_code.astype(np.float32), np.full(n_epochs, step, np.float32))
+
+
+# ---- GPS L1 C/A code tables for synthetic inputs (independent of oracle/: bench.py and tools/ use these) ----------
+# IS-GPS-200 Table 3-Ia: G2 output = XOR of two stages (code phase selection) for PRN 1..32.
+_G2_TAPS = [(2, 6), (3, 7), (4, 8), (5, 9), (1, 9), (2, 10), (1, 8), (2, 9), (3, 10), (2, 3), (3, 4), (5, 6), (6, 7), (7, 8), (8, 9),
+            (9, 10), (1, 4), (2, 5), (3, 6), (4, 7), (5, 8), (6, 9), (1, 3), (4, 6), (5, 7), (6, 8), (7, 9), (8, 10), (1, 6), (2, 7),
+            (3, 8), (4, 9)]
+
+
+def gps_ca_code(prn: int) -> np.ndarray:
+    """1023 chips of the C/A code of PRN 1..32 as float32 +-1 (chip value 1 -> +1, 0 -> -1), the table the reference's
+    gps_l1_ca_code_gen_float produces (checked against the oracle port in tests/test_codes.py)."""
+    g1 = np.ones(10, np.uint8)
+    g2 = np.ones(10, np.uint8)
+    s1, s2 = _G2_TAPS[prn - 1]
+    out = np.empty(1023, np.float32)
+    for k in range(1023):
+        chip = g1[9] ^ g2[s1 - 1] ^ g2[s2 - 1]
+        out[k] = 1.0 if chip else -1.0
+        f1 = g1[2] ^ g1[9]
+        f2 = g2[1] ^ g2[2] ^ g2[5] ^ g2[7] ^ g2[8] ^ g2[9]
+        g1[1:] = g1[:-1]
+        g1[0] = f1
+        g2[1:] = g2[:-1]
+        g2[0] = f2
+    return out
+
+
+def gps_ca_code_complex_sampled(prn: int, fs: int) -> np.ndarray:
+    """One code period sampled at fs as (0, +-1) complex64, as gps_l1_ca_code_gen_complex_sampled does
+    (float32 index arithmetic, last sample pinned to the last chip)."""
+    code = gps_ca_code(prn)
+    n = int(float(fs) / (1023000.0 / 1023.0))
+    tc = np.float32(1.0) / np.float32(1023000)
+    ts = np.float32(1.0) / np.float32(fs)
+    i = np.arange(n, dtype=np.float32)
+    idx = np.floor((ts * i) / tc).astype(np.int64)
+    idx[n - 1] = 1022
+    return (1j * code[idx]).astype(np.complex64)

@@ -78,3 +78,13 @@ def test_fine_doppler_block_matches_oracle(oracle, case):
     assert got["Acq_doppler_hz"] == want["Acq_doppler_hz"]
     blk.close()
     e.close()
+
+
+def test_fine_doppler_rejects_unsupported_sizes():
+    from gnss_sdr_b200 import capi
+    e = capi.Engine()
+    for n in (16368, 30000, 1):          # prime factors 11 and 31; 10 N above 10 x 27648; degenerate
+        with pytest.raises(capi.B200Error) as ei:
+            capi.AcqFineDoppler(e, n)
+        assert ei.value.code in (-5, -1), n
+    e.close()

@@ -37,3 +37,14 @@ def test_sampled_complex_code_is_imaginary_and_last_chip_fixed(oracle):
     base = oracle.port.gps_ca_code(3)
     assert c.imag[-1] == base[-1]
     assert np.array_equal(c.imag[:8], np.repeat(base[:3], [4, 4, 4])[:8])
+
+
+def test_synthetic_input_generators_match_the_oracle(oracle):
+    """tests/gnss_synth.py carries its own C/A generator (bench.py and tools/ must not import oracle/ outside the
+    CPU-baseline legs); it must produce the very tables the reference's generator does."""
+    import gnss_synth as gs
+    for prn in range(1, 33):
+        assert np.array_equal(gs.gps_ca_code(prn), oracle.port.gps_ca_code(prn)), prn
+    for fs in (2000000, 4000000, 25000000):
+        for prn in (1, 9, 32):
+            assert np.array_equal(gs.gps_ca_code_complex_sampled(prn, fs), oracle.port.gps_ca_code_complex_sampled(prn, fs)), (prn, fs)

@@ -363,3 +363,41 @@ def test_dump_file_round_trip(oracle, tmp_path):
         got = ol.ref_dump_read(fn)
         assert np.array_equal(got[:, 7], rec[0, :cnt[0]]["PRN_start_sample_count"].astype(np.float64))
     e.close()
+
+
+def test_loop_api_rejects_inconsistent_requests(oracle):
+    """Error behaviour of the loop entry points: return codes, never exit() (all functions return int)."""
+    from gnss_sdr_b200 import capi
+    e = capi.Engine()
+    e.iq_create(0, 1 << 16)
+    code = oracle.port.gps_ca_code(1)
+    ch3 = e.channel_create(0, 3)
+    e.channel_set_code(ch3, code, [-0.5, 0.0, 0.5])
+    ch_hd = e.channel_create(0, 3)
+    e.channel_set_code(ch_hd, code, [-0.5, 0.0, 0.5], high_dyn=True)
+    ch_empty = e.channel_create(0, 3)
+    good = conf_to_capi(capi, ol.default_conf())
+    with pytest.raises(capi.B200Error) as ei:
+        e.loop_create(ch_empty, good)                      # no code table
+    assert ei.value.code == -4
+    with pytest.raises(capi.B200Error) as ei:
+        e.loop_create(ch3, conf_to_capi(capi, ol.default_conf(veml=1)))   # five taps wanted, three registered
+    assert ei.value.code == -1
+    with pytest.raises(capi.B200Error) as ei:
+        e.loop_create(ch_hd, good)                          # high-dynamics resampler: not in the device loop
+    assert ei.value.code == -1
+    for bad in (dict(cn0_samples=65), dict(cn0_samples=0), dict(pll_filter_order=4), dict(dll_filter_order=0), dict(slope=0.0),
+                dict(code_period=0.0004)):
+        with pytest.raises(capi.B200Error) as ei:
+            e.loop_create(ch3, conf_to_capi(capi, ol.default_conf(**bad)))
+        assert ei.value.code == -5, bad
+    rec, cnt = e.loop_run(5)                                # no loops yet: nothing to do, no error
+    assert rec.shape == (0, 5) and cnt.size == 0
+    lid = e.loop_create(ch3, good)
+    rec, cnt = e.loop_run(5)                                # created but never started: standby
+    assert cnt[lid] == 0 and e.loop_status(lid).state == 0
+    with pytest.raises(capi.B200Error):
+        e.loop_start(lid + 7, 0.0, 0.0, 0, 0)
+    with pytest.raises(capi.B200Error):
+        e.loop_set_mode(3)
+    e.close()

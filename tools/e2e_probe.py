@@ -11,11 +11,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 import bench  # noqa: E402
 import gnss_sdr_b200.capi as capi  # noqa: E402
-import oracle  # noqa: E402
+import gnss_synth  # noqa: E402
 
 dev = torch.device("cuda", 0)
 N_CH, EPOCH, N_EPOCHS, TAPS = bench.N_CH, bench.EPOCH, bench.N_EPOCHS, bench.TAPS
-codes = {p: oracle.port.gps_ca_code(p) for p in range(1, N_CH + 1)}
+codes = {p: gnss_synth.gps_ca_code(p) for p in range(1, N_CH + 1)}
 svs = bench.svs_for_rank(0)
 n_iq = EPOCH * N_EPOCHS
 host_iq = torch.empty((n_iq, 2), dtype=torch.float32, pin_memory=True)

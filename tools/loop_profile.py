@@ -9,11 +9,11 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch  # noqa: E402
 import bench  # noqa: E402
 import gnss_sdr_b200.capi as capi  # noqa: E402
-import oracle  # noqa: E402
+import gnss_synth  # noqa: E402
 
 n_ep = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 dev = torch.device("cuda", 0)
-codes = {p: oracle.port.gps_ca_code(p) for p in range(1, bench.N_CH + 1)}
+codes = {p: gnss_synth.gps_ca_code(p) for p in range(1, bench.N_CH + 1)}
 svs = bench.svs_for_rank(0)
 n_iq = bench.EPOCH * (n_ep + 4)
 iq = bench.synth_iq_device(torch, codes, svs, n_iq + 16, 2, dev)
