@@ -163,6 +163,16 @@ def ncu_traffic_bytes():
         return None
 
 
+def ncu_limiter():
+    """What ncu says bounds the dominant kernel (committed summary of the --set full capture)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("limiter")
+    except Exception:
+        return None
+
+
 # ---- acquisition sub-benchmark (BASELINE configs[3], SURVEY 8d "C4") -----------------------------------
 ACQ_FS = 25000000
 ACQ_N = 25000
@@ -673,7 +683,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "trk_shared_kernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "algorithmic_bytes_per_launch": ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE,
-                "launch_ms": launch_ms, "peak_source": peak_src,
+                "launch_ms": launch_ms, "peak_source": peak_src, "limiter": ncu_limiter(),
                 "note": "algorithmic bytes = 8 B per channel-sample (SURVEY 8d) = what 32 independent per-channel correlators read; "
                         "the 32 channels share one IQ stream, so DRAM traffic (`traffic`, from ncu) is the 200 MB stream read once and "
                         "the shared-window kernel stages each tile once per 8 items (L2->SM 0.87 GB per launch): frac > 1 against the HBM "
