@@ -16,6 +16,7 @@ def build():
            os.path.join(libdir, "host", "b200_multicorrelator_real_codes.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_core.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_fine_doppler_core.cc"),
+           os.path.join(libdir, "host", "b200_dll_pll_veml_loop.cc"),
            "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(libdir, "host"),
            "-L" + libdir, "-lb200gnss", "-Wl,-rpath," + libdir, "-lpthread", "-o", EXE]
     if os.path.exists(ref):

@@ -321,6 +321,47 @@ def test_loops_stall_on_missing_samples_and_resume(oracle):
         assert a.tobytes() == b.tobytes()
 
 
+def test_streaming_through_a_small_ring_is_identical(oracle):
+    """A receiver-like session: the band is a ring of 2^20 samples (0.26 s) fed 0.1 s at a time while the loops run;
+    epochs straddle the wrap-around and old samples are overwritten behind the loops.  Records must equal those of
+    one push into a band that holds everything."""
+    from gnss_sdr_b200 import capi
+    fs = 4e6
+    svs, codes, iq = _closed_loop_case(oracle, seconds=1.0)
+    confs = [ol.default_conf(fs_in=fs, prn=sv["prn"], pull_in_time_s=1) for sv in svs]
+
+    def start_all(e, ids):
+        for lid, sv in zip(ids, svs):
+            e.loop_start(lid, float(sv["delay"]), sv["doppler"] + 15.0, 0, 0)
+
+    e, ids = make_engine_with_loops(capi, oracle, confs, fs, band_samples=iq, prns=[sv["prn"] for sv in svs])
+    e.iq_push(0, iq)
+    start_all(e, ids)
+    whole, wcnt = e.loop_run(1000)
+    e.close()
+
+    e = capi.Engine()
+    e.iq_create(0, 1 << 20)
+    ids = []
+    for c, sv in zip(confs, svs):
+        ch = e.channel_create(0, 3)
+        e.channel_set_code(ch, codes[sv["prn"]], [-0.5, 0.0, 0.5])
+        ids.append(e.loop_create(ch, conf_to_capi(capi, c)))
+    start_all(e, ids)
+    got = [[] for _ in ids]
+    step = 400_000
+    for pos in range(0, len(iq), step):
+        e.iq_push(0, iq[pos:pos + step])
+        rec, cnt = e.loop_run(150)
+        for i in range(len(ids)):
+            got[i].append(rec[i, :cnt[i]])
+    e.close()
+    for i in range(len(ids)):
+        g = np.concatenate(got[i])
+        assert len(g) == wcnt[i] and wcnt[i] > 980
+        assert g.tobytes() == whole[i, :wcnt[i]].tobytes()
+
+
 def test_noise_only_input_ends_in_loss_of_lock(oracle):
     """Noise only: once the pull-in transitory is over (:1910-1918, integer seconds since acquisition) the C/N0
     carrier lock test sits near 0 < carrier_lock_th and the carrier-lock counter runs out - same epoch as the oracle's
