@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_loop_persistent_kernel(LoopDe
     LoopDev* sL = reinterpret_cast<LoopDev*>(smem_red + (kTrkThreads / 32) * B200_MAX_TAPS);
     __shared__ b200_trk_item s_item;
     __shared__ int s_go;
+    __shared__ int s_tbl_cache[2];  // chip-index window held in smem_tbl (process_item<.., REUSE>)
 
     const int i = blockIdx.x;
     const int tid = threadIdx.x;
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_loop_persistent_kernel(LoopDe
         const unsigned int* src = reinterpret_cast<const unsigned int*>(loops + i);
         unsigned int* dst = reinterpret_cast<unsigned int*>(sL);
         for (int w = tid; w < static_cast<int>(sizeof(LoopDev) / 4); w += kTrkThreads) dst[w] = src[w];
+        if (tid == 0) s_tbl_cache[0] = s_tbl_cache[1] = 0;
     }
     __syncthreads();
     const ChanDesc& ch = chans[sL->channel];
@@ -454,14 +456,14 @@ __global__ void __launch_bounds__(kTrkThreads) trk_loop_persistent_kernel(LoopDe
             if (taps == 3)
                 {
                     float2 r[3];
-                    process_item<3>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r);
+                    process_item<3, true>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r, s_tbl_cache);
 #pragma unroll
                     for (int q = 0; q < 3; q++) t[q] = r[q];
                 }
             else
                 {
                     float2 r[5];
-                    process_item<5>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r);
+                    process_item<5, true>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r, s_tbl_cache);
 #pragma unroll
                     for (int q = 0; q < 5; q++) t[q] = r[q];
                 }

@@ -257,9 +257,11 @@ __device__ __forceinline__ void correlate_range_hd(const ItemCtx& cx, float rate
         }
 }
 
-template <int TAPS>
+// REUSE (persistent tracker: one CTA keeps serving the same channel): tbl_cache[0..1] = [begin, end) of the chip-index
+// window already staged in smem_tbl; an epoch whose window lies inside it skips the staging pass.
+template <int TAPS, bool REUSE = false>
 __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const BandDesc& bd, float* smem_tbl,
-    int tbl_cap, float2* smem_red, int slice, int slices, float2 (&result)[TAPS])
+    int tbl_cap, float2* smem_red, int slice, int slices, float2 (&result)[TAPS], int* tbl_cache = nullptr)
 {
     const int tid = threadIdx.x;
     ItemCtx cx;
@@ -336,16 +338,43 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
 
             if (span <= static_cast<long long>(tbl_cap))
                 {
-                    const int base_i = static_cast<int>(tbl_base);
-                    int r = mod_pos(base_i + tid, L);
-                    const int stride = kTrkThreads % L;
-                    for (int j = tid; j < static_cast<int>(span); j += kTrkThreads)
+                    int base_i = static_cast<int>(tbl_base);
+                    int span_st = static_cast<int>(span);
+                    bool stage = true;
+                    if (REUSE)
                         {
-                            smem_tbl[j] = ch.code[r];
-                            r += stride;
-                            if (r >= L) r -= L;
+                            const int cb = tbl_cache[0], ce = tbl_cache[1];
+                            if (ce > cb && base_i >= cb && base_i + span_st <= ce)
+                                {
+                                    stage = false;
+                                    base_i = cb;
+                                }
+                            else
+                                {
+                                    // a little wider than needed: the window drifts by a chip or two per epoch
+                                    int margin = (tbl_cap - span_st) / 2;
+                                    margin = margin > 8 ? 8 : (margin < 0 ? 0 : margin);
+                                    base_i -= margin;
+                                    span_st += 2 * margin;
+                                }
+                        }
+                    if (stage)
+                        {
+                            int r = mod_pos(base_i + tid, L);
+                            const int stride = kTrkThreads % L;
+                            for (int j = tid; j < span_st; j += kTrkThreads)
+                                {
+                                    smem_tbl[j] = ch.code[r];
+                                    r += stride;
+                                    if (r >= L) r -= L;
+                                }
                         }
                     __syncthreads();
+                    if (REUSE && stage && tid == 0)
+                        {
+                            tbl_cache[0] = base_i;
+                            tbl_cache[1] = base_i + span_st;
+                        }
                     LookupExt lut{smem_tbl - base_i};
                     if (lo > -4000000LL && hi < 4000000LL)
                         {
@@ -373,6 +402,7 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
             else
                 {
                     const bool in_smem = L <= tbl_cap;
+                    if (REUSE && tid == 0) tbl_cache[1] = tbl_cache[0];  // smem_tbl no longer holds an extended window
                     if (in_smem)
                         {
                             for (int j = tid; j < L; j += kTrkThreads) smem_tbl[j] = ch.code[j];
