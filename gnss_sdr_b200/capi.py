@@ -96,6 +96,8 @@ _SIGS.update({
     "b200_acq_set_local_code": ([_vp, C.c_uint32, _vp], C.c_int),
     "b200_acq_set_doppler_center": ([_vp, C.c_int32, C.c_int32], C.c_int),
     "b200_acq_search": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
+    "b200_acq_search_submit": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32], C.c_int),
+    "b200_acq_search_wait": ([_vp, _vp], C.c_int),
     "b200_acq_set_step_two": ([_vp, C.c_float, C.c_float, C.c_uint32], C.c_int),
     "b200_acq_search_step_two": ([_vp, _vp, C.c_uint32, C.c_uint32, C.c_float, _vp], C.c_int),
     "b200_acq_search_dev": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
@@ -432,6 +434,18 @@ class PcpsAcquisition:
         res = np.zeros(slots.size, ACQ_RESULT_DTYPE)
         _chk(lib.b200_acq_search(self.h, iq.ctypes.data, slots.ctypes.data, slots.size, dwell_counter, res.ctypes.data),
              "b200_acq_search")
+        return res
+
+    def search_submit(self, iq, slots, dwell_counter: int = 1):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        assert iq.size >= self.conf.consumed_samples
+        slots = np.ascontiguousarray(slots, np.uint32)
+        _chk(lib.b200_acq_search_submit(self.h, iq.ctypes.data, slots.ctypes.data, slots.size, dwell_counter), "b200_acq_search_submit")
+        self._pending_n = slots.size      # only once the sweep is really in flight: wait() sizes its buffer from it
+
+    def search_wait(self) -> np.ndarray:
+        res = np.zeros(max(getattr(self, "_pending_n", 0), self.conf.n_code_slots), ACQ_RESULT_DTYPE)[:getattr(self, "_pending_n", 0)]
+        _chk(lib.b200_acq_search_wait(self.h, res.ctypes.data), "b200_acq_search_wait")
         return res
 
     def set_step_two(self, center: float, step2: float, bins2: int):

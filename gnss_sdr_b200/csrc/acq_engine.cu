@@ -51,6 +51,11 @@ struct b200_acq
     b200_acq_result* results_pin{nullptr};
     int* slot_pin{nullptr};
     std::vector<char> slot_set;
+    // asynchronous search (b200_acq_search_submit / _wait): one sweep in flight per object
+    float2* in_pin{nullptr};
+    cudaEvent_t done{nullptr};
+    uint32_t pending_slots{0};
+    bool pending{false};
 };
 
 namespace
@@ -228,18 +233,51 @@ extern "C"
         return B200_OK;
     }
 
+    int b200_acq_search_submit(b200_acq* a, const b200_cf32* in_host, const uint32_t* slots, uint32_t n_slots, uint32_t dwell_counter)
+    {
+        if (!a || !in_host) return B200_ERR_ARG;
+        if (a->pending)
+            {
+                set_error("a search is already in flight on this acquisition object: call b200_acq_search_wait");
+                return B200_ERR_STATE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        if (!a->in_pin) B200_CUDA_TRY(cudaMallocHost(&a->in_pin, sizeof(float2) * a->c.fft_size));
+        if (!a->done) B200_CUDA_TRY(cudaEventCreateWithFlags(&a->done, cudaEventDisableTiming));
+        // the caller's buffer is free as soon as this returns: stage it in pinned memory so that the copy is truly asynchronous
+        std::memcpy(a->in_pin, in_host, sizeof(float2) * a->c.consumed_samples);
+        B200_CUDA_TRY(cudaMemcpyAsync(a->in_dev, a->in_pin, sizeof(float2) * a->c.consumed_samples, cudaMemcpyHostToDevice, a->stream));
+        int rc = search_impl(a, a->in_dev, slots, n_slots, dwell_counter, a->results_dev);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaMemcpyAsync(a->results_pin, a->results_dev, sizeof(b200_acq_result) * n_slots, cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaEventRecord(a->done, a->stream));
+        a->pending = true;
+        a->pending_slots = n_slots;
+        return B200_OK;
+    }
+
+    int b200_acq_search_wait(b200_acq* a, b200_acq_result* results_host)
+    {
+        if (!a || !results_host) return B200_ERR_ARG;
+        if (!a->pending)
+            {
+                set_error("no search in flight on this acquisition object");
+                return B200_ERR_STATE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_CUDA_TRY(cudaEventSynchronize(a->done));
+        std::memcpy(results_host, a->results_pin, sizeof(b200_acq_result) * a->pending_slots);
+        a->pending = false;
+        return B200_OK;
+    }
+
     int b200_acq_search(b200_acq* a, const b200_cf32* in_host, const uint32_t* slots, uint32_t n_slots,
         uint32_t dwell_counter, b200_acq_result* results_host)
     {
         if (!a || !in_host || !results_host) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
-        B200_CUDA_TRY(cudaMemcpyAsync(a->in_dev, in_host, sizeof(float2) * a->c.consumed_samples, cudaMemcpyHostToDevice, a->stream));
-        int rc = search_impl(a, a->in_dev, slots, n_slots, dwell_counter, a->results_dev);
+        const int rc = b200_acq_search_submit(a, in_host, slots, n_slots, dwell_counter);
         if (rc) return rc;
-        B200_CUDA_TRY(cudaMemcpyAsync(a->results_pin, a->results_dev, sizeof(b200_acq_result) * n_slots, cudaMemcpyDeviceToHost, a->stream));
-        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
-        std::memcpy(results_host, a->results_pin, sizeof(b200_acq_result) * n_slots);
-        return B200_OK;
+        return b200_acq_search_wait(a, results_host);
     }
 
     int b200_acq_set_step_two(b200_acq* a, float doppler_center_step_two, float doppler_step2, uint32_t num_doppler_bins_step2)
@@ -327,6 +365,8 @@ extern "C"
         cudaFree(a->partial);
         cudaFree(a->X);
         cudaFree(a->codes);
+        if (a->in_pin) cudaFreeHost(a->in_pin);
+        if (a->done) cudaEventDestroy(a->done);
         cudaFree(a->in_dev);
         cudaFree(a->code_stage);
         cudaFree(a->grid);

@@ -319,6 +319,12 @@ extern "C"
     int b200_acq_set_step_two(b200_acq* a, float doppler_center_step_two, float doppler_step2, uint32_t num_doppler_bins_step2);
     int b200_acq_search_step_two(b200_acq* a, const b200_cf32* in_host, uint32_t slot, uint32_t dwell_counter,
         float prev_input_power, b200_acq_result* result_host);
+    /* Asynchronous form: submit returns once the sweep is queued (the input is copied first, the caller's buffer
+     * is free again), wait blocks for its results.  One sweep may be in flight per acquisition object; objects own
+     * their stream, so the sweeps of different channels' blocks overlap on the device as the reference's
+     * acquisition threads overlap on the host. */
+    int b200_acq_search_submit(b200_acq* a, const b200_cf32* in_host, const uint32_t* slots_host, uint32_t n_slots, uint32_t dwell_counter);
+    int b200_acq_search_wait(b200_acq* a, b200_acq_result* results_host);
     /* same with the input already on the device and results left on the device (asynchronous) */
     int b200_acq_search_dev(b200_acq* a, const b200_cf32* in_dev, const uint32_t* slots_host, uint32_t n_slots,
         uint32_t dwell_counter, b200_acq_result* results_dev);

@@ -325,3 +325,33 @@ def test_two_level_fft_sizes(capi, engine, oracle, fs, sampled_ms, dmax, dstep, 
     assert np.max(np.abs(g - ref_g)) / ref_g.max() < 2e-5
     assert abs(want["doppler"] - svs[0]["doppler"]) <= max(dstep, 666 / sampled_ms)
     acq.close()
+
+
+@pytest.mark.gpu
+def test_async_search_matches_synchronous_and_guards_misuse(oracle):
+    """b200_acq_search_submit / _wait: same results as b200_acq_search, one sweep in flight per object."""
+    from gnss_sdr_b200 import capi
+    import gnss_synth as gs
+    fs, n = 4e6, 4000
+    code = gs.gps_ca_code(3)
+    iq = gs.make_iq({3: code}, fs, n, [dict(prn=3, doppler=2100.0, code_phase_chips=400.0, cn0=48.0)], seed=8)
+    e = capi.Engine()
+    a = capi.PcpsAcquisition(e, fs_in=int(fs), samples_per_ms=float(n), samples_per_chip=4, doppler_max=5000, doppler_step=250, n_code_slots=2)
+    b = capi.PcpsAcquisition(e, fs_in=int(fs), samples_per_ms=float(n), samples_per_chip=4, doppler_max=5000, doppler_step=250, n_code_slots=2)
+    for o in (a, b):
+        o.set_local_code(0, gs.gps_ca_code_complex_sampled(3, int(fs)))
+        o.set_local_code(1, gs.gps_ca_code_complex_sampled(4, int(fs)))
+    want = a.search(iq, [0, 1])
+    a.search_submit(iq, [0, 1])
+    b.search_submit(iq, [1, 0])
+    with pytest.raises(capi.B200Error) as ei:
+        a.search_submit(iq, [0])
+    assert ei.value.code == -4
+    ra, rb = a.search_wait(), b.search_wait()
+    assert ra.tobytes() == want.tobytes()
+    assert rb[::-1].tobytes() == want.tobytes()
+    with pytest.raises(capi.B200Error):
+        a.search_wait()
+    a.close()
+    b.close()
+    e.close()
