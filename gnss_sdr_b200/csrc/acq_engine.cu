@@ -56,6 +56,7 @@ struct b200_acq
     cudaEvent_t done{nullptr};
     uint32_t pending_slots{0};
     bool pending{false};
+    std::vector<int> slots_on_device;  // slot list last uploaded (sweeps usually repeat it)
 };
 
 namespace
@@ -79,10 +80,18 @@ int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32
                     set_error("slot %u has no local code", slots[i]);
                     return B200_ERR_STATE;
                 }
-            a->slot_pin[i] = static_cast<int>(slots[i]);
         }
     cudaStream_t st = a->stream;
-    B200_CUDA_TRY(cudaMemcpyAsync(a->slot_list, a->slot_pin, sizeof(int) * n_slots, cudaMemcpyHostToDevice, st));
+    bool same = a->slots_on_device.size() == n_slots;
+    for (uint32_t i = 0; same && i < n_slots; i++) same = a->slots_on_device[i] == static_cast<int>(slots[i]);
+    if (!same)
+        {
+            // slot_pin is read by the asynchronous copy: wait for a previous upload's reader before rewriting it
+            B200_CUDA_TRY(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < n_slots; i++) a->slot_pin[i] = static_cast<int>(slots[i]);
+            B200_CUDA_TRY(cudaMemcpyAsync(a->slot_list, a->slot_pin, sizeof(int) * n_slots, cudaMemcpyHostToDevice, st));
+            a->slots_on_device.assign(a->slot_pin, a->slot_pin + n_slots);
+        }
     const int n = static_cast<int>(c.fft_size);
     if (step_two && (a->bins2 == 0 || !a->wipe2 || n_slots != 1))
         {

@@ -621,19 +621,43 @@ __global__ void acq_stats_kernel(const AcqRowStat* __restrict__ rowstat, int n_s
     int doppler_center, int doppler_step, unsigned int dwell_counter, int use_cfar, AcqBest* __restrict__ best,
     b200_acq_result* __restrict__ results, int step_two, float center2, float step2, float prev_input_power)
 {
-    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per PRN slot.  The reference scans the bins in ascending order with a strict '>' from 0.0
+    // (:417-426 / :464-473): the winner is the largest per-bin maximum, the lowest bin among equals, and (0, 0)
+    // when nothing exceeds 0.  Lanes scan bins lane, lane+32, ... in ascending order, then combine.
+    const int sp = blockIdx.x;
     if (sp >= n_slots) return;
+    const int lane = threadIdx.x;
     const AcqRowStat* rs = rowstat + static_cast<size_t>(sp) * bins;
     float grid_maximum = 0.0f;
-    unsigned int index_doppler = 0, index_time = 0;
-    for (int i = 0; i < bins; i++)
+    unsigned int index_doppler = 0xffffffffu, index_time = 0;
+    for (int i = lane; i < bins; i += 32)
         {
-            if (rs[i].max > grid_maximum)
+            const AcqRowStat v = rs[i];
+            if (v.max > grid_maximum)
                 {
-                    grid_maximum = rs[i].max;
+                    grid_maximum = v.max;
                     index_doppler = static_cast<unsigned int>(i);
-                    index_time = rs[i].argmax;
+                    index_time = v.argmax;
                 }
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        {
+            const float ov = __shfl_xor_sync(0xffffffffu, grid_maximum, o);
+            const unsigned int od = __shfl_xor_sync(0xffffffffu, index_doppler, o);
+            const unsigned int ot = __shfl_xor_sync(0xffffffffu, index_time, o);
+            if (ov > grid_maximum || (ov == grid_maximum && od < index_doppler))
+                {
+                    grid_maximum = ov;
+                    index_doppler = od;
+                    index_time = ot;
+                }
+        }
+    if (lane != 0) return;
+    if (index_doppler == 0xffffffffu)
+        {
+            index_doppler = 0;
+            index_time = 0;
         }
     b200_acq_result r;
     r.index_time = index_time;
@@ -942,7 +966,7 @@ int acq_launch_stats(const AcqRowStat* rowstat, int n_slots, int bins, int ne, i
     int doppler_step, unsigned int dwell_counter, int use_cfar, void* best, b200_acq_result* results, int step_two, float center2,
     float step2, float prev_input_power, cudaStream_t st)
 {
-    acq_stats_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(rowstat, n_slots, bins, ne, doppler_max, doppler_center, doppler_step,
+    acq_stats_kernel<<<n_slots, 32, 0, st>>>(rowstat, n_slots, bins, ne, doppler_max, doppler_center, doppler_step,
         dwell_counter, use_cfar, static_cast<AcqBest*>(best), results, step_two, center2, step2, prev_input_power);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
