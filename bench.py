@@ -469,6 +469,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL writes its NCCL_DEBUG lines (e.g. "NCCL version ...") to stdout unless told otherwise; stdout is for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
