@@ -183,22 +183,35 @@ extern "C"
         f->n1ms = static_cast<int>(fft_size);
         f->m = static_cast<int>(m);
         f->plan = pl;
+#define B200_FINE_TRY(expr)                                                                              \
+    do                                                                                                   \
+        {                                                                                                \
+            const cudaError_t _e = (expr);                                                               \
+            if (_e != cudaSuccess)                                                                       \
+                {                                                                                        \
+                    set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+                    b200_acq_fine_destroy(f);                                                            \
+                    return _e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA;             \
+                }                                                                                        \
+        }                                                                                                \
+    while (0)
         if (e->own_stream)
             {
-                B200_CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+                B200_FINE_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
                 f->own_stream = true;
             }
         else
             {
                 f->stream = e->stream;
             }
-        B200_CUDA_TRY(cudaMalloc(&f->tw, sizeof(float2) * m));
-        B200_CUDA_TRY(cudaMalloc(&f->code_dev, sizeof(float2) * fft_size));
-        B200_CUDA_TRY(cudaMalloc(&f->rows, sizeof(float2) * m * kZeroPadding));
-        B200_CUDA_TRY(cudaMalloc(&f->in_dev, sizeof(float2) * m));
-        B200_CUDA_TRY(cudaMalloc(&f->X, sizeof(float2) * m * kZeroPadding));
-        B200_CUDA_TRY(cudaMalloc(&f->best_dev, sizeof(FineBest)));
-        B200_CUDA_TRY(cudaMallocHost(&f->best_pin, sizeof(FineBest)));
+        B200_FINE_TRY(cudaMalloc(&f->tw, sizeof(float2) * m));
+        B200_FINE_TRY(cudaMalloc(&f->code_dev, sizeof(float2) * fft_size));
+        B200_FINE_TRY(cudaMalloc(&f->rows, sizeof(float2) * m * kZeroPadding));
+        B200_FINE_TRY(cudaMalloc(&f->in_dev, sizeof(float2) * m));
+        B200_FINE_TRY(cudaMalloc(&f->X, sizeof(float2) * m * kZeroPadding));
+        B200_FINE_TRY(cudaMalloc(&f->best_dev, sizeof(FineBest)));
+        B200_FINE_TRY(cudaMallocHost(&f->best_pin, sizeof(FineBest)));
+#undef B200_FINE_TRY
         int rc = acq_launch_twiddles(f->tw, f->plan, f->stream);
         if (rc)
             {

@@ -400,7 +400,10 @@ __global__ void trk_loop_cycle_kernel(LoopDev* loops, int n_loops, int mode, Loo
             if (logged && n_records) n_records[i] = k + 1;
             L.pending = 0;
         }
-    if ((mode & kLoopPrepare) && !L.pending)
+    // A prepare-only call opens every API entry (run / peek / step): it always re-derives the item from the state
+    // (idempotent once the loop is in state 2), so an item buffer that was reallocated since cannot be stale.
+    const bool force = (mode & kLoopPrepare) && !(mode & kLoopUpdate);
+    if ((mode & kLoopPrepare) && (force || !L.pending))
         {
             b200_trk_item it;
             L.pending = loop_prepare(L, it, check, lo, hi) ? 1 : 0;
