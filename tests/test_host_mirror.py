@@ -52,3 +52,65 @@ def test_host_mirror_runs_and_matches_reference():
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "HOST_MIRROR_OK" in r.stdout
+
+
+def test_fine_doppler_host_arithmetic_against_cxx_semantics(tmp_path):
+    """The two host-side quirks of estimate_Doppler that the Python mirror and the oracle restate - the std::rotate over
+    N - 1 elements (pcps_acquisition_fine_doppler_cc.cc:336-340) and the float/double mix of fftFreqBins (:360-373) -
+    checked against the C++ expressions themselves, compiled here."""
+    import numpy as np
+    from gnss_sdr_b200.fine_doppler import PcpsAcquisitionFineDoppler
+    from oracle.acq_fine_np import FineDopplerOracle
+    src = tmp_path / "q.cc"
+    src.write_text(r'''
+#include <algorithm>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+int main()
+{
+    const int n = 17;
+    for (int shift : {0, 1, 5, 16})
+        {
+            std::vector<int> v(n);
+            for (int i = 0; i < n; i++) v[i] = i;
+            if (shift != 0) std::rotate(v.data(), v.data() + (n - shift), v.data() + n - 1);
+            std::printf("ROT %d", shift);
+            for (int x : v) std::printf(" %d", x);
+            std::printf("\n");
+        }
+    const int64_t fs_in = 4000000;
+    const int fft_size_extended = 320000;
+    std::vector<float> fftFreqBins(fft_size_extended);
+    int counter = 0;
+    for (int k = 0; k < (fft_size_extended / 2); k++)
+        {
+            fftFreqBins[counter] = ((static_cast<float>(fs_in) / 2.0) * static_cast<float>(k)) / (static_cast<float>(fft_size_extended) / 2.0);
+            counter++;
+        }
+    for (int k = fft_size_extended / 2; k > 0; k--)
+        {
+            fftFreqBins[counter] = ((-static_cast<float>(fs_in) / 2.0) * static_cast<float>(k)) / (static_cast<float>(fft_size_extended) / 2.0);
+            counter++;
+        }
+    for (int idx : {0, 1, 88, 159999, 160000, 160001, 319912, 319999}) std::printf("BIN %d %.9g\n", idx, fftFreqBins[idx]);
+    return 0;
+}
+''')
+    exe = tmp_path / "q"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    base = np.arange(17).astype(np.complex64)
+    blk = PcpsAcquisitionFineDoppler.__new__(PcpsAcquisitionFineDoppler)
+    blk.fs_in = 4000000
+    orc = FineDopplerOracle.__new__(FineDopplerOracle)
+    orc.fs_in = 4000000
+    for ln in out:
+        f = ln.split()
+        if f[0] == "ROT":
+            want = np.array([int(x) for x in f[2:]])
+            for rot in (PcpsAcquisitionFineDoppler.rotate_code_replica, FineDopplerOracle.rotate_code_replica):
+                assert np.array_equal(rot(base, int(f[1])).real.astype(int), want), ln
+        else:
+            idx, val = int(f[1]), np.float32(float(f[2]))
+            assert blk.fft_freq_bins(idx, 320000) == val and orc.fft_freq_bins(idx, 320000) == val, ln
