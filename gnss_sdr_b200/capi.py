@@ -58,6 +58,8 @@ _SIGS = {
     "b200_iq_push_i16": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_push_i8": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_attach_dev": ([_vp, C.c_int, _vp, C.c_uint64, C.c_uint64], C.c_int),
+    "b200_iq_push_file": ([_vp, C.c_int, C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
     "b200_trk_create": ([_vp, C.POINTER(_vp), C.c_int, C.c_int], C.c_int),
     "b200_trk_set_high_dynamics_resampler": ([_vp, C.c_int], C.c_int),
     "b200_trk_set_local_code_and_taps": ([_vp, C.c_int, _vp, _vp], C.c_int),
@@ -263,6 +265,14 @@ class Engine:
             fn = lib.b200_iq_push_i16 if bits == 16 else lib.b200_iq_push_i8
             _chk(fn(self.h, band, ptr, n, C.byref(first)), "b200_iq_push_int")
         return first.value
+
+    def iq_push_file(self, band: int, path: str, item_type: str = "gr_complex", header_bytes: int = 0, skip_samples: int = 0,
+                     max_samples: int = 0, chunk_samples: int = 0):
+        """-> (first_index, samples_pushed)"""
+        first, n = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib.b200_iq_push_file(self.h, band, path.encode(), item_type.encode(), header_bytes, skip_samples, max_samples,
+                                   chunk_samples, C.byref(first), C.byref(n)), "b200_iq_push_file")
+        return first.value, n.value
 
     def iq_attach_dev(self, band: int, dev_ptr: int, n_samples: int, first_index: int = 0):
         _chk(lib.b200_iq_attach_dev(self.h, band, dev_ptr, n_samples, first_index), "b200_iq_attach_dev")

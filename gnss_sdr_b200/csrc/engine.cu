@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -365,6 +366,105 @@ extern "C"
     int b200_iq_push_i8(b200_engine* e, int band, const int8_t* host_iq, uint64_t n, uint64_t* first_index)
     {
         return push_raw(e, band, host_iq, n, first_index, 1);
+    }
+
+    int b200_iq_push_file(b200_engine* e, int band, const char* path, const char* item_type, uint64_t header_bytes, uint64_t skip_samples,
+        uint64_t max_samples, uint64_t chunk_samples, uint64_t* first_index, uint64_t* samples_pushed)
+    {
+        if (!e || !path || !item_type || band < 0 || band >= kMaxBands) return B200_ERR_ARG;
+        // FileSourceBase::itemTypeToSize (file_source_base.cc:340-378): complex samples as interleaved (I, Q) pairs
+        int bytes_per_component;
+        if (std::strcmp(item_type, "gr_complex") == 0)
+            bytes_per_component = 4;
+        else if (std::strcmp(item_type, "ishort") == 0)
+            bytes_per_component = 2;
+        else if (std::strcmp(item_type, "ibyte") == 0)
+            bytes_per_component = 1;
+        else
+            {
+                set_error("iq_push_file: item type %s is not an interleaved complex type (gr_complex, ishort, ibyte)", item_type);
+                return B200_ERR_ARG;
+            }
+        unsigned long long capacity;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            const Band& b = e->bands[band];
+            if (!b.in_use || b.attached || !b.dev)
+                {
+                    set_error("band %d is not an owned ring (call b200_iq_create)", band);
+                    return B200_ERR_STATE;
+                }
+            capacity = b.capacity;
+        }
+        if (chunk_samples == 0) chunk_samples = 1ULL << 20;
+        if (chunk_samples > capacity / 2) chunk_samples = capacity / 2 ? capacity / 2 : 1;
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        FILE* f = std::fopen(path, "rb");
+        if (!f)
+            {
+                set_error("iq_push_file: cannot open %s", path);
+                return B200_ERR_STATE;
+            }
+        const size_t sample_bytes = 2u * static_cast<size_t>(bytes_per_component);
+        // samplesToSkip (:385-414): header, then whole samples
+        if (std::fseek(f, static_cast<long>(header_bytes + skip_samples * sample_bytes), SEEK_SET) != 0)
+            {
+                std::fclose(f);
+                set_error("iq_push_file: cannot seek in %s", path);
+                return B200_ERR_RANGE;
+            }
+        // two pinned staging buffers: the disk read of block k+1 overlaps the host->device copy of block k
+        void* stage[2] = {nullptr, nullptr};
+        cudaEvent_t freed[2] = {nullptr, nullptr};
+        int rc = B200_OK;
+        for (int k = 0; k < 2 && rc == B200_OK; k++)
+            {
+                if (cudaMallocHost(&stage[k], chunk_samples * sample_bytes) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming) != cudaSuccess)
+                    {
+                        set_error("iq_push_file: pinned staging allocation failed");
+                        rc = B200_ERR_NOMEM;
+                    }
+            }
+        uint64_t total = 0;
+        bool have_first = false;
+        for (int k = 0; rc == B200_OK && (max_samples == 0 || total < max_samples); k ^= 1)
+            {
+                if (cudaEventSynchronize(freed[k]) != cudaSuccess)  // the copy that last read this buffer has finished
+                    {
+                        rc = B200_ERR_CUDA;
+                        break;
+                    }
+                uint64_t want = chunk_samples;
+                if (max_samples != 0 && max_samples - total < want) want = max_samples - total;
+                const size_t got = std::fread(stage[k], sample_bytes, static_cast<size_t>(want), f);
+                if (got == 0) break;
+                uint64_t first = 0;
+                if (bytes_per_component == 4)
+                    rc = b200_iq_push(e, band, static_cast<const b200_cf32*>(stage[k]), got, &first);
+                else if (bytes_per_component == 2)
+                    rc = b200_iq_push_i16(e, band, static_cast<const int16_t*>(stage[k]), got, &first);
+                else
+                    rc = b200_iq_push_i8(e, band, static_cast<const int8_t*>(stage[k]), got, &first);
+                if (rc != B200_OK) break;
+                if (cudaEventRecord(freed[k], e->copy_stream) != cudaSuccess) rc = B200_ERR_CUDA;
+                if (!have_first)
+                    {
+                        have_first = true;
+                        if (first_index) *first_index = first;
+                    }
+                total += got;
+                if (got < want) break;  // end of file
+            }
+        std::fclose(f);
+        cudaStreamSynchronize(e->copy_stream);
+        for (int k = 0; k < 2; k++)
+            {
+                if (stage[k]) cudaFreeHost(stage[k]);
+                if (freed[k]) cudaEventDestroy(freed[k]);
+            }
+        if (samples_pushed) *samples_pushed = total;
+        return rc;
     }
 
     int b200_iq_attach_dev(b200_engine* e, int band, const b200_cf32* dev, uint64_t n_samples, uint64_t first_index)

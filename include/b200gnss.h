@@ -83,6 +83,14 @@ extern "C"
      * host_iq holds 2*n integers.  Conversion is exact (int -> float). */
     int b200_iq_push_i16(b200_engine* e, int band, const int16_t* host_iq, uint64_t n, uint64_t* first_index);
     int b200_iq_push_i8(b200_engine* e, int band, const int8_t* host_iq, uint64_t n, uint64_t* first_index);
+    /* Stream a sample file into the band the way File_Signal_Source feeds the flowgraph
+     * (src/algorithms/signal_source/adapters/file_source_base.cc: item types :340-378, header / seconds_to_skip
+     * :385-414): item_type "gr_complex", "ishort" or "ibyte" (interleaved I,Q); header_bytes and skip_samples are
+     * skipped; at most max_samples complex samples (0 = to the end of the file) are pushed in blocks of chunk_samples
+     * (0 = 2^20) through two pinned staging buffers, so the disk read of one block overlaps the PCIe copy of the
+     * previous one.  Integer types are converted on the device (b200_iq_push_i16 / _i8). */
+    int b200_iq_push_file(b200_engine* e, int band, const char* path, const char* item_type, uint64_t header_bytes,
+        uint64_t skip_samples, uint64_t max_samples, uint64_t chunk_samples, uint64_t* first_index, uint64_t* samples_pushed);
     /* Use caller-owned device memory as the band (no copy): dev[0] is absolute index
      * first_index; n_samples need not be a power of two (no wrap). */
     int b200_iq_attach_dev(b200_engine* e, int band, const b200_cf32* dev, uint64_t n_samples, uint64_t first_index);

@@ -540,3 +540,58 @@ def test_shared_kernel_groups_that_cannot_share(capi, oracle):
         want = int_oracle(xs[c % 2][s0:s0 + n], codes[c], idx)
         assert np.array_equal(got[i, :, 0].astype(np.int64), want), (c, k)
         assert np.all(got[i, :, 1] == 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("item_type", ["gr_complex", "ishort", "ibyte"])
+def test_file_source_push_matches_array_push(oracle, tmp_path, item_type):
+    """b200_iq_push_file (File_Signal_Source semantics: header, skipped samples, interleaved I/Q item types, blocks
+    through pinned double buffers) fills the band with exactly what the array pushes do: taps bit-identical."""
+    from gnss_sdr_b200 import capi
+    import gnss_synth as gs
+    fs, n, prn = 4e6, 4000, 6
+    code = gs.gps_ca_code(prn)
+    sv = dict(prn=prn, doppler=1250.0, code_phase_chips=77.0, cn0=50.0)
+    total = 9 * n + 123
+    iq = gs.make_iq({prn: code}, fs, total, [sv], seed=12)
+    header, skip = 16, 100
+    path = str(tmp_path / "capture.dat")
+    if item_type == "gr_complex":
+        payload = iq
+        arr_push = lambda e, b, a: e.iq_push(b, a)
+    else:
+        bits = 16 if item_type == "ishort" else 8
+        scale = 256.0 if bits == 16 else 16.0
+        q = np.clip(np.round(iq.view(np.float32) * scale), -(2 ** (bits - 1) - 1), 2 ** (bits - 1) - 1).astype(np.int16 if bits == 16 else np.int8)
+        payload = q
+        arr_push = lambda e, b, a: e.iq_push_int(b, a)
+    with open(path, "wb") as f:
+        f.write(bytes([0x7F]) * header)
+        f.write(payload.tobytes())
+    per = 1 if item_type == "gr_complex" else 2          # array elements per complex sample
+    e = capi.Engine()
+    for b in (0, 1):
+        e.iq_create(b, 1 << 16)
+    first_a = arr_push(e, 0, payload[skip * per:])
+    first_b, pushed = e.iq_push_file(1, path, item_type, header_bytes=header, skip_samples=skip, chunk_samples=4096)
+    assert pushed == total - skip and first_a == first_b == 0
+    first_c, pushed_c = e.iq_push_file(1, path, item_type, header_bytes=header, skip_samples=0, max_samples=5000, chunk_samples=1024)
+    assert pushed_c == 5000 and first_c == total - skip
+    items = np.zeros(8, capi.TRK_ITEM_DTYPE)
+    _, rc, dp, rcode, st = gs.trk_params_for(sv, fs, n, 8)
+    out = []
+    for b in (0, 1):
+        ch = e.channel_create(b, 3)
+        e.channel_set_code(ch, code, [-0.5, 0.0, 0.5])
+        items["channel"], items["n"] = ch, n
+        items["sample_index"] = np.arange(8) * n
+        items["rem_carrier_phase_rad"], items["phase_step_rad"] = rc, dp
+        items["rem_code_phase_chips"], items["code_phase_step_chips"] = rcode, st
+        out.append(e.trk_batch(items, 3))
+    assert out[0].tobytes() == out[1].tobytes()
+    assert np.abs(out[0][:, 1]).min() > 0
+    with pytest.raises(capi.B200Error):
+        e.iq_push_file(1, path, "float")
+    with pytest.raises(capi.B200Error):
+        e.iq_push_file(1, str(tmp_path / "missing.dat"))
+    e.close()
