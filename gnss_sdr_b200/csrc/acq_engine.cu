@@ -36,6 +36,7 @@ struct b200_acq
     float2* X{nullptr};        // bins x n   forward spectra (digit-reversed)
     float2* codes{nullptr};    // slots x n  conj(FFT(code)) (digit-reversed)
     float2* in_dev{nullptr};   // consumed
+    short* raw_dev{nullptr};   // 2 x consumed int16 (cshort input, converted on the device)
     float2* code_stage{nullptr};
     float* grid{nullptr};      // slots x bins x ne (optional)
     float2* wipe2{nullptr};    // step-two wipe-offs (bins2 x n)
@@ -154,6 +155,8 @@ extern "C"
         b200_acq* a = new (std::nothrow) b200_acq();
         if (!a) return B200_ERR_NOMEM;
         a->e = e;
+        // every early return of the body below destroys the half-built object
+        rc = [&]() -> int {
         a->c = c;
         a->plan = pl;
         a->slot_set.assign(c.n_code_slots, 0);
@@ -188,7 +191,6 @@ extern "C"
                 if (zerr != cudaSuccess)
                     {
                         set_error("two-level FFT workspace (%zu bytes): %s", sizeof(float2) * n * rows, cudaGetErrorString(zerr));
-                        b200_acq_destroy(a);
                         return B200_ERR_NOMEM;
                     }
                 B200_CUDA_TRY(cudaMalloc(&a->partial, sizeof(AcqRowStat) * rows * acq_final_chunks(pl)));
@@ -199,19 +201,26 @@ extern "C"
                 if (err != cudaSuccess)
                     {
                         set_error("magnitude grid (%zu bytes): %s", sizeof(float) * ne * bins * slots, cudaGetErrorString(err));
-                        b200_acq_destroy(a);
                         return B200_ERR_NOMEM;
                     }
                 B200_CUDA_TRY(cudaMemsetAsync(a->grid, 0, sizeof(float) * ne * bins * slots, a->stream));
             }
-        rc = acq_launch_twiddles(a->tw, a->plan, a->stream);
-        if (rc) return rc;
-        rc = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, 0, 0.f, 0.f, a->stream);
-        if (rc) return rc;
+        int r2 = acq_launch_twiddles(a->tw, a->plan, a->stream);
+        if (r2) return r2;
+        r2 = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, 0, 0.f, 0.f, a->stream);
+        if (r2) return r2;
         B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return B200_OK;
+        }();
+        if (rc != B200_OK)
+            {
+                b200_acq_destroy(a);
+                return rc;
+            }
         *out = a;
         return B200_OK;
     }
+
 
     int b200_acq_set_local_code(b200_acq* a, uint32_t slot, const b200_cf32* code_host)
     {
@@ -287,6 +296,60 @@ extern "C"
         const int rc = b200_acq_search_submit(a, in_host, slots, n_slots, dwell_counter);
         if (rc) return rc;
         return b200_acq_search_wait(a, results_host);
+    }
+
+    // cshort input (pcps_acquisition.cc:653-656 converts with volk_gnsssdr_16ic_convert_32fc on the host): the raw 16-bit
+    // pairs cross PCIe (half the bytes) and become float2 on the device; int -> float is exact, so results are those
+    // of the float path on the converted samples.
+    static int upload_i16(b200_acq* a, const int16_t* in_host_iq)
+    {
+        const size_t n = a->c.consumed_samples;
+        if (!a->in_pin) B200_CUDA_TRY(cudaMallocHost(&a->in_pin, sizeof(float2) * a->c.fft_size));
+        if (!a->raw_dev) B200_CUDA_TRY(cudaMalloc(&a->raw_dev, sizeof(short) * 2 * a->c.fft_size));
+        std::memcpy(a->in_pin, in_host_iq, sizeof(int16_t) * 2 * n);
+        B200_CUDA_TRY(cudaMemcpyAsync(a->raw_dev, a->in_pin, sizeof(int16_t) * 2 * n, cudaMemcpyHostToDevice, a->stream));
+        const int rc = launch_convert_i16(a->raw_dev, a->in_dev, ~0ULL, 0ULL, n, a->stream);
+        if (rc == B200_OK)
+            {
+                std::lock_guard<std::mutex> lk(a->e->mu);
+                a->e->launches++;
+            }
+        return rc;
+    }
+
+    int b200_acq_search_i16(b200_acq* a, const int16_t* in_host_iq, const uint32_t* slots, uint32_t n_slots, uint32_t dwell_counter,
+        b200_acq_result* results_host)
+    {
+        if (!a || !in_host_iq || !results_host) return B200_ERR_ARG;
+        if (a->pending)
+            {
+                set_error("a search is already in flight on this acquisition object: call b200_acq_search_wait");
+                return B200_ERR_STATE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        int rc = upload_i16(a, in_host_iq);
+        if (rc) return rc;
+        rc = search_impl(a, a->in_dev, slots, n_slots, dwell_counter, a->results_dev);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaMemcpyAsync(a->results_pin, a->results_dev, sizeof(b200_acq_result) * n_slots, cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        std::memcpy(results_host, a->results_pin, sizeof(b200_acq_result) * n_slots);
+        return B200_OK;
+    }
+
+    int b200_acq_search_step_two_i16(b200_acq* a, const int16_t* in_host_iq, uint32_t slot, uint32_t dwell_counter, float prev_input_power,
+        b200_acq_result* result_host)
+    {
+        if (!a || !in_host_iq || !result_host) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        int rc = upload_i16(a, in_host_iq);
+        if (rc) return rc;
+        rc = search_impl(a, a->in_dev, &slot, 1, dwell_counter, a->results_dev, 1, prev_input_power);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaMemcpyAsync(a->results_pin, a->results_dev, sizeof(b200_acq_result), cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        *result_host = a->results_pin[0];
+        return B200_OK;
     }
 
     int b200_acq_set_step_two(b200_acq* a, float doppler_center_step_two, float doppler_step2, uint32_t num_doppler_bins_step2)
@@ -377,6 +440,7 @@ extern "C"
         if (a->in_pin) cudaFreeHost(a->in_pin);
         if (a->done) cudaEventDestroy(a->done);
         cudaFree(a->in_dev);
+        cudaFree(a->raw_dev);
         cudaFree(a->code_stage);
         cudaFree(a->grid);
         cudaFree(a->rowstat);

@@ -726,10 +726,11 @@ __global__ void acq_twiddle_kernel(float2* __restrict__ tw, FftPlan pl)
         }
 }
 
-bool g_attr_done = false;
+DeviceOnce g_attr_once;  // per device (a second engine on another GPU needs its own opt-in), thread-safe
 int set_attrs()
 {
-    if (g_attr_done) return B200_OK;
+    const int once_dev = g_attr_once.begin();
+    if (once_dev < 0) return B200_OK;
     const int bytes = kAcqMaxSmemPoints * static_cast<int>(sizeof(float2));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_code_fft_kernel<kAcqThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_fwd_kernel<kAcqThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -739,7 +740,7 @@ int set_attrs()
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_kernel<kAcqThreads25>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_block_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     B200_CUDA_TRY(cudaFuncSetAttribute(acq_corr_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    g_attr_done = true;
+    g_attr_once.done(once_dev);
     return B200_OK;
 }
 }  // namespace

@@ -4,6 +4,7 @@
 #include "../../include/b200gnss.h"
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -25,6 +26,26 @@ const char* get_error();
                 }                                                                                      \
         }                                                                                              \
     while (0)
+
+// Function attributes (opt-in dynamic shared memory) are per device: remember per device, thread-safe, which
+// kernels have been prepared.  Usage:
+//   static DeviceOnce once;  const int d = once.begin();  if (d >= 0) { cudaFuncSetAttribute(...); once.done(d); }
+struct DeviceOnce
+{
+    std::atomic<unsigned long long> mask{0ULL};
+    // current device index when its attributes still have to be set (64 = unknown device: set them again,
+    // the call is idempotent), -1 when nothing is left to do
+    int begin()
+    {
+        int d = -1;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return 64;
+        return (mask.load(std::memory_order_acquire) & (1ULL << d)) ? -1 : d;
+    }
+    void done(int d)
+    {
+        if (d >= 0 && d < 64) mask.fetch_or(1ULL << d, std::memory_order_release);
+    }
+};
 
 // One conditioned IQ stream resident in HBM.  Sample with absolute index i lives at
 // base[(i - first_index) & mask]; attach-mode (linear) bands use mask = ~0.

@@ -153,20 +153,28 @@ extern "C"
         b200_engine* e = new (std::nothrow) b200_engine();
         if (!e) return B200_ERR_NOMEM;
         e->device = device;
-        if (stream)
+        const int rc = [&]() -> int {
+            if (stream)
+                {
+                    e->stream = static_cast<cudaStream_t>(stream);
+                }
+            else
+                {
+                    B200_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+                    e->own_stream = true;
+                }
+            B200_CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+            B200_CUDA_TRY(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
+            B200_CUDA_TRY(cudaEventCreate(&e->t0));
+            B200_CUDA_TRY(cudaEventCreate(&e->t1));
+            B200_CUDA_TRY(cudaMalloc(&e->bands_dev, sizeof(BandDesc) * kMaxBands));
+            return B200_OK;
+        }();
+        if (rc != B200_OK)
             {
-                e->stream = static_cast<cudaStream_t>(stream);
+                b200_engine_destroy(e);  // tolerates a half-built engine
+                return rc;
             }
-        else
-            {
-                B200_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-                e->own_stream = true;
-            }
-        B200_CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        B200_CUDA_TRY(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
-        B200_CUDA_TRY(cudaEventCreate(&e->t0));
-        B200_CUDA_TRY(cudaEventCreate(&e->t1));
-        B200_CUDA_TRY(cudaMalloc(&e->bands_dev, sizeof(BandDesc) * kMaxBands));
         *out = e;
         return B200_OK;
     }
@@ -175,8 +183,8 @@ extern "C"
     {
         if (!e) return B200_ERR_ARG;
         cudaSetDevice(e->device);
-        cudaStreamSynchronize(e->stream);
-        cudaStreamSynchronize(e->copy_stream);
+        if (e->stream) cudaStreamSynchronize(e->stream);
+        if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
         for (auto& b : e->bands)
             {
                 if (b.dev) cudaFree(b.dev);
@@ -206,11 +214,11 @@ extern "C"
                 if (sl.done) cudaEventDestroy(sl.done);
                 if (sl.items_ready) cudaEventDestroy(sl.items_ready);
             }
-        cudaEventDestroy(e->copy_done);
-        cudaEventDestroy(e->t0);
-        cudaEventDestroy(e->t1);
-        cudaStreamDestroy(e->copy_stream);
-        if (e->own_stream) cudaStreamDestroy(e->stream);
+        if (e->copy_done) cudaEventDestroy(e->copy_done);
+        if (e->t0) cudaEventDestroy(e->t0);
+        if (e->t1) cudaEventDestroy(e->t1);
+        if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+        if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
         delete e;
         return B200_OK;
     }
@@ -271,6 +279,7 @@ extern "C"
         b.mask = cap - 1;
         b.first_index = 0;
         b.write_index = 0;
+        b.valid_from = 0;
         b.attached = false;
         b.in_use = true;
         e->tables_dirty = true;
@@ -355,6 +364,49 @@ extern "C"
                 B200_CUDA_TRY(cudaEventRecord(b.raw_free[k], e->stream));
             }
         b.write_index += n;
+        return B200_OK;
+    }
+
+    int b200_iq_push_at(b200_engine* e, int band, uint64_t abs_index, const b200_cf32* host, uint64_t n, uint64_t* n_new)
+    {
+        if (!e || band < 0 || band >= kMaxBands || (!host && n)) return B200_ERR_ARG;
+        if (n_new) *n_new = 0;
+        // competing producers of one band (every tracking block of a flowgraph sees the same stream and offers the same
+        // samples) are serialised here; e->mu itself is only held for the bookkeeping and inside b200_iq_push
+        std::lock_guard<std::mutex> plk(e->push_mu[band]);
+        uint64_t skip = 0;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            Band& b = e->bands[band];
+            if (!b.in_use || b.attached || !b.dev)
+                {
+                    set_error("band %d is not an owned ring (call b200_iq_create)", band);
+                    return B200_ERR_STATE;
+                }
+            if (abs_index + n <= b.write_index) return B200_OK;  // every sample of this block is already in the band
+            if (abs_index > b.write_index)
+                {
+                    // a gap (e.g. the first block to track starts long after sample 0): what the ring held is history
+                    b.valid_from = abs_index;
+                    b.write_index = abs_index;
+                }
+            skip = b.write_index - abs_index;
+        }
+        uint64_t first = 0;
+        const int rc = b200_iq_push(e, band, host + skip, n - skip, &first);
+        if (rc == B200_OK && n_new) *n_new = n - skip;
+        return rc;
+    }
+
+    int b200_iq_window(b200_engine* e, int band, uint64_t* valid_from, uint64_t* write_index)
+    {
+        if (!e || band < 0 || band >= kMaxBands) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> lk(e->mu);
+        const Band& b = e->bands[band];
+        if (!b.in_use) return B200_ERR_STATE;
+        const unsigned long long oldest = (!b.attached && b.write_index > b.capacity) ? b.write_index - b.capacity : b.first_index;
+        if (valid_from) *valid_from = b.valid_from > oldest ? b.valid_from : oldest;
+        if (write_index) *write_index = b.write_index;
         return B200_OK;
     }
 
@@ -489,6 +541,7 @@ extern "C"
         b.mask = ~0ULL;
         b.first_index = first_index;
         b.write_index = first_index + n_samples;
+        b.valid_from = first_index;
         b.attached = true;
         b.in_use = true;
         e->tables_dirty = true;
@@ -543,11 +596,26 @@ extern "C"
         return B200_OK;
     }
 
-    int b200_trk_batch_dev(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices)
+    int b200_trk_channel_set_taps(b200_engine* e, int channel_id, const float* shifts_chips)
     {
-        if (!e || n_items < 0 || (n_items && (!items_dev || !out_dev)) || out_stride < 1) return B200_ERR_ARG;
-        if (n_items == 0) return B200_OK;
+        if (!e || !shifts_chips) return B200_ERR_ARG;
         std::lock_guard<std::mutex> lk(e->mu);
+        if (channel_id < 0 || channel_id >= static_cast<int>(e->chans.size())) return B200_ERR_ARG;
+        Channel& c = e->chans[channel_id];
+        bool changed = false;
+        for (int t = 0; t < c.desc.taps; t++)
+            {
+                if (c.desc.shifts[t] != shifts_chips[t]) changed = true;
+                c.desc.shifts[t] = shifts_chips[t];
+            }
+        // the descriptor table is re-uploaded in stream order before the next launch (earlier launches keep the old taps)
+        if (changed) e->tables_dirty = true;
+        return B200_OK;
+    }
+
+    // caller holds e->mu
+    static int batch_dev_impl(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices)
+    {
         B200_CUDA_TRY(cudaSetDevice(e->device));
         int rc = upload_tables(e);
         if (rc) return rc;
@@ -572,100 +640,136 @@ extern "C"
         return rc;
     }
 
+    int b200_trk_batch_dev(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices)
+    {
+        if (!e || n_items < 0 || (n_items && (!items_dev || !out_dev)) || out_stride < 1) return B200_ERR_ARG;
+        if (n_items == 0) return B200_OK;
+        std::lock_guard<std::mutex> lk(e->mu);
+        return batch_dev_impl(e, items_dev, n_items, out_dev, out_stride, slices);
+    }
+
     int b200_trk_submit(b200_engine* e, const b200_trk_item* items_host, int n_items, int out_stride, uint64_t* ticket)
     {
         if (!e || !ticket || n_items < 1 || !items_host || out_stride < 1) return B200_ERR_ARG;
-        b200_engine::Slot* sl = nullptr;
-        {
-            std::lock_guard<std::mutex> lk(e->mu);
-            B200_CUDA_TRY(cudaSetDevice(e->device));
-            for (int i = 0; i < n_items; i++)
-                {
-                    const int ch = items_host[i].channel;
-                    if (ch < 0 || ch >= static_cast<int>(e->chans.size()) || e->chans[ch].desc.code == nullptr)
-                        {
-                            set_error("item %d: channel %d has no code table", i, ch);
-                            return B200_ERR_STATE;
-                        }
-                    if (e->chans[ch].desc.taps > out_stride)
-                        {
-                            set_error("item %d: out_stride %d < taps %d", i, out_stride, e->chans[ch].desc.taps);
-                            return B200_ERR_ARG;
-                        }
-                }
-            for (auto& s : e->slots)
-                if (!s.busy)
+        // one lock for the whole submission: concurrent submitters (the reference runs one thread per tracking block)
+        // queue whole batches, never interleave the item copy of one with the launch of another
+        std::lock_guard<std::mutex> lk(e->mu);
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        for (int i = 0; i < n_items; i++)
+            {
+                const int ch = items_host[i].channel;
+                if (ch < 0 || ch >= static_cast<int>(e->chans.size()) || e->chans[ch].desc.code == nullptr)
                     {
-                        sl = &s;
-                        break;
+                        set_error("item %d: channel %d has no code table", i, ch);
+                        return B200_ERR_STATE;
                     }
-            if (!sl)
+                if (e->chans[ch].desc.taps > out_stride)
+                    {
+                        set_error("item %d: out_stride %d < taps %d", i, out_stride, e->chans[ch].desc.taps);
+                        return B200_ERR_ARG;
+                    }
+                // ring bands: the epoch must lie inside what has been pushed and not yet overwritten
+                const Band& b = e->bands[e->chans[ch].desc.band];
+                if (b.in_use && !b.attached && items_host[i].n > 0)
+                    {
+                        const unsigned long long s0 = items_host[i].sample_index, s1 = s0 + static_cast<unsigned long long>(items_host[i].n);
+                        const unsigned long long oldest = b.write_index > b.capacity ? b.write_index - b.capacity : 0ULL;
+                        if (s0 < b.valid_from || s0 < oldest || s1 > b.write_index)
+                            {
+                                set_error("item %d: samples [%llu, %llu) are outside the band's window [%llu, %llu)", i, s0, s1,
+                                    b.valid_from > oldest ? b.valid_from : oldest, b.write_index);
+                                return B200_ERR_RANGE;
+                            }
+                    }
+            }
+        b200_engine::Slot* sl = nullptr;
+        for (auto& s : e->slots)
+            if (!s.busy)
                 {
-                    set_error("more than %d batches in flight: call b200_trk_wait", b200_engine::kSlots);
-                    return B200_ERR_STATE;
+                    sl = &s;
+                    break;
                 }
-            if (!sl->done) B200_CUDA_TRY(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
-            if (!sl->items_ready) B200_CUDA_TRY(cudaEventCreateWithFlags(&sl->items_ready, cudaEventDisableTiming));
-            if (n_items > sl->items_cap)
-                {
-                    if (sl->items_dev) B200_CUDA_TRY(cudaFree(sl->items_dev));
-                    if (sl->items_pin) B200_CUDA_TRY(cudaFreeHost(sl->items_pin));
-                    sl->items_cap = n_items + n_items / 2 + 64;
-                    B200_CUDA_TRY(cudaMalloc(&sl->items_dev, sizeof(b200_trk_item) * sl->items_cap));
-                    B200_CUDA_TRY(cudaMallocHost(&sl->items_pin, sizeof(b200_trk_item) * sl->items_cap));
-                }
-            const int out_elems = n_items * out_stride;
-            if (out_elems > sl->out_cap)
-                {
-                    if (sl->out_dev) B200_CUDA_TRY(cudaFree(sl->out_dev));
-                    if (sl->out_pin) B200_CUDA_TRY(cudaFreeHost(sl->out_pin));
-                    sl->out_cap = out_elems + out_elems / 2 + 64;
-                    B200_CUDA_TRY(cudaMalloc(&sl->out_dev, sizeof(float2) * sl->out_cap));
-                    B200_CUDA_TRY(cudaMallocHost(&sl->out_pin, sizeof(float2) * sl->out_cap));
-                }
-            sl->busy = true;
-            sl->n_items = n_items;
-            sl->out_stride = out_stride;
-            sl->ticket = e->next_ticket++;
-            // The shared-window kernel serves items 8g..8g+7 from one copy of the samples, so items
-            // should be ordered by start sample.  Already-ordered input (the usual epoch-major layout)
-            // is copied as is; otherwise sort a permutation and undo it in b200_trk_wait.
-            bool sorted = true;
-            for (int i = 1; i < n_items && sorted; i++) sorted = items_host[i - 1].sample_index <= items_host[i].sample_index;
-            sl->perm.clear();
-            if (sorted)
-                {
-                    std::memcpy(sl->items_pin, items_host, sizeof(b200_trk_item) * n_items);
-                }
-            else
-                {
-                    sl->perm.resize(n_items);
-                    for (int i = 0; i < n_items; i++) sl->perm[i] = i;
-                    std::stable_sort(sl->perm.begin(), sl->perm.end(),
-                        [&](int a, int b) { return items_host[a].sample_index < items_host[b].sample_index; });
-                    for (int i = 0; i < n_items; i++) sl->items_pin[i] = items_host[sl->perm[i]];
-                }
-            // The work items travel on the COPY stream, queued behind the sample pushes made so far, and the compute
-            // stream waits on an event.  Issued on the compute stream instead, this small host->device copy sits in
-            // the copy engine's queue until the previous batch's kernel has finished and holds up every sample
-            // push queued behind it (measured: 41.7 instead of 54.6 GB/s of sustained host->device traffic).
-            B200_CUDA_TRY(cudaMemcpyAsync(sl->items_dev, sl->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->copy_stream));
-            B200_CUDA_TRY(cudaEventRecord(sl->items_ready, e->copy_stream));
-            B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl->items_ready, 0));
-        }
+        if (!sl)
+            {
+                set_error("more than %d batches in flight: call b200_trk_wait", b200_engine::kSlots);
+                return B200_ERR_STATE;
+            }
+        // the slot is released again on every early return below (a transient CUDA error must not leak it)
+        struct BusyGuard
+        {
+            b200_engine::Slot* s;
+            bool keep{false};
+            ~BusyGuard()
+            {
+                if (!keep) s->busy = false;
+            }
+        } guard{sl};
+        sl->busy = true;
+        if (!sl->done) B200_CUDA_TRY(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
+        if (!sl->items_ready) B200_CUDA_TRY(cudaEventCreateWithFlags(&sl->items_ready, cudaEventDisableTiming));
+        if (n_items > sl->items_cap)
+            {
+                if (sl->items_dev) B200_CUDA_TRY(cudaFree(sl->items_dev));
+                sl->items_dev = nullptr;
+                if (sl->items_pin) B200_CUDA_TRY(cudaFreeHost(sl->items_pin));
+                sl->items_pin = nullptr;
+                sl->items_cap = 0;
+                const int cap = n_items + n_items / 2 + 64;
+                B200_CUDA_TRY(cudaMalloc(&sl->items_dev, sizeof(b200_trk_item) * cap));
+                B200_CUDA_TRY(cudaMallocHost(&sl->items_pin, sizeof(b200_trk_item) * cap));
+                sl->items_cap = cap;
+            }
+        const int out_elems = n_items * out_stride;
+        if (out_elems > sl->out_cap)
+            {
+                if (sl->out_dev) B200_CUDA_TRY(cudaFree(sl->out_dev));
+                sl->out_dev = nullptr;
+                if (sl->out_pin) B200_CUDA_TRY(cudaFreeHost(sl->out_pin));
+                sl->out_pin = nullptr;
+                sl->out_cap = 0;
+                const int cap = out_elems + out_elems / 2 + 64;
+                B200_CUDA_TRY(cudaMalloc(&sl->out_dev, sizeof(float2) * cap));
+                B200_CUDA_TRY(cudaMallocHost(&sl->out_pin, sizeof(float2) * cap));
+                sl->out_cap = cap;
+            }
+        sl->n_items = n_items;
+        sl->out_stride = out_stride;
+        // The shared-window kernel serves items 8g..8g+7 from one copy of the samples, so items
+        // should be ordered by start sample.  Already-ordered input (the usual epoch-major layout)
+        // is copied as is; otherwise sort a permutation and undo it in b200_trk_wait.
+        bool sorted = true;
+        for (int i = 1; i < n_items && sorted; i++) sorted = items_host[i - 1].sample_index <= items_host[i].sample_index;
+        sl->perm.clear();
+        if (sorted)
+            {
+                std::memcpy(sl->items_pin, items_host, sizeof(b200_trk_item) * n_items);
+            }
+        else
+            {
+                sl->perm.resize(n_items);
+                for (int i = 0; i < n_items; i++) sl->perm[i] = i;
+                std::stable_sort(sl->perm.begin(), sl->perm.end(),
+                    [&](int a, int b) { return items_host[a].sample_index < items_host[b].sample_index; });
+                for (int i = 0; i < n_items; i++) sl->items_pin[i] = items_host[sl->perm[i]];
+            }
+        // The work items travel on the COPY stream, queued behind the sample pushes made so far, and the compute
+        // stream waits on an event.  Issued on the compute stream instead, this small host->device copy sits in
+        // the copy engine's queue until the previous batch's kernel has finished and holds up every sample
+        // push queued behind it (measured: 41.7 instead of 54.6 GB/s of sustained host->device traffic).
+        B200_CUDA_TRY(cudaMemcpyAsync(sl->items_dev, sl->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->copy_stream));
+        B200_CUDA_TRY(cudaEventRecord(sl->items_ready, e->copy_stream));
+        B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl->items_ready, 0));
         // few items: split epochs into slices so the whole chip works on them
         int slices = 1;
         if (n_items < 592) slices = (592 + n_items - 1) / n_items;
         if (slices > 64) slices = 64;
-        int rc = b200_trk_batch_dev(e, sl->items_dev, n_items, reinterpret_cast<b200_cf32*>(sl->out_dev), out_stride, slices);
-        if (rc)
-            {
-                sl->busy = false;
-                return rc;
-            }
+        const int rc = batch_dev_impl(e, sl->items_dev, n_items, reinterpret_cast<b200_cf32*>(sl->out_dev), out_stride, slices);
+        if (rc) return rc;
         B200_CUDA_TRY(cudaMemcpyAsync(sl->out_pin, sl->out_dev, sizeof(float2) * n_items * out_stride, cudaMemcpyDeviceToHost, e->stream));
         B200_CUDA_TRY(cudaEventRecord(sl->done, e->stream));
+        sl->ticket = e->next_ticket++;
         *ticket = sl->ticket;
+        guard.keep = true;
         return B200_OK;
     }
 
@@ -754,14 +858,22 @@ extern "C"
         t->e = e;
         t->max_len = max_signal_length_samples;
         t->taps = n_correlators;
-        B200_CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
-        B200_CUDA_TRY(cudaMalloc(&t->sig_dev, sizeof(float2) * (static_cast<size_t>(t->max_len) + 2)));
-        B200_CUDA_TRY(cudaHostAlloc(&t->ctl, sizeof(b200_trk::Ctl), cudaHostAllocMapped));
-        std::memset(t->ctl, 0, sizeof(b200_trk::Ctl));
-        t->slices_cap = 64;
-        B200_CUDA_TRY(cudaMalloc(&t->partial, sizeof(float2) * trk_partial_elems(1, t->slices_cap)));
-        B200_CUDA_TRY(cudaMalloc(&t->counter, sizeof(unsigned int)));
-        B200_CUDA_TRY(cudaMemsetAsync(t->counter, 0, sizeof(unsigned int), t->stream));
+        const int rc = [&]() -> int {
+            B200_CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+            B200_CUDA_TRY(cudaMalloc(&t->sig_dev, sizeof(float2) * (static_cast<size_t>(t->max_len) + 2)));
+            B200_CUDA_TRY(cudaHostAlloc(&t->ctl, sizeof(b200_trk::Ctl), cudaHostAllocMapped));
+            std::memset(t->ctl, 0, sizeof(b200_trk::Ctl));
+            t->slices_cap = 64;
+            B200_CUDA_TRY(cudaMalloc(&t->partial, sizeof(float2) * trk_partial_elems(1, t->slices_cap)));
+            B200_CUDA_TRY(cudaMalloc(&t->counter, sizeof(unsigned int)));
+            B200_CUDA_TRY(cudaMemsetAsync(t->counter, 0, sizeof(unsigned int), t->stream));
+            return B200_OK;
+        }();
+        if (rc != B200_OK)
+            {
+                b200_trk_destroy(t);  // tolerates a half-built correlator
+                return rc;
+            }
         *out = t;
         return B200_OK;
     }
@@ -793,6 +905,15 @@ extern "C"
         c.band = 0;
         for (int k = 0; k < t->taps; k++) c.shifts[k] = shifts_chips[k];
         t->have_code = true;
+        return B200_OK;
+    }
+
+    int b200_trk_set_taps(b200_trk* t, const float* shifts_chips)
+    {
+        if (!t || !shifts_chips) return B200_ERR_ARG;
+        // the descriptor lives in the host-mapped control block the kernel reads at launch; calls on one handle are
+        // serialised by the caller and b200_trk_correlate is synchronous, so no launch is in flight here
+        for (int k = 0; k < t->taps; k++) t->ctl->chan.shifts[k] = shifts_chips[k];
         return B200_OK;
     }
 
@@ -853,13 +974,13 @@ extern "C"
     {
         if (!t) return B200_ERR_ARG;
         cudaSetDevice(t->e->device);
-        cudaStreamSynchronize(t->stream);
+        if (t->stream) cudaStreamSynchronize(t->stream);
         if (t->sig_dev) cudaFree(t->sig_dev);
         if (t->code_dev) cudaFree(t->code_dev);
         if (t->ctl) cudaFreeHost(t->ctl);
         if (t->partial) cudaFree(t->partial);
         if (t->counter) cudaFree(t->counter);
-        cudaStreamDestroy(t->stream);
+        if (t->stream) cudaStreamDestroy(t->stream);
         delete t;
         return B200_OK;
     }

@@ -19,6 +19,7 @@ struct Band
     unsigned long long first_index{0};
     unsigned long long capacity{0};
     unsigned long long write_index{0};  // absolute index of the next pushed sample
+    unsigned long long valid_from{0};   // oldest absolute index whose sample is meaningful (after a gap push)
     bool attached{false};
     bool in_use{false};
     // device staging for integer sample pushes: two buffers, so that the next raw copy runs while the previous
@@ -46,6 +47,7 @@ struct b200_engine
     cudaEvent_t copy_done{nullptr};
     cudaEvent_t t0{nullptr}, t1{nullptr};
     std::mutex mu;
+    std::mutex push_mu[b200::kMaxBands];  // serialises competing producers of one band (b200_iq_push_at)
     b200::Band bands[b200::kMaxBands];
     std::vector<b200::Channel> chans;
     // device mirrors

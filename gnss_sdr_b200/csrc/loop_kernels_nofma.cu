@@ -499,11 +499,12 @@ int launch_loop_persistent(LoopDev* loops, int n_loops, int max_epochs, const Lo
     if (tbl_cap > cap_limit) tbl_cap = cap_limit;
     tbl_cap = (tbl_cap + 3) & ~3;
     const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kTrkThreads / 32) * B200_MAX_TAPS * sizeof(float2) + sizeof(LoopDev);
-    static bool attr_set = false;
-    if (!attr_set)
+    static DeviceOnce once;
+    const int once_dev = once.begin();
+    if (once_dev >= 0)
         {
             B200_CUDA_TRY(cudaFuncSetAttribute(trk_loop_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
+            once.done(once_dev);
         }
     trk_loop_persistent_kernel<<<n_loops, kTrkThreads, smem_bytes, st>>>(loops, n_loops, max_epochs, avail, chans, bands, records, rec_capacity,
         n_records, tbl_cap);

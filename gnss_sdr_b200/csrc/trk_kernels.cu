@@ -119,11 +119,12 @@ template <int T>
 int launch_one(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands, float2* out,
     int out_stride, int slices, float2* partial, unsigned int* counters, int tbl_cap, size_t smem_bytes, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set)
+    static DeviceOnce once;
+    const int once_dev = once.begin();
+    if (once_dev >= 0)
         {
             B200_CUDA_TRY(cudaFuncSetAttribute(trk_correlate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
+            once.done(once_dev);
         }
     const long long work = static_cast<long long>(n_items) * slices;
     // plain grid for moderate sizes, grid-stride beyond (keeps blockIdx math in int)

@@ -328,8 +328,10 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
             // The code replica is staged per TILE: a tile spans 512*step chips (+ the tap spread), so a
             // 256-entry window per warp serves any code length (1023-chip C/A, 8184-value E1, 10230-chip L5).
             const float span_bound = ceilf(fabsf(step) * static_cast<float>(kShTile)) + ceilf(smax - smin) + 6.0f;
-            table_path = !ch->high_dyn && span_bound <= static_cast<float>(kShWin) && fabsf(step) * static_cast<float>(it.n) < 4.0e6f &&
+            table_path = !ch->high_dyn && span_bound <= static_cast<float>(kShWin) && fabsf(step) * static_cast<float>(it.n) < 3.0e6f &&
                          fabsf(smax) < 1.0e5f && fabsf(smin) < 1.0e5f && fabsf(rem) < 1.0e6f;
+            // (3.0e6 + 1.0e6 + 1.0e5 < 2^22: every chip index of the epoch stays inside the range where the
+            //  1.5*2^23 floor trick and the table-offset LEA of warp_tile are exact)
             if (table_path)
                 {
                     // whole-epoch table when the epoch's chip range fits the warp's storage (C/A at any rate):
@@ -544,13 +546,14 @@ int launch_trk_shared(const b200_trk_item* items, int n_items, const ChanDesc* c
 {
     if (n_items <= 0) return B200_OK;
     const int groups = (n_items + kShK - 1) / kShK;
-    static bool attr_done = false;
-    if (!attr_done)
+    static DeviceOnce once;  // per device: a second engine on another GPU needs its own opt-in
+    const int once_dev = once.begin();
+    if (once_dev >= 0)
         {
             B200_CUDA_TRY(cudaFuncSetAttribute(trk_shared_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ShSmem))));
             B200_CUDA_TRY(cudaFuncSetAttribute(trk_shared_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ShSmem))));
             B200_CUDA_TRY(cudaFuncSetAttribute(trk_shared_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(ShSmem))));
-            attr_done = true;
+            once.done(once_dev);
         }
     const size_t smem = sizeof(ShSmem);
     switch (taps_uniform)

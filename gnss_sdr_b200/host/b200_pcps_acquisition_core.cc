@@ -145,13 +145,36 @@ void Pcps_Acquisition_Core::update_synchro(const AcquisitionResult& result)
 
 int Pcps_Acquisition_Core::acquisition_core(const std::complex<float>* in, uint64_t sample_count, AcquisitionResult* out)
 {
+    return acquisition_core_any(in, false, sample_count, out);
+}
+
+
+int Pcps_Acquisition_Core::acquisition_core_i16(const int16_t* in_iq, uint64_t sample_count, AcquisitionResult* out)
+{
+    return acquisition_core_any(in_iq, true, sample_count, out);
+}
+
+
+int Pcps_Acquisition_Core::acquisition_core_any(const void* in, bool cshort, uint64_t sample_count, AcquisitionResult* out)
+{
     if (d_acq == nullptr) return 2;
     d_num_noncoherent_integrations_counter++;  // :666
     const uint32_t slot = 0;
     b200_acq_result r{};
     // doppler_grid + compute_statistics (:680-682) on the device
-    const int rc = d_step_two ? b200_acq_search_step_two(d_acq, reinterpret_cast<const b200_cf32*>(in), slot, d_num_noncoherent_integrations_counter, d_input_power, &r)
-                              : b200_acq_search(d_acq, reinterpret_cast<const b200_cf32*>(in), &slot, 1, d_num_noncoherent_integrations_counter, &r);
+    int rc;
+    if (cshort)
+        {
+            const auto* iq = static_cast<const int16_t*>(in);
+            rc = d_step_two ? b200_acq_search_step_two_i16(d_acq, iq, slot, d_num_noncoherent_integrations_counter, d_input_power, &r)
+                            : b200_acq_search_i16(d_acq, iq, &slot, 1, d_num_noncoherent_integrations_counter, &r);
+        }
+    else
+        {
+            const auto* cf = static_cast<const b200_cf32*>(in);
+            rc = d_step_two ? b200_acq_search_step_two(d_acq, cf, slot, d_num_noncoherent_integrations_counter, d_input_power, &r)
+                            : b200_acq_search(d_acq, cf, &slot, 1, d_num_noncoherent_integrations_counter, &r);
+        }
     if (rc != B200_OK)
         {
             // a GPU failure surfaces as a negative acquisition, never as exit()

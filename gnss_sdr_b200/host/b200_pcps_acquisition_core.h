@@ -90,6 +90,14 @@ public:
      *  samples.  Returns the event the block would emit: 1 positive, 2 negative, 0 none yet
      *  (more dwells needed). */
     int acquisition_core(const std::complex<float>* in, uint64_t sample_count, AcquisitionResult* out);
+    /*! the same on cshort input (Acq_Conf::it_size == sizeof(lv_16sc_t), pcps_acquisition.cc:653-656): 2 x d_consumed_samples
+     *  int16, converted to float on the device */
+    int acquisition_core_i16(const int16_t* in_iq, uint64_t sample_count, AcquisitionResult* out);
+    //! state the gr::block shell needs (pcps_acquisition.cc:749-853)
+    bool active() const { return d_active; }
+    int state() const { return d_state; }
+    bool step_two() const { return d_step_two; }
+    uint32_t dwell_counter() const { return d_num_noncoherent_integrations_counter; }
 
     bool read_grid(float* grid) const;  // d_magnitude_grid, bins x effective_fft_size
 
@@ -101,6 +109,7 @@ public:
 
 private:
     void update_synchro(const AcquisitionResult& result);
+    int acquisition_core_any(const void* in, bool cshort, uint64_t sample_count, AcquisitionResult* out);
 
     Acq_Conf_Core d_acq_parameters;
     b200_acq* d_acq{nullptr};

@@ -76,6 +76,15 @@ extern "C"
     /* Append n host samples (async H2D on the copy stream, ordered before later launches).
      * *first_index receives the absolute index of host[0]. */
     int b200_iq_push(b200_engine* e, int band, const b200_cf32* host, uint64_t n, uint64_t* first_index);
+    /* Idempotent push by ABSOLUTE index, for hosts where several threads hold the same stream: every tracking
+     * block of a flowgraph receives the same conditioned samples in its own GNU Radio input buffer
+     * (gnss_flowgraph.cc:1227-1231 fans one conditioner out to all channels).  Each block offers
+     * [abs_index, abs_index + n); only the part beyond the band's write index is copied (*n_new samples), the
+     * rest is already there.  abs_index beyond the write index opens a gap: the band restarts there
+     * (b200_iq_window reports the new oldest valid sample).  Thread-safe. */
+    int b200_iq_push_at(b200_engine* e, int band, uint64_t abs_index, const b200_cf32* host, uint64_t n, uint64_t* n_new);
+    /* [valid_from, write_index): absolute indices of the samples a work item may address right now */
+    int b200_iq_window(b200_engine* e, int band, uint64_t* valid_from, uint64_t* write_index);
     /* Same for front ends that deliver interleaved 16-bit / 8-bit (I,Q) integers (lv_16sc_t / lv_8sc_t):
      * the raw integers cross PCIe and are converted to float on the device, replacing the CPU
      * adapters src/algorithms/data_type_adapter/gnuradio_blocks/cshort_to_gr_complex.cc:48
@@ -102,8 +111,13 @@ extern "C"
     /* set_high_dynamics_resampler(bool)                                    (.cc:27-31 in .h:41) */
     int b200_trk_set_high_dynamics_resampler(b200_trk* t, int use_high_dynamics_resampler);
     /* set_local_code_and_taps(code_length_chips, local_code_in, shifts_chips) (.cc:53-63).
-     * The table and shifts are COPIED (the reference keeps the caller's pointers). */
+     * The table and shifts are COPIED.  The reference keeps the caller's shifts_chips POINTER and reads it on every
+     * correlation, and dll_pll_veml_tracking mutates that array in place without calling this function again
+     * (start_tracking :1045-1053, the narrow-correlator switch :2132-2146) - hosts that mirror the class must
+     * therefore re-send the current values before each correlation with b200_trk_set_taps (a write into the
+     * host-mapped control block: no copy, no synchronisation); B200_Multicorrelator_Real_Codes does. */
     int b200_trk_set_local_code_and_taps(b200_trk* t, int code_length_chips, const float* local_code_in, const float* shifts_chips);
+    int b200_trk_set_taps(b200_trk* t, const float* shifts_chips);
     /* set_input_output_vectors + Carrier_wipeoff_multicorrelator_resampler (.cc:66-72,103-127):
      * corr_out[k] = sum_n sig_in[n] * exp(-j(rem_carrier + n*phase_step [+ rate term])) *
      *               code[ floor(step*n + shift_k - rem_code) mod L ].
@@ -136,6 +150,8 @@ extern "C"
 
     int b200_trk_channel_create(b200_engine* e, int band, int n_correlators, int* channel_id);
     int b200_trk_channel_set_code(b200_engine* e, int channel_id, int code_length_chips, const float* local_code_in, const float* shifts_chips, int high_dynamics);
+    /* tap shifts only (same reason as b200_trk_set_taps); takes effect, in stream order, from the next batch */
+    int b200_trk_channel_set_taps(b200_engine* e, int channel_id, const float* shifts_chips);
     /* Correlate n_items (channel, epoch) work items.  out: n_items x out_stride complex taps
      * (out_stride >= the channel's n_correlators).  Host variant is synchronous (items H2D,
      * launch, taps D2H); the _dev variant takes device pointers and is asynchronous on the
@@ -326,6 +342,13 @@ extern "C"
      * step one :428-438).  One PRN slot per call. */
     int b200_acq_set_step_two(b200_acq* a, float doppler_center_step_two, float doppler_step2, uint32_t num_doppler_bins_step2);
     int b200_acq_search_step_two(b200_acq* a, const b200_cf32* in_host, uint32_t slot, uint32_t dwell_counter,
+        float prev_input_power, b200_acq_result* result_host);
+    /* cshort input (Acq_Conf::it_size == sizeof(lv_16sc_t); the reference converts on the host with
+     * volk_gnsssdr_16ic_convert_32fc, pcps_acquisition.cc:653-656): in_host_iq holds 2 * consumed_samples int16
+     * (I,Q interleaved); half the PCIe bytes, exact int -> float conversion on the device, then the float path. */
+    int b200_acq_search_i16(b200_acq* a, const int16_t* in_host_iq, const uint32_t* slots, uint32_t n_slots,
+        uint32_t dwell_counter, b200_acq_result* results_host);
+    int b200_acq_search_step_two_i16(b200_acq* a, const int16_t* in_host_iq, uint32_t slot, uint32_t dwell_counter,
         float prev_input_power, b200_acq_result* result_host);
     /* Asynchronous form: submit returns once the sweep is queued (the input is copied first, the caller's buffer
      * is free again), wait blocks for its results.  One sweep may be in flight per acquisition object; objects own

@@ -18,8 +18,9 @@ def ca_amplitude(cn0_dbhz: float, fs: float) -> float:
 
 
 def make_iq(codes: dict, fs: float, n: int, svs: list, seed: int, noise: bool = True, chips_per_table_chip: float = 1.0):
-    """codes: prn -> float32 table (one period); svs: list of dict(prn, doppler, code_phase_chips, cn0, phase0).
-    Returns complex64[n]."""
+    """codes: prn -> float32 table (one period); svs: list of dict(prn, doppler, code_phase_chips, cn0, phase0
+    [, symbols, periods_per_symbol]): `symbols` (+-1 array, cycled) modulates the code, one value every
+    `periods_per_symbol` code periods (navigation bits, secondary codes).  Returns complex64[n]."""
     rng = np.random.default_rng(seed)
     t = np.arange(n, dtype=np.float64)
     x = np.zeros(n, np.complex128)
@@ -27,9 +28,15 @@ def make_iq(codes: dict, fs: float, n: int, svs: list, seed: int, noise: bool = 
         tbl = codes[sv["prn"]]
         L = len(tbl)
         rate = CA_RATE * chips_per_table_chip * (1.0 + sv["doppler"] / GPS_L1_FREQ)
-        idx = np.floor(sv["code_phase_chips"] + t * (rate / fs)).astype(np.int64) % L
+        chip = np.floor(sv["code_phase_chips"] + t * (rate / fs)).astype(np.int64)
+        idx = chip % L
         amp = ca_amplitude(sv.get("cn0", 45.0), fs)
-        x += amp * tbl[idx] * np.exp(1j * (sv.get("phase0", 0.0) + 2 * np.pi * sv["doppler"] * t / fs))
+        sig = amp * tbl[idx] * np.exp(1j * (sv.get("phase0", 0.0) + 2 * np.pi * sv["doppler"] * t / fs))
+        if sv.get("symbols") is not None:
+            sym = np.asarray(sv["symbols"], np.float64)
+            period = chip // L  # code period number since t = 0 (may start mid-period: symbol edges follow the code)
+            sig = sig * sym[(period // int(sv.get("periods_per_symbol", 1))) % len(sym)]
+        x += sig
     if noise:
         x += rng.standard_normal(n) + 1j * rng.standard_normal(n)
     return x.astype(np.complex64)
