@@ -55,6 +55,12 @@ _SIGS = {
     "b200_engine_launch_count": ([_vp, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_create": ([_vp, C.c_int, C.c_uint64], C.c_int),
     "b200_iq_push": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
+    "b200_iq_push_at": ([_vp, C.c_int, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
+    "b200_iq_window": ([_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
+    "b200_trk_set_taps": ([_vp, _vp], C.c_int),
+    "b200_trk_channel_set_taps": ([_vp, C.c_int, _vp], C.c_int),
+    "b200_acq_search_i16": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
+    "b200_acq_search_step_two_i16": ([_vp, _vp, C.c_uint32, C.c_uint32, C.c_float, _vp], C.c_int),
     "b200_iq_push_i16": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_push_i8": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_attach_dev": ([_vp, C.c_int, _vp, C.c_uint64, C.c_uint64], C.c_int),
@@ -247,6 +253,18 @@ class Engine:
         _chk(lib.b200_iq_push(self.h, band, iq.ctypes.data, iq.size, C.byref(first)), "b200_iq_push")
         return first.value
 
+    def iq_push_at(self, band: int, abs_index: int, iq: np.ndarray) -> int:
+        """idempotent push by absolute index; returns how many samples were actually copied"""
+        iq = np.ascontiguousarray(iq, np.complex64)
+        n_new = C.c_uint64(0)
+        _chk(lib.b200_iq_push_at(self.h, band, int(abs_index), iq.ctypes.data, iq.size, C.byref(n_new)), "b200_iq_push_at")
+        return n_new.value
+
+    def iq_window(self, band: int):
+        lo, hi = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib.b200_iq_window(self.h, band, C.byref(lo), C.byref(hi)), "b200_iq_window")
+        return lo.value, hi.value
+
     def iq_push_ptr(self, band: int, host_ptr: int, n: int) -> int:
         first = C.c_uint64(0)
         _chk(lib.b200_iq_push(self.h, band, host_ptr, n, C.byref(first)), "b200_iq_push")
@@ -288,6 +306,10 @@ class Engine:
         shifts = np.ascontiguousarray(shifts, np.float32)
         _chk(lib.b200_trk_channel_set_code(self.h, cid, code.size, code.ctypes.data, shifts.ctypes.data, int(high_dyn)),
              "b200_trk_channel_set_code")
+
+    def channel_set_taps(self, cid: int, shifts):
+        shifts = np.ascontiguousarray(shifts, np.float32)
+        _chk(lib.b200_trk_channel_set_taps(self.h, cid, shifts.ctypes.data), "b200_trk_channel_set_taps")
 
     def trk_batch(self, items: np.ndarray, out_stride: int) -> np.ndarray:
         items = np.ascontiguousarray(items, TRK_ITEM_DTYPE)

@@ -27,12 +27,18 @@
 #include <gnuradio/shim_runner.h>
 #include <gnuradio/top_block.h>
 #include <pmt/pmt.h>
+#include "galileo_e1_signal_replica.h"
+#include "gps_l5_signal_replica.h"
+#include "gps_sdr_signal_replica.h"
+#include <array>
 #include <cstdint>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 #ifdef HARNESS_B200
+#include "b200_trk_coalescer.h"
 #include "gnss_block_factory_b200.h"
 #endif
 
@@ -363,5 +369,75 @@ extern "C"
         auto* ch = static_cast<Channel*>(h);
         gr::block* b = which == 0 ? ch->acq_block : ch->trk_block;
         return b ? b->nitems_read(0) : 0;
+    }
+
+    // Several channels at once, one thread each over the same sample array - what GNU Radio's thread-per-block
+    // scheduler does with the tracking blocks of a receiver.  out: n_channels x max_out_per_channel items.
+    void itf_trk_run_parallel(void** hs, int n_channels, const void* samples, uint64_t n_items, itf_synchro* out, long max_out_per_channel,
+        long* n_out)
+    {
+        std::vector<std::thread> th;
+        for (int c = 0; c < n_channels; c++)
+            th.emplace_back([=] { n_out[c] = itf_trk_run(hs[c], samples, n_items, out + static_cast<size_t>(c) * max_out_per_channel, max_out_per_channel, -1); });
+        for (auto& t : th) t.join();
+    }
+
+    // the reference's code generators, for synthesising test signals: tracking replica as a float table
+    // (1 value per chip, 2 for the Galileo E1 sinBOC(1,1) replica).  Returns the table length or -1.
+    int itf_code_float(char system, const char* signal, uint32_t prn, float* out, int max)
+    {
+        const std::string sig(signal);
+        std::vector<float> t;
+        if (system == 'G' && sig == "1C")
+            {
+                t.resize(1023);
+                gps_l1_ca_code_gen_float(t, prn, 0);
+            }
+        else if (system == 'E' && (sig == "1B" || sig == "1C"))
+            {
+                t.resize(2 * 4092);
+                const std::array<char, 3> s3 = {{sig[0], sig[1], '\0'}};
+                galileo_e1_code_gen_sinboc11_float(t, s3, prn);
+            }
+        else if (system == 'G' && sig == "5I")
+            {
+                t.resize(10230);
+                gps_l5i_code_gen_float(t, prn);
+            }
+        else if (system == 'G' && sig == "5Q")
+            {
+                t.resize(10230);
+                gps_l5q_code_gen_float(t, prn);
+            }
+        else
+            return -1;
+        if (static_cast<int>(t.size()) > max) return -1;
+        std::memcpy(out, t.data(), sizeof(float) * t.size());
+        return static_cast<int>(t.size());
+    }
+
+    // coalescer counters of the B200 build: batches, items, window_expired, mean batch round trip [us], mean and max
+    // item latency [us], samples copied, samples offered.  Returns 0, or -1 without a usable GPU / in the reference build.
+    int itf_coalescer_stats(double* out8, int reset)
+    {
+#ifdef HARNESS_B200
+        b200::Trk_Coalescer* co = b200::Trk_Coalescer::instance();
+        if (co == nullptr) return -1;
+        const auto st = co->stats();
+        out8[0] = static_cast<double>(st.batches);
+        out8[1] = static_cast<double>(st.items);
+        out8[2] = static_cast<double>(st.window_expired);
+        out8[3] = st.batches ? st.sum_batch_us / static_cast<double>(st.batches) : 0.0;
+        out8[4] = st.items ? st.sum_latency_us / static_cast<double>(st.items) : 0.0;
+        out8[5] = st.max_latency_us;
+        out8[6] = static_cast<double>(st.samples_copied);
+        out8[7] = static_cast<double>(st.samples_offered);
+        if (reset) co->reset_stats();
+        return 0;
+#else
+        (void)out8;
+        (void)reset;
+        return -1;
+#endif
     }
 }

@@ -75,6 +75,10 @@ extern "C"
         return 0;
     }
 
+    /* The shifts array the reference object keeps a POINTER to (cpu_multicorrelator_real_codes.cc:53-63): tests mutate it in
+     * place between correlations, as dll_pll_veml_tracking does (:1045-1053, :2132-2146). */
+    float* ref_mc_shifts(void* hv) { return static_cast<RefMc*>(hv)->shifts; }
+
     void ref_mc_destroy(void* hv)
     {
         auto* h = static_cast<RefMc*>(hv);

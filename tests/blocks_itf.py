@@ -68,6 +68,9 @@ def _load(name):
     lib.itf_nitems_read.restype = C.c_uint64
     lib.itf_nitems_read.argtypes = [C.c_void_p, C.c_int]
     lib.itf_select_arch.argtypes = [C.c_char_p]
+    lib.itf_trk_run_parallel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_long, C.c_void_p]
+    lib.itf_code_float.argtypes = [C.c_char, C.c_char_p, C.c_uint32, C.c_void_p, C.c_int]
+    lib.itf_coalescer_stats.argtypes = [C.c_void_p, C.c_int]
     _libs[name] = lib
     return lib
 
@@ -160,3 +163,31 @@ class Channel:
 
     def nitems_read(self, which):
         return int(self.lib.itf_nitems_read(self.h, 0 if which == "acq" else 1))
+
+
+def code_table(lib, system: str, signal: str, prn: int) -> np.ndarray:
+    """Tracking replica of the reference's generators: 'G','1C' | 'E','1B' / '1C' (sinBOC(1,1), 2 per chip) | 'G','5I' / '5Q'."""
+    buf = np.zeros(16384, np.float32)
+    n = lib.itf_code_float(system.encode(), signal.encode(), prn, buf.ctypes.data, len(buf))
+    if n < 0:
+        raise ValueError(f"no generator for {system} {signal}")
+    return buf[:n].copy()
+
+
+def trk_run_parallel(lib, channels, samples: np.ndarray, max_out=20000):
+    """Run the tracking blocks of `channels` concurrently (one thread each) over the same samples."""
+    samples = np.ascontiguousarray(samples, np.complex64)
+    n = len(channels)
+    hs = (C.c_void_p * n)(*[ch.h for ch in channels])
+    out = np.zeros((n, max_out), SYNCHRO_DTYPE)
+    n_out = np.zeros(n, np.int64)
+    lib.itf_trk_run_parallel(hs, n, samples.ctypes.data, len(samples), out.ctypes.data, max_out, n_out.ctypes.data)
+    return [out[c, :min(int(n_out[c]), max_out)] for c in range(n)]
+
+
+def coalescer_stats(lib, reset=False):
+    buf = np.zeros(8, np.float64)
+    if lib.itf_coalescer_stats(buf.ctypes.data, 1 if reset else 0) != 0:
+        return None
+    keys = ["batches", "items", "window_expired", "mean_batch_us", "mean_latency_us", "max_latency_us", "samples_copied", "samples_offered"]
+    return dict(zip(keys, buf.tolist()))

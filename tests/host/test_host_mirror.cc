@@ -11,6 +11,9 @@
 #include "b200_pcps_acquisition_core.h"
 #include "b200_dll_pll_veml_loop.h"
 #include "b200_pcps_acquisition_fine_doppler_core.h"
+#include "b200_trk_coalescer.h"
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <complex>
@@ -28,6 +31,7 @@ extern "C"
     int ref_mc_correlate(void* h, const float* in_iq, float rem_carr_rad, float phase_step_rad, float phase_rate_step_rad,
         float rem_code_chips, float code_step_chips, float code_rate_step_chips, int n, float* out_taps);
     void ref_mc_destroy(void* h);
+    float* ref_mc_shifts(void* h);
     int ref_select_arch(const char* arch);
 }
 #endif
@@ -68,6 +72,129 @@ static void correlator_worker(int tid, int n, int iters, const std::vector<float
     mc.free();
 }
 
+// The tracking block rewrites its tap-shift array IN PLACE after set_local_code_and_taps and never calls it again
+// (dll_pll_veml_tracking.cc:1030 then :1045-1053 in start_tracking; the narrow-correlator switch :2132-2146).  The
+// CPU class keeps the pointer, so it follows; the B200 class must too - on the synchronous and on the coalesced path.
+static void shift_pointer_semantics(const std::vector<float>& code, const std::vector<std::complex<float>>& in)
+{
+    const int n = 4000;
+    volatile float wide = 0.5F, narrow = 0.15F;
+    for (int coalesced = 0; coalesced < 2; coalesced++)
+        {
+            float shifts[3] = {-wide, 0.0F, wide};
+            B200_Multicorrelator_Real_Codes mc;
+            std::complex<float> out_wide[3], out_narrow[3], out_back[3];
+            CHECK(mc.init(8192, 3), "init");
+            mc.set_high_dynamics_resampler(false);
+            mc.set_local_code_and_taps(1023, code.data(), shifts);
+            auto run = [&](std::complex<float>* out, uint64_t pos) {
+                mc.set_input_output_vectors(out, in.data() + pos);
+                if (coalesced) mc.set_stream_position(7, 1000000ULL + pos, n);
+                return mc.Carrier_wipeoff_multicorrelator_resampler(0.3F, 0.01F, 0.0F, 0.4F, 0.2557F, 0.0F, n);
+            };
+            CHECK(run(out_wide, 0), "correlate wide: %s", mc.last_error());
+            shifts[0] = -narrow;  // in place, no set_local_code_and_taps
+            shifts[2] = narrow;
+            CHECK(run(out_narrow, 0), "correlate narrow: %s", mc.last_error());
+            shifts[0] = -wide;  // start_tracking restores the wide spacing the same way
+            shifts[2] = wide;
+            CHECK(run(out_back, 0), "correlate wide again");
+            CHECK(out_back[0] == out_wide[0] && out_back[2] == out_wide[2], "wide taps after the round trip differ (coalesced=%d)", coalesced);
+            CHECK(std::abs(out_narrow[0] - out_wide[0]) > 1e-3F * std::abs(out_wide[1]), "early tap did not move with the shift array (coalesced=%d)", coalesced);
+            CHECK(out_narrow[1] == out_wide[1], "prompt must not change");
+#ifdef HAVE_REF
+            ref_select_arch("a_avx");
+            void* h = ref_mc_create(8192, 3, 0);
+            float s0[3] = {-wide, 0.0F, wide};
+            ref_mc_set_code(h, code.data(), 1023, s0);
+            std::complex<float> want[3];
+            float* kept = ref_mc_shifts(h);
+            kept[0] = -narrow;
+            kept[2] = narrow;
+            ref_mc_correlate(h, reinterpret_cast<const float*>(in.data()), 0.3F, 0.01F, 0.0F, 0.4F, 0.2557F, 0.0F, n, reinterpret_cast<float*>(want));
+            for (int k = 0; k < 3; k++)
+                {
+                    const float rel = std::abs(out_narrow[k] - want[k]) / std::abs(want[1]);
+                    CHECK(rel < 1e-3F, "narrow taps vs reference class: tap %d rel %g (coalesced=%d)", k, rel, coalesced);
+                }
+            ref_mc_destroy(h);
+#endif
+            mc.free();
+        }
+    std::printf("shift-pointer semantics: ok\n");
+}
+
+// N block threads drive the CLASS interface in coalesced mode on one band (what N tracking blocks of a flowgraph do):
+// samples cross PCIe once, the epochs of all channels share launches.  Shape of the reference's engine benchmark
+// (cpu_multicorrelator_real_codes_test.cc:135-169: N concurrent correlators, each calling in a loop), C2 sizes.
+static void coalescer_throughput(int n_threads, int epochs, int window_us)
+{
+    const int n = 25000;  // 1 ms at 25 Msps
+    const uint64_t total = static_cast<uint64_t>(n) * epochs + n;
+    std::vector<std::complex<float>> iq(total);
+    std::mt19937 rng(3);
+    std::uniform_real_distribution<float> ud(-1.0F, 1.0F);
+    for (auto& v : iq) v = std::complex<float>(ud(rng), ud(rng));
+    std::vector<float> code(1023);
+    for (auto& c : code) c = (rng() & 1U) ? 1.0F : -1.0F;
+    b200::Trk_Coalescer* co = b200::Trk_Coalescer::instance();
+    if (co == nullptr)
+        {
+            std::printf("no GPU: coalescer benchmark skipped\n");
+            return;
+        }
+    co->set_window_us(window_us);
+    co->ensure_band(3, 1ULL << 24);
+    co->reset_stats();
+    std::vector<double> lat_sum(n_threads, 0.0), lat_max(n_threads, 0.0);
+    std::atomic<int> failed{0};
+    const uint64_t base = 0;
+    auto worker = [&](int t) {
+        B200_Multicorrelator_Real_Codes mc;
+        float shifts[3] = {-0.5F, 0.0F, 0.5F};
+        std::complex<float> out[3];
+        if (!mc.init(2 * n, 3))
+            {
+                failed++;
+                return;
+            }
+        mc.set_high_dynamics_resampler(false);
+        mc.set_local_code_and_taps(1023, code.data(), shifts);
+        const float step = 1.023e6F / 25.0e6F;
+        for (int k = 0; k < epochs; k++)
+            {
+                const uint64_t pos = static_cast<uint64_t>(k) * n;
+                mc.set_input_output_vectors(out, iq.data() + pos);
+                mc.set_stream_position(3, base + pos, n);
+                const auto t0 = std::chrono::steady_clock::now();
+                if (!mc.Carrier_wipeoff_multicorrelator_resampler(0.1F * t, 0.001F + 1e-5F * t, 0.0F, 0.25F * (t % 4), step, 0.0F, n)) failed++;
+                const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+                lat_sum[t] += us;
+                lat_max[t] = std::max(lat_max[t], us);
+            }
+        mc.free();
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) pool.emplace_back(worker, t);
+    for (auto& t : pool) t.join();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const auto st = co->stats();
+    double mean = 0.0, mx = 0.0;
+    for (int t = 0; t < n_threads; t++)
+        {
+            mean += lat_sum[t] / epochs / n_threads;
+            mx = std::max(mx, lat_max[t]);
+        }
+    CHECK(failed.load() == 0, "%d correlations failed: %s", failed.load(), co->last_error());
+    std::printf("COALESCED {\"threads\": %d, \"epochs\": %d, \"window_us\": %d, \"msamples_per_s\": %.1f, \"call_latency_us_mean\": %.1f, "
+                "\"call_latency_us_max\": %.1f, \"batches\": %llu, \"items_per_batch\": %.1f, \"batch_round_trip_us\": %.1f, "
+                "\"window_expired\": %llu, \"copy_ratio\": %.3f}\n",
+        n_threads, epochs, window_us, static_cast<double>(n_threads) * epochs * n / dt / 1e6, mean, mx, static_cast<unsigned long long>(st.batches),
+        st.batches ? static_cast<double>(st.items) / st.batches : 0.0, st.batches ? st.sum_batch_us / st.batches : 0.0,
+        static_cast<unsigned long long>(st.window_expired), st.samples_offered ? static_cast<double>(st.samples_copied) / st.samples_offered : 0.0);
+}
+
 int main(int argc, char** argv)
 {
     if (argc > 1 && std::string(argv[1]) == "--thresholds")
@@ -82,6 +209,15 @@ int main(int argc, char** argv)
                     std::printf("THRESH %g %u %u %u %.9g\n", pfas[i], sizes[j], bins[j], dw[j], b200::compute_threshold(pfas[i], sizes[j], bins[j], dw[j]));
             return 0;
         }
+    if (argc > 1 && std::string(argv[1]) == "--coalescer")
+        {
+            // throughput of the class interface through the coalescer: ./test_host_mirror --coalescer [threads epochs window_us]
+            const int threads = argc > 2 ? std::atoi(argv[2]) : 32;
+            const int epochs = argc > 3 ? std::atoi(argv[3]) : 200;
+            const int window = argc > 4 ? std::atoi(argv[4]) : 200;
+            coalescer_throughput(threads, epochs, window);
+            return g_fail ? 1 : 0;
+        }
     std::mt19937 rng(7);
     std::uniform_real_distribution<float> ud(0.0F, 1.0F);
     std::vector<float> code(1023);
@@ -89,6 +225,7 @@ int main(int argc, char** argv)
     std::vector<std::complex<float>> in(2 * 8192);
     for (auto& v : in) v = std::complex<float>(ud(rng), ud(rng));
 
+    shift_pointer_semantics(code, in);
     const int sizes[3] = {2048, 4096, 8192};
     for (int n : sizes)
         {

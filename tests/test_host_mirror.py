@@ -14,6 +14,7 @@ def build():
     ref = os.path.join(ROOT, "oracle", "_ref", "liboracle_ref.so")
     cmd = ["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "host", "test_host_mirror.cc"),
            os.path.join(libdir, "host", "b200_multicorrelator_real_codes.cc"),
+           os.path.join(libdir, "host", "b200_trk_coalescer.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_core.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_fine_doppler_core.cc"),
            os.path.join(libdir, "host", "b200_dll_pll_veml_loop.cc"),
@@ -114,3 +115,21 @@ int main()
         else:
             idx, val = int(f[1]), np.float32(float(f[2]))
             assert blk.fft_freq_bins(idx, 320000) == val and orc.fft_freq_bins(idx, 320000) == val, ln
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads,epochs", [(32, 300), (256, 100)])
+def test_class_interface_through_the_coalescer(threads, epochs):
+    """N std::threads drive B200_Multicorrelator_Real_Codes in coalesced mode on one band (C2 sizes: 25 000 samples per
+    epoch): every correlation succeeds, the samples cross PCIe once (copy ratio ~ 1/N) and the epochs share launches.
+    The throughput / per-call latency line is what bench.py reports as `coalesced_class_interface`."""
+    import json
+    exe = build()
+    r = subprocess.run([exe, "--coalescer", str(threads), str(epochs), "200"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("COALESCED ")][0]
+    st = json.loads(line[len("COALESCED "):])
+    print(st)
+    assert st["items_per_batch"] > threads / 4
+    assert st["copy_ratio"] < 2.5 / threads
+    assert st["msamples_per_s"] > 1000.0  # more than real time for 32 channels at 25 Msps (800 Msamples/s)

@@ -595,3 +595,66 @@ def test_file_source_push_matches_array_push(oracle, tmp_path, item_type):
     with pytest.raises(capi.B200Error):
         e.iq_push_file(1, str(tmp_path / "missing.dat"))
     e.close()
+
+
+def test_push_at_is_idempotent_and_handles_gaps(capi, oracle):
+    """b200_iq_push_at: every tracking block of a flowgraph offers the same samples by absolute index - overlapping
+    offers copy only what is new, a later start opens a gap, and items outside [valid_from, write_index) are refused."""
+    eng = capi.Engine(0)
+    rng = np.random.default_rng(5)
+    n = 30000
+    iq = (rng.integers(-50, 50, n) + 1j * rng.integers(-50, 50, n)).astype(np.complex64)
+    eng.iq_create(2, 1 << 16)
+    base = 1_000_000  # the first block to track starts long after sample 0
+    assert eng.iq_push_at(2, base, iq[:10000]) == 10000
+    assert eng.iq_window(2) == (base, base + 10000)
+    assert eng.iq_push_at(2, base, iq[:10000]) == 0              # a second block offers the same samples
+    assert eng.iq_push_at(2, base + 4000, iq[4000:16000]) == 6000  # overlap: only the tail is copied
+    assert eng.iq_push_at(2, base + 2000, iq[2000:9000]) == 0
+    assert eng.iq_window(2) == (base, base + 16000)
+    code = np.where(rng.integers(0, 2, 1023) > 0, 1.0, -1.0).astype(np.float32)
+    shifts = [-0.5, 0.0, 0.5]
+    ch = eng.channel_create(2, 3)
+    eng.channel_set_code(ch, code, shifts)
+    items = np.zeros(1, capi.TRK_ITEM_DTYPE)
+    items[0] = (ch, 4000, base + 8000, 0.2, 0.01, 0.0, 0.3, 0.2557, 0.0)
+    got = eng.trk_batch(items, 3)[0]
+    want = oracle.port.multicorrelator(1, iq[8000:12000], code, shifts, 0.2, 0.01, 0.3, 0.2557)
+    assert np.max(np.abs(got - want)) <= 1e-3 * np.abs(want[1])
+    items[0]["sample_index"] = base + 14000  # runs past the write index
+    with pytest.raises(capi.B200Error):
+        eng.trk_batch(items, 3)
+    items[0]["sample_index"] = base - 100    # before the gap
+    with pytest.raises(capi.B200Error):
+        eng.trk_batch(items, 3)
+    eng.close()
+
+
+def test_channel_set_taps_takes_effect_in_stream_order(capi, oracle):
+    """b200_trk_channel_set_taps: the batch submitted before the change keeps the old spacing, the next one has the new
+    one (the narrow-correlator switch of the tracking block, dll_pll_veml_tracking.cc:2132-2146)."""
+    eng = capi.Engine(0)
+    rng = np.random.default_rng(6)
+    n = 4000
+    iq = (rng.standard_normal(8 * n) + 1j * rng.standard_normal(8 * n)).astype(np.complex64)
+    code = np.where(rng.integers(0, 2, 1023) > 0, 1.0, -1.0).astype(np.float32)
+    eng.iq_create(0, 1 << 16)
+    eng.iq_push(0, iq)
+    ch = eng.channel_create(0, 3)
+    wide, narrow = [-0.5, 0.0, 0.5], [-0.15, 0.0, 0.15]
+    eng.channel_set_code(ch, code, wide)
+    items = np.zeros(2, capi.TRK_ITEM_DTYPE)
+    for k in range(2):
+        items[k] = (ch, n, k * n, 0.1, 0.02, 0.0, 0.4, 0.2557, 0.0)
+    a = eng.trk_batch(items, 3)
+    eng.channel_set_taps(ch, narrow)
+    b = eng.trk_batch(items, 3)
+    eng.channel_set_taps(ch, wide)
+    c = eng.trk_batch(items, 3)
+    for k in range(2):
+        ww = oracle.port.multicorrelator(1, iq[k * n:(k + 1) * n], code, wide, 0.1, 0.02, 0.4, 0.2557)
+        wn = oracle.port.multicorrelator(1, iq[k * n:(k + 1) * n], code, narrow, 0.1, 0.02, 0.4, 0.2557)
+        assert np.max(np.abs(a[k] - ww)) <= 1e-3 * np.abs(ww[1])
+        assert np.max(np.abs(b[k] - wn)) <= 1e-3 * np.abs(wn[1])
+        assert np.array_equal(a[k], c[k])
+    eng.close()
