@@ -208,6 +208,7 @@ class _Ref:
         self.lib = C.CDLL(_REF_SO)
         self.lib.ref_mc_create.restype = C.c_void_p
         self.lib.ref_mc_bench.restype = C.c_double
+        self.lib.ref_mc_bench_pinned.restype = C.c_double
 
     def select_arch(self, arch: str):
         assert self.lib.ref_select_arch(arch.encode()) == 0
@@ -300,10 +301,10 @@ class _Ref:
     def mc_destroy(self, h):
         self.lib.ref_mc_destroy(h)
 
-    def mc_bench(self, threads, n, taps, code_len, iters, n_epochs_buf=8, high_dyn=False) -> float:
-        return float(self.lib.ref_mc_bench(C.c_int(threads), C.c_int(n), C.c_int(taps), C.c_int(code_len),
-                                           C.c_int(iters), C.c_int(n_epochs_buf), C.c_int(int(high_dyn))))
-
+    def mc_bench(self, threads, n, taps, code_len, iters, n_epochs_buf=8, high_dyn=False, pin=True) -> float:
+        """seconds for `threads` concurrent reference correlators doing `iters` calls each (threads pinned round robin)"""
+        return float(self.lib.ref_mc_bench_pinned(C.c_int(threads), C.c_int(n), C.c_int(taps), C.c_int(code_len),
+                                                  C.c_int(iters), C.c_int(n_epochs_buf), C.c_int(1 if high_dyn else 0), C.c_int(1 if pin else 0)))
 
 port = _Port()
 ref = _Ref() if os.path.exists(_REF_SO) else None

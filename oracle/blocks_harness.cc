@@ -31,7 +31,11 @@
 #include "gps_l5_signal_replica.h"
 #include "gps_sdr_signal_replica.h"
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <pthread.h>
+#include <sched.h>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -439,5 +443,63 @@ extern "C"
         (void)reset;
         return -1;
 #endif
+    }
+
+    // CPU timing of the acquisition chain: `threads` channels, each with its own adapter + block created by implementation
+    // string, each running `searches_per_thread` complete searches (Channel::set_signal -> set_local_code -> reset ->
+    // general_work until the block reports) on the same samples, PRN = 1 + (thread + k * threads) % 32.  Threads are pinned
+    // round robin over the process's CPUs and start together.  Returns elapsed seconds (-1 on error); *positives =
+    // number of positive acquisitions.  This is the reference arm of bench.py's acquisition figure.
+    double itf_acq_bench(void* cfg, const char* impl, const char* role, char system, const char* signal, int threads, int searches_per_thread,
+        const void* samples, uint64_t n_items, int pin, int* positives)
+    {
+        std::vector<void*> chans(threads, nullptr);
+        for (int t = 0; t < threads; t++)
+            {
+                chans[t] = itf_channel_create(cfg, impl, role, "", "", t);
+                if (!chans[t]) return -1.0;
+            }
+        std::vector<int> cpus;
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0)
+            for (int c = 0; c < CPU_SETSIZE; c++)
+                if (CPU_ISSET(c, &set)) cpus.push_back(c);
+        std::atomic<int> ready{0}, pos{0};
+        std::atomic<bool> go{false};
+        auto worker = [&](int t) {
+            if (pin && !cpus.empty())
+                {
+                    cpu_set_t one;
+                    CPU_ZERO(&one);
+                    CPU_SET(cpus[t % cpus.size()], &one);
+                    pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+                }
+            auto* ch = static_cast<Channel*>(chans[t]);
+            ready++;
+            while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+            for (int k = 0; k < searches_per_thread; k++)
+                {
+                    itf_set_satellite(chans[t], system, signal, 1U + static_cast<uint32_t>((t + k * threads) % 32));
+                    const size_t before = ch->acq_block->shim_published().size();
+                    ch->acq->reset();
+                    ch->acq_runner->rebase();
+                    ch->acq_runner->run(samples, n_items, -1);
+                    ch->acq->stop_acquisition();
+                    const auto pub = ch->acq_block->shim_published();
+                    for (size_t i = before; i < pub.size(); i++)
+                        if (pub[i].first == "events" && pmt::is_integer(pub[i].second) && pmt::to_long(pub[i].second) == 1) pos++;
+                }
+        };
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++) th.emplace_back(worker, t);
+        while (ready.load() < threads) std::this_thread::yield();
+        const auto t0 = std::chrono::steady_clock::now();
+        go.store(true, std::memory_order_release);
+        for (auto& x : th) x.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (void* c : chans) itf_channel_destroy(c);
+        if (positives) *positives = pos.load();
+        return dt;
     }
 }

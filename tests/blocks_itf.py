@@ -71,6 +71,9 @@ def _load(name):
     lib.itf_trk_run_parallel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_long, C.c_void_p]
     lib.itf_code_float.argtypes = [C.c_char, C.c_char_p, C.c_uint32, C.c_void_p, C.c_int]
     lib.itf_coalescer_stats.argtypes = [C.c_void_p, C.c_int]
+    lib.itf_acq_bench.restype = C.c_double
+    lib.itf_acq_bench.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_int,
+                                  C.POINTER(C.c_int)]
     _libs[name] = lib
     return lib
 
@@ -191,3 +194,19 @@ def coalescer_stats(lib, reset=False):
         return None
     keys = ["batches", "items", "window_expired", "mean_batch_us", "mean_latency_us", "max_latency_us", "samples_copied", "samples_offered"]
     return dict(zip(keys, buf.tolist()))
+
+
+def acq_bench(lib, conf: dict, impl: str, samples: np.ndarray, threads: int, searches_per_thread: int, role="Acquisition_1C", system="G",
+              signal="1C", pin=True):
+    """(seconds, positives) for threads x searches_per_thread complete acquisitions through adapter + block on the CPU."""
+    cfg = lib.itf_config_create()
+    for k, v in conf.items():
+        if isinstance(v, bool):
+            v = "true" if v else "false"
+        lib.itf_config_set(cfg, str(k).encode(), str(v).encode())
+    samples = np.ascontiguousarray(samples, np.complex64)
+    pos = C.c_int(0)
+    dt = lib.itf_acq_bench(cfg, impl.encode(), role.encode(), system.encode(), signal.encode(), threads, searches_per_thread,
+                           samples.ctypes.data, len(samples), 1 if pin else 0, C.byref(pos))
+    lib.itf_config_destroy(cfg)
+    return float(dt), int(pos.value)
