@@ -44,7 +44,9 @@ def config_dict(n_gpus):
             "channels_per_gpu": N_CH, "fs_sps": FS, "epoch_samples": EPOCH, "epochs_per_step": N_EPOCHS, "taps": TAPS,
             "channel_samples_per_step_per_gpu": N_CH * EPOCH * N_EPOCHS,
             "l2_policy": "IQ band (200 MB) exceeds L2 (126 MB); streamed once per step, shared by the 32 channels",
-            "sharding": "channels sharded across ranks, no data-path collective" if n_gpus > 1 else "single GPU"}
+            "sharding": (f"ONE receiver, ONE band, {N_CH} x {n_gpus} channels: every rank correlates its own {N_CH} channels on the same IQ "
+                         "stream; end to end the band crosses PCIe once (rank 0) and fans out to the peers by one NCCL broadcast over "
+                         "NVLink per step (SURVEY 8e); no other data-path collective") if n_gpus > 1 else "single GPU"}
 
 
 def svs_for_rank(rank):
@@ -173,6 +175,146 @@ def ncu_limiter():
         return None
 
 
+def bind_to_gpu_numa(torch, local_rank):
+    """Bind this rank (and with it the first-touch placement of its pinned buffers) to the NUMA node its GPU hangs off.
+    Round 1: eight unbound ranks pushing 54 GB/s each halved the 8-GPU end-to-end efficiency."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = out
+        bus = bus.lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]            # nvidia-smi prints an 8-digit domain, sysfs uses 4
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "bound": False, "why": "single NUMA node"}
+        cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed) or sorted(allowed)
+        os.sched_setaffinity(0, use)
+        return {"numa_node": node, "bound": True, "cpus": len(use)}
+    except Exception as ex:
+        return {"numa_node": None, "bound": False, "why": repr(ex)}
+
+
+def run_trk_config(torch, capi, dev, name, fs, groups, seconds, steps=20, warmup=3, layout="shared", stream=None):
+    """Device-resident throughput of the tracking correlator on one workload.
+    groups: list of dict(n_ch, N, L, shifts, table_rate[, pilot_data]); table_rate = table values per second;
+    pilot_data=True adds, per channel, the 1-tap data-prompt correlator of a tracked pilot (dll_pll_veml_tracking.cc:1246-1256).
+    layout "shared": all channels read one band (a receiver); "distinct": every (channel, epoch) work item reads its own
+    region of a channels-times-larger band, so that 8 B per channel-sample really cross HBM (the roofline run of SURVEY 8d)."""
+    st = stream or torch.cuda.current_stream(dev)
+    eng = capi.Engine(dev.index, st.cuda_stream)
+    n_ch_total = sum(g["n_ch"] for g in groups)
+    n_iq = int(fs * seconds)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    band_len = n_iq * (n_ch_total if layout == "distinct" else 1)
+    iq = torch.randn((band_len + 16, 2), generator=g, device=dev, dtype=torch.float32)
+    eng.iq_attach_dev(0, iq.data_ptr(), band_len + 16, 0)
+    rng = np.random.default_rng(3)
+    items = []
+    max_taps = max(len(gr["shifts"]) for gr in groups)
+    ch_samples = 0
+    c_global = 0
+    for gr in groups:
+        for c in range(gr["n_ch"]):
+            code = rng.choice([-1.0, 1.0], gr["L"]).astype(np.float32)
+            cids = [eng.channel_create(0, len(gr["shifts"]))]
+            eng.channel_set_code(cids[0], code, gr["shifts"])
+            if gr.get("pilot_data"):
+                cids.append(eng.channel_create(0, 1))
+                eng.channel_set_code(cids[1], rng.choice([-1.0, 1.0], gr["L"]).astype(np.float32), [0.0])
+            n_ep = n_iq // gr["N"]
+            doppler = rng.uniform(-5000, 5000)
+            step = gr["table_rate"] * (1 + doppler / 1575.42e6) / fs
+            k = np.arange(n_ep)
+            for cid in cids:
+                arr = np.zeros(n_ep, capi.TRK_ITEM_DTYPE)
+                arr["channel"] = cid
+                arr["n"] = gr["N"]
+                arr["sample_index"] = k * gr["N"] + (c_global * n_iq if layout == "distinct" else 0)
+                arr["rem_carrier_phase_rad"] = np.mod(2 * np.pi * doppler / fs * k * gr["N"], 2 * np.pi)
+                arr["phase_step_rad"] = 2 * np.pi * doppler / fs
+                arr["rem_code_phase_chips"] = -np.mod(rng.uniform(0, gr["L"]) + step * k * gr["N"], gr["L"])
+                arr["code_phase_step_chips"] = step
+                items.append(arr)
+                ch_samples += n_ep * gr["N"]
+            c_global += 1
+    items = np.concatenate(items)
+    if layout == "shared":
+        items = items[np.argsort(items["sample_index"], kind="stable")]     # epoch-major: neighbours share samples
+    it_dev = torch.from_numpy(items.view(np.uint8)).to(dev)
+    out = torch.zeros((items.size, max_taps, 2), dtype=torch.float32, device=dev)
+    for _ in range(warmup):
+        eng.trk_batch_dev(it_dev.data_ptr(), items.size, out.data_ptr(), max_taps, 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        eng.trk_batch_dev(it_dev.data_ptr(), items.size, out.data_ptr(), max_taps, 1)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    line = {"workload": name, "layout": layout, "items": int(items.size), "channel_samples_per_step": int(ch_samples), "ms_per_step": ms,
+            "value": ch_samples / (ms * 1e-3) / 1e6, "unit": UNIT, "algorithmic_GBps": ch_samples * 8 / (ms * 1e-3) / 1e9,
+            "band_bytes": int(band_len * 8)}
+    eng.close()
+    del iq, out, it_dev
+    return line
+
+
+E1_SHIFTS = [-1.2, -0.3, 0.0, 0.3, 1.2]     # VE/E/P/L/VL at -0.6,-0.15,0,0.15,0.6 chips x 2 table values per chip (:632-636)
+
+
+def other_configs(torch, capi, dev, stream, steps):
+    """BASELINE configs[2] (C3) with and without the pilot's data tap, the per-GPU share of configs[4] (C5), and the C2
+    workload laid out so that the algorithmic bytes really come from HBM."""
+    out = {}
+    def leg(key, *a, **kw):
+        try:
+            out[key] = run_trk_config(torch, capi, dev, *a, steps=steps, stream=stream, **kw)
+        except Exception as ex:
+            out[key] = {"error": repr(ex)}
+    leg("C3", "C3: Galileo E1 64 ch x 50 Msps x 1 s, N=200000, sinBOC(1,1) table of 8184, 5 taps VE/E/P/L/VL", 50e6,
+        [dict(n_ch=64, N=200000, L=8184, shifts=E1_SHIFTS, table_rate=2 * 1.023e6)], 1.0)
+    leg("C3_track_pilot", "C3 with track_pilot (default): + one data-prompt tap per channel on the E1B replica", 50e6,
+        [dict(n_ch=64, N=200000, L=8184, shifts=E1_SHIFTS, table_rate=2 * 1.023e6, pilot_data=True)], 1.0)
+    leg("C5_per_gpu_share", "C5 / 8 GPUs: 12 GPS L1 (N=50000) + 12 Galileo E1 (N=200000, 5 taps) + 8 GPS L5 (N=50000, L=10230) at 50 Msps x 1 s",
+        50e6, [dict(n_ch=12, N=50000, L=1023, shifts=SHIFTS, table_rate=1.023e6),
+               dict(n_ch=12, N=200000, L=8184, shifts=E1_SHIFTS, table_rate=2 * 1.023e6),
+               dict(n_ch=8, N=50000, L=10230, shifts=SHIFTS, table_rate=10.23e6)], 1.0)
+    leg("C2_distinct_iq", "C2 arithmetic, but every (channel, epoch) reads its own samples: 32 ch x 25 Msps x 0.5 s from a 3.2 GB band",
+        FS, [dict(n_ch=N_CH, N=EPOCH, L=1023, shifts=SHIFTS, table_rate=1.023e6)], 0.5, layout="distinct")
+    return out
+
+
+def coalesced_class_interface():
+    """Throughput and per-call latency of the reference-shaped CLASS interface (B200_Multicorrelator_Real_Codes, one
+    std::thread per channel, C2 epoch size) through the per-process coalescer: tests/host/test_host_mirror --coalescer."""
+    exe = os.path.join(ROOT, "tests", "host", "test_host_mirror")
+    if not os.path.exists(exe):
+        return {"error": "tests/host/test_host_mirror not built"}
+    res = []
+    for threads, epochs in ((32, 400), (256, 150)):
+        try:
+            r = subprocess.run([exe, "--coalescer", str(threads), str(epochs), "200"], capture_output=True, text=True, timeout=300)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("COALESCED ")]
+            res.append(json.loads(line[0][len("COALESCED "):]) if line else {"threads": threads, "error": (r.stdout + r.stderr)[-300:]})
+        except Exception as ex:
+            res.append({"threads": threads, "error": repr(ex)})
+    return res
+
+
 # ---- acquisition sub-benchmark (BASELINE configs[3], SURVEY 8d "C4") -----------------------------------
 ACQ_FS = 25000000
 ACQ_N = 25000
@@ -210,16 +352,40 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
     res_dev = torch.zeros(len(my_slots) * capi.ACQ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     prn_dev = torch.from_numpy((my_slots + 1).astype(np.int64)).to(dev)
 
-    def sweep():
+    peak_dev = torch.zeros(4, dtype=torch.int32, device=dev)
+    prn32_dev = torch.from_numpy((my_slots + 1).astype(np.int32)).to(dev)
+
+    def local_sweep():
         acq.search_dev(iq_dev.data_ptr(), slots, res_dev.data_ptr())
         if world > 1:
-            # packed key (statistic bits | prn | doppler bin | code phase), MAX all-reduce over NVLink
-            r = res_dev.view(torch.int32).view(-1, 7).to(torch.int64)
-            key = ((r[:, 3] & 0xFFFFFFFF) << 32) | (prn_dev << 24) | (r[:, 1] << 15) | r[:, 0]
-            best = key.max().reshape(1)
-            dist.all_reduce(best, op=dist.ReduceOp.MAX)
-            return best
-        return None
+            acq.sweep_best_dev(res_dev.data_ptr(), prn32_dev.data_ptr(), len(my_slots), peak_dev.data_ptr())
+
+    # the sweep's launches are captured once in a CUDA graph (a repeated sweep over the same slots issues no host
+    # synchronisation): one graph launch per sweep instead of five kernel launches through ctypes
+    graph = None
+    try:
+        local_sweep()
+        torch.cuda.synchronize()
+        cur = torch.cuda.current_stream(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cur):
+            local_sweep()
+        torch.cuda.synchronize()
+    except Exception:
+        graph = None
+        torch.cuda.synchronize()
+
+    gathered = [None]
+
+    def sweep():
+        if graph is not None:
+            graph.replay()
+        else:
+            local_sweep()
+        if world > 1:
+            # the only exchange: an all-gather of the ranks' 16-byte (statistic, PRN, bin, code phase) records over NVLink
+            gathered[0] = bd.allgather_peaks(peak_dev)
+        return gathered[0]
 
     for _ in range(warmup):
         sweep()
@@ -238,13 +404,13 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
         tms = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    launches = eng.launch_count() - l0
+    launches = (eng.launch_count() - l0) if graph is None else steps * (5 if world == 1 else 6)
     res_local = np.frombuffer(res_dev.cpu().numpy().tobytes(), capi.ACQ_RESULT_DTYPE)
     if world > 1:
         res = bd.gather_results(res_local, [int(x) for x in my_slots], ACQ_PRNS, device=dev)
-        _, bprn, bd_bin, bt = bd.unpack_peak_key(best.cpu().numpy())
+        winner = bd.best_peak(best.cpu().numpy().view(bd.PEAK_DTYPE))
         w = int(np.argmax(res["test_statistics"]))
-        assert int(bprn[0]) == w + 1 and int(bt[0]) == int(res["index_time"][w]), "all-reduced peak != gathered table"
+        assert int(winner["prn"]) == w + 1 and int(winner["index_time"]) == int(res["index_time"][w]), "exchanged peak != gathered table"
     else:
         res = res_local
     # compute_threshold (pcps_acquisition.cc:52-56): 2 * gamma_p_inv(2 * dwells, (1 - pfa)^(1 / (N * bins)))
@@ -286,7 +452,7 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
                    "d2h_bytes_per_step": ACQ_PRNS * capi.ACQ_RESULT_DTYPE.itemsize, "ms_per_sweep": dt * 1e3,
                    "synchronous_one_object": {"value": ACQ_PRNS / dt_sync, "ms_per_sweep": dt_sync * 1e3},
                    "path": "b200_acq_search_submit / _wait alternating over two acquisition objects"},
-           "gpu_launches_per_sweep": launches / steps,
+           "gpu_launches_per_sweep": launches / steps, "cuda_graph": graph is not None,
            "roofline": {"bound": "hbm", "kernel": "acq_corr_kernel", "achieved": abytes / (ms * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": abytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                         "algorithmic_bytes_per_sweep": abytes, "algorithmic_gflop_per_sweep": aflops / 1e9,
@@ -295,7 +461,8 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
                                 "shared-memory/FP32 bound, see DESIGN.md"},
            "detected_prns": detected, "present_prns": present,
            "e2e_matches_dev": bool(np.array_equal(r2["index_time"], res_local["index_time"])),
-           "n_gpus": world, "sharding": "PRNs round-robin over ranks; one 8-byte MAX all-reduce of the packed peak key per sweep" if world > 1 else "single GPU"}
+           "n_gpus": world, "sharding": ("PRNs round-robin over ranks; per sweep one CUDA-graph launch per rank and one all-gather of 16-byte peak records "
+                        "(b200_acq_sweep_best_dev)") if world > 1 else "single GPU"}
     if with_cpu:
         out["cpu_baseline"] = cpu_baseline_acq(iq)
     acq.close()
@@ -363,64 +530,103 @@ def bench_closed_loop(capi, eng, svs, cids, n_epochs=990, repeats=3, replicas=1,
                     "resident CTAs; per_epoch_launch_mode = the same arithmetic as 2 launches per epoch"}
 
 
-def cpu_baseline_acq(iq=None, n_prn=2):
-    """numpy restatement of pcps_acquisition (pocketfft float32, all cores via scipy.fft workers); FFTW/GNU Radio
-    are not installable here, so kind is "port"."""
-    import oracle
-    from oracle.acq_np import AcqConf, PcpsAcquisitionOracle
-    from gnss_synth import make_iq
-    cores = os.cpu_count() or 1
-    if iq is None:
-        code = oracle.port.gps_ca_code(2)
-        iq = make_iq({2: code}, float(ACQ_FS), ACQ_N, [dict(prn=2, doppler=1234.0, code_phase_chips=100.0, cn0=45.0)], seed=4)
-    conf = AcqConf(fs_in=ACQ_FS, samples_per_ms=float(ACQ_N), samples_per_code=float(ACQ_N), samples_per_chip=24,
-                   doppler_max=ACQ_DMAX, doppler_step=ACQ_DSTEP, pfa=0.001)
-    o = PcpsAcquisitionOracle(conf, workers=cores)
-    o.set_local_code(oracle.port.gps_ca_code_complex_sampled(2, ACQ_FS))
-    o.acquisition_core(iq)   # warm-up (plans, caches)
-    t0 = time.perf_counter()
-    for _ in range(n_prn):
-        o.num_noncoherent_integrations_counter = 0
-        o.acquisition_core(iq)
-    dt = time.perf_counter() - t0
-    return {"value": n_prn / dt, "unit": "acquisitions/s", "cores": cores, "kind": "port",
-            "sample": f"{n_prn} PRN searches x {conf.num_doppler_bins} bins x N={ACQ_N}; numpy restatement of pcps_acquisition.cc "
-                      f"with scipy.fft (pocketfft, float32, workers={cores})"}
-
-
 # ---- CPU baseline (the reference's own SIMD path, timed like its own harness) --------------------
-def cpu_baseline(budget_s=12.0):
+def usable_cpus():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(budget_s=12.0, sweep=False):
+    """The reference's Cpu_Multicorrelator_Real_Codes (u_avx kernels) compiled in place: one correlator per host thread,
+    threads PINNED round robin over the process's CPUs and started together (oracle/ref_engine.cc ref_mc_bench_pinned),
+    shaped like cpu_multicorrelator_real_codes_test.cc:41-62,135-169.  sweep=True adds the T in {1, nproc/2, nproc} x
+    length {2048, 4096, 8192 (the reference's), 25000, 200000 (ours)} table BASELINE.md promises, per-thread figures included."""
     import oracle
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     if oracle.ref is not None:
         kind = "reference"
         oracle.ref.select_arch("u_avx")   # GNU Radio buffers are unaligned: VOLK dispatches to u_ variants
 
-        def run(iters):
-            return oracle.ref.mc_bench(cores, EPOCH, TAPS, 1023, iters, 8, False)
+        def run(iters, threads=cores, n=EPOCH, taps=TAPS, L=1023):
+            return oracle.ref.mc_bench(threads, n, taps, L, iters, 8, False, pin=True)
     else:
         kind = "port"
         rng = np.random.default_rng(0)
         iq = (rng.standard_normal(EPOCH * 8) + 1j * rng.standard_normal(EPOCH * 8)).astype(np.complex64)
         code = oracle.port.gps_ca_code(1)
 
-        def run(iters):
-            params = np.tile(np.array([[0.4, 0.001, 0.3, 1023.0 / EPOCH]], np.float32), (iters * cores, 1))
-            idx_iq = np.tile(iq, 1)
+        def run(iters, threads=cores, n=EPOCH, taps=TAPS, L=1023):
+            params = np.tile(np.array([[0.4, 0.001, 0.3, 1023.0 / n]], np.float32), (iters * threads, 1))
             t0 = time.perf_counter()
-            # items walk over 8 distinct epochs
-            oracle.port.multicorrelator_batch(1, cores, idx_iq, 0, code, SHIFTS, params, EPOCH)
+            oracle.port.multicorrelator_batch(1, threads, np.tile(iq, max(1, n // EPOCH + 1)), 0, code, SHIFTS, params, n)
             return time.perf_counter() - t0
     t = run(20)
     iters = int(max(20, min(400000, 20 * budget_s / max(t, 1e-6))))
     t = run(iters)
     samples = cores * iters * EPOCH
-    return {"value": samples / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{cores} threads x {iters} epochs of {EPOCH} samples x {TAPS} taps, L=1023 "
-                      f"({samples / 1e6:.0f} M channel-samples, {t:.1f} s); "
-                      + ("reference Cpu_Multicorrelator_Real_Codes with volk_gnsssdr u_avx kernels "
-                         "(harness shaped like cpu_multicorrelator_real_codes_test.cc:41-62,135-169)"
-                         if kind == "reference" else "C port of the a_avx/u_avx arithmetic")}, t
+    out = {"value": samples / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind, "per_thread": samples / t / 1e6 / cores, "pinned": True,
+           "sample": f"{cores} pinned threads x {iters} epochs of {EPOCH} samples x {TAPS} taps, L=1023 "
+                     f"({samples / 1e6:.0f} M channel-samples, {t:.1f} s); "
+                     + ("reference Cpu_Multicorrelator_Real_Codes with volk_gnsssdr u_avx kernels "
+                        "(harness shaped like cpu_multicorrelator_real_codes_test.cc:41-62,135-169)"
+                        if kind == "reference" else "C port of the a_avx/u_avx arithmetic")}
+    if sweep:
+        table = []
+        for T in sorted({1, max(1, cores // 2), cores}):
+            for n, taps, L in ((2048, 3, 1023), (4096, 3, 1023), (8192, 3, 1023), (25000, 3, 1023), (200000, 5, 8184)):
+                it = max(4, int(4.0e6 / n))
+                dt = run(it, threads=T, n=n, taps=taps, L=L)
+                table.append({"threads": T, "length": n, "taps": taps, "msamples_per_s": T * it * n / dt / 1e6,
+                              "per_thread": it * n / dt / 1e6})
+        out["sweep"] = table
+    return out, t
+
+
+def cpu_baseline_acq(iq=None, budget_s=15.0):
+    """Acquisition on the host: the reference's OWN chain compiled in place - GpsL1CaPcpsAcquisition adapter ->
+    pcps_acquisition block (general_work buffering, doppler_grid, CFAR statistic) - driven by the single-block scheduler of
+    oracle/shim, one channel per pinned host thread, threads over PRNs (oracle/blocks_harness.cc itf_acq_bench).  The
+    FFT behind gr::fft is our float32 mixed-radix Stockham transform (oracle/shim/gnuradio/fft/fft.h; FFTW is not
+    installable here).  Falls back to the numpy restatement where the block library is absent."""
+    from gnss_synth import make_iq, gps_ca_code
+    cores = usable_cpus()
+    if iq is None:
+        iq = make_iq({2: gps_ca_code(2)}, float(ACQ_FS), 2 * ACQ_N + 64, [dict(prn=2, doppler=1234.0, code_phase_chips=100.0, cn0=45.0)], seed=4)
+    try:
+        import blocks_itf as bi
+        lib = bi.ref_lib()
+    except Exception:
+        lib = None
+    if lib is not None:
+        conf = {"GNSS-SDR.internal_fs_sps": ACQ_FS, "Acquisition_1C.item_type": "gr_complex", "Acquisition_1C.doppler_max": ACQ_DMAX,
+                "Acquisition_1C.doppler_step": ACQ_DSTEP, "Acquisition_1C.pfa": 0.001, "Acquisition_1C.blocking": True}
+        feed = np.ascontiguousarray(np.resize(iq, 2 * ACQ_N + 64))
+        dt1, _ = bi.acq_bench(lib, conf, "GPS_L1_CA_PCPS_Acquisition", feed, 1, 2)
+        per_thread = 2 / dt1
+        k = int(max(1, min(64, budget_s * per_thread * 0.5)))
+        dt, pos = bi.acq_bench(lib, conf, "GPS_L1_CA_PCPS_Acquisition", feed, cores, k)
+        bins = int(np.ceil(2 * ACQ_DMAX / ACQ_DSTEP))
+        return {"value": cores * k / dt, "unit": "acquisitions/s", "cores": cores, "kind": "reference", "per_thread_alone": per_thread,
+                "per_thread_loaded": k / dt, "pinned": True,
+                "sample": f"{cores} pinned threads x {k} searches ({bins} Doppler bins x N={ACQ_N}) through the reference's own "
+                          f"GpsL1CaPcpsAcquisition adapter + pcps_acquisition block compiled in place ({dt:.1f} s); FFT = float32 "
+                          "mixed-radix Stockham shim behind gr::fft (FFTW / GNU Radio not installable)"}
+    import oracle
+    from oracle.acq_np import AcqConf, PcpsAcquisitionOracle
+    conf = AcqConf(fs_in=ACQ_FS, samples_per_ms=float(ACQ_N), samples_per_code=float(ACQ_N), samples_per_chip=24,
+                   doppler_max=ACQ_DMAX, doppler_step=ACQ_DSTEP, pfa=0.001)
+    o = PcpsAcquisitionOracle(conf, workers=cores)
+    o.set_local_code(oracle.port.gps_ca_code_complex_sampled(2, ACQ_FS))
+    o.acquisition_core(iq[:ACQ_N])
+    t0 = time.perf_counter()
+    for _ in range(2):
+        o.num_noncoherent_integrations_counter = 0
+        o.acquisition_core(iq[:ACQ_N])
+    dt = time.perf_counter() - t0
+    return {"value": 2 / dt, "unit": "acquisitions/s", "cores": cores, "kind": "port",
+            "sample": f"2 PRN searches x {conf.num_doppler_bins} bins x N={ACQ_N}; numpy restatement of pcps_acquisition.cc with scipy.fft"}
 
 
 def run_reference_arm(args):
@@ -434,7 +640,17 @@ def run_reference_arm(args):
             vals.append(cb["value"])
             times.append(t)
     cb["value"] = float(np.mean(vals))
-    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+    cb["per_thread"] = cb["value"] / cb["cores"]
+    try:
+        sw, _ = cpu_baseline(budget_s=0.5, sweep=True)
+        cb["sweep"] = sw.get("sweep")
+    except Exception as ex:
+        cb["sweep"] = {"error": repr(ex)}
+    try:
+        acq_ref = cpu_baseline_acq()
+    except Exception as ex:
+        acq_ref = {"error": repr(ex)}
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "acq": acq_ref,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args.gpus), "cpu_baseline": cb,
@@ -454,6 +670,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-acq", action="store_true")
     ap.add_argument("--no-loop", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sustained leg, the other BASELINE configs and the coalescer leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -474,12 +691,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(torch, local_rank)   # before any pinned allocation (first touch)
 
     from gnss_synth import gps_ca_code   # synthetic-input code tables; oracle/ is only touched by the CPU-baseline legs
     codes = {p: gps_ca_code(p) for p in range(1, N_CH + 1)}
-    svs = svs_for_rank(rank)
+    # one receiver: every rank sees the SAME band (the 32 satellites of C2); rank r owns channels 32 r .. 32 r + 31
+    svs = svs_for_rank(0)
     n_iq = EPOCH * N_EPOCHS
-    iq_dev = synth_iq_device(torch, codes, svs, n_iq + 16, SEED + rank, dev)
+    iq_dev = synth_iq_device(torch, codes, svs, n_iq + 16, SEED, dev)
 
     # a dedicated (non-default) torch stream is made current and handed to the engine, so that the
     # torch.cuda.Event timings below are recorded on the very stream the kernels are launched on
@@ -545,7 +764,62 @@ def main():
 
     # ---- e2e: host buffers through the public C ABI, copies inside the timed region --------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world > 1:
+        # ---- one receiver on N GPUs: the band crosses PCIe ONCE (rank 0, b200_iq_refill from pinned memory into a device
+        # buffer), fans out to the peers with one NCCL broadcast over NVLink, every rank correlates its own 32 channels and
+        # returns its taps to its host.  Two band buffers: step k+1's copy + broadcast overlap step k's correlation.
+        host_iq = None
+        if rank == 0:
+            host_iq = torch.empty((n_iq, 2), dtype=torch.float32, pin_memory=True)
+            host_iq.copy_(iq_dev[:n_iq])
+        bands = [torch.zeros((n_iq + 16, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        items_b, outs_b, outs_host, done_ev = [], [], [], []
+        for b in range(2):
+            eng.iq_attach_dev(2 + b, bands[b].data_ptr(), n_iq + 16, 0)
+            cb_ids = []
+            for sv in svs:
+                cid = eng.channel_create(2 + b, TAPS)
+                eng.channel_set_code(cid, codes[sv["prn"]], SHIFTS)
+                cb_ids.append(cid)
+            items_b.append(torch.from_numpy(build_items(capi, svs, cb_ids, 0).view(np.uint8)).to(dev))
+            outs_b.append(torch.zeros((n_items, TAPS, 2), dtype=torch.float32, device=dev))
+            outs_host.append(torch.empty((n_items, TAPS, 2), dtype=torch.float32, pin_memory=True))
+            done_ev.append(torch.cuda.Event())
+        torch.cuda.synchronize()
+
+        def run_one_receiver(n_steps):
+            for k in range(n_steps):
+                b = k % 2
+                if k >= 2:
+                    done_ev[b].synchronize()          # step k-2's taps are on the host: its band buffer is free again
+                if rank == 0:
+                    eng.iq_refill_ptr(2 + b, host_iq.data_ptr(), n_iq, 0)   # C ABI: pinned host -> device, copy stream, engine stream waits
+                dist.broadcast(bands[b], src=0)        # NVLink fan-out, ordered after the refill on the engine stream
+                eng.trk_batch_dev(items_b[b].data_ptr(), n_items, outs_b[b].data_ptr(), TAPS, 1)
+                outs_host[b].copy_(outs_b[b], non_blocking=True)
+                done_ev[b].record()
+            torch.cuda.synchronize()
+            return outs_host[(n_steps - 1) % 2]
+
+        run_one_receiver(max(3, args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        res_t = run_one_receiver(args.steps)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        res = res_t.numpy()[:, :, 0] + 1j * res_t.numpy()[:, :, 1]
+        e2e = {"value": world * ch_samples_step * args.steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_iq * 8), "d2h_bytes_per_step": int(world * n_items * TAPS * 8),
+               "nvlink_broadcast_bytes_per_step": int((n_iq + 16) * 8), "ms_per_step": dt / args.steps * 1e3,
+               "max_rel_diff_vs_value_run": float(np.max(np.abs(res - taps)) / np.max(np.abs(taps))),
+               "numa": numa,
+               "path": "rank 0: b200_iq_refill (pinned host -> device, once per step for the whole job); all ranks: NCCL broadcast of the "
+                       "band over NVLink, b200_trk_batch_dev on the rank's 32 channels, taps D2H to pinned host memory; two band "
+                       "buffers so that step k+1's copy and broadcast overlap step k's correlation"}
+    elif not args.no_e2e:
         host_iq = torch.empty((n_iq, 2), dtype=torch.float32, pin_memory=True)
         host_iq.copy_(iq_dev[:n_iq])
         torch.cuda.synchronize()
@@ -692,33 +966,74 @@ def main():
         except Exception as ex:
             closed = {"error": repr(ex)}
 
+    # ---- sustained leg: the same step back to back for >= 2 s (the 20-step timed region above is 17 ms) -------------
+    sustained = None
+    if not args.no_extra:
+        n_sus = int(max(args.steps, 2.2 / max(ms_per_step * 1e-3, 1e-6)))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        s0.record()
+        for _ in range(n_sus):
+            step_dev()
+        s1.record()
+        barrier()
+        sus_ms = s0.elapsed_time(s1)
+        tsus = torch.tensor([sus_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tsus, op=dist.ReduceOp.MAX)
+        sus_ms = float(tsus.item())
+        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                     "value": world * ch_samples_step * n_sus / (sus_ms * 1e-3) / 1e6, "unit": UNIT,
+                     "clocks": sampler2.stop() if rank == 0 else None}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant (only) kernel ----------------------------------------------------
+    extra = None
+    coalesced = None
+    if not args.no_extra and world == 1:
+        extra = other_configs(torch, capi, dev, tstream, steps=max(5, min(args.steps, 20)))
+        coalesced = coalesced_class_interface()
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------
+    # `achieved` follows the contract: ALGORITHMIC bytes (8 B per channel-sample) per launch / mean launch time of the
+    # timed region.  On C2 the 32 channels share one IQ stream, so those bytes do not cross HBM 32 times (`traffic` = what
+    # ncu saw) and frac can exceed 1: it is NOT the kernel's distance from a limit.  Two companions say what is:
+    #   hbm_true   the same arithmetic with every (channel, epoch) reading its own samples: 8 B per channel-sample really from HBM;
+    #   fp32_issue what ncu names as the limiter of the C2 launch (instruction issue / FMA pipe), from profiles/.
     peak, peak_src = measured_peak_gbs()
     launch_ms = float(np.mean(per_launch_ms))
     achieved = ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE / (launch_ms * 1e-3) / 1e9
+    hbm_true = None
+    if extra and isinstance(extra.get("C2_distinct_iq"), dict) and "ms_per_step" in extra["C2_distinct_iq"]:
+        d = extra["C2_distinct_iq"]
+        hbm_true = {"workload": d["workload"], "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s", "frac": d["algorithmic_GBps"] / peak,
+                    "ms_per_launch": d["ms_per_step"], "value": d["value"],
+                    "note": "band = channels x samples: no sharing between channels, DRAM traffic == algorithmic bytes (+ items/taps)"}
     roofline = {"bound": "hbm", "kernel": "trk_shared_kernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "algorithmic_bytes_per_launch": ch_samples_step * ALGO_BYTES_PER_CHANNEL_SAMPLE,
-                "launch_ms": launch_ms, "peak_source": peak_src, "limiter": ncu_limiter(),
-                "note": "algorithmic bytes = 8 B per channel-sample (SURVEY 8d) = what 32 independent per-channel correlators read; "
-                        "the 32 channels share one IQ stream, so DRAM traffic (`traffic`, from ncu) is the 200 MB stream read once and "
-                        "the shared-window kernel stages each tile once per 8 items (L2->SM 0.87 GB per launch): frac > 1 against the HBM "
-                        "copy peak is expected; the kernel is bound by FP32 instruction issue (ncu: issue 68 %, FMA pipe 67 %), see DESIGN.md 4.2"}
+                "launch_ms": launch_ms, "peak_source": peak_src, "limiter": ncu_limiter(), "hbm_true": hbm_true,
+                "note": "achieved/frac = algorithmic bytes (8 B per channel-sample, SURVEY 8d) over the launch time, as the contract defines "
+                        "them; the 32 channels of C2 share one IQ stream, so real DRAM traffic is `traffic` (the 200 MB stream once) and "
+                        "frac > 1 is possible - see `hbm_true` for the fraction with distinct samples per channel-epoch and `limiter` for "
+                        "what ncu names as the bound of the C2 launch (FP32 instruction issue / FMA pipe)"}
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        cb, _ = cpu_baseline()
+        cb, _ = cpu_baseline(sweep=True)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
             "stream_msps": value / N_CH, "prompt_over_noise": prompt_snr, "engine_timer_check_ms": check_ms,
-            "acq": acq, "closed_loop": closed}
+            "acq": acq, "closed_loop": closed, "sustained": sustained, "other_configs": extra,
+            "coalesced_class_interface": coalesced, "numa": numa}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

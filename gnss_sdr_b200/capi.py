@@ -57,8 +57,10 @@ _SIGS = {
     "b200_iq_push": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_push_at": ([_vp, C.c_int, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_window": ([_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
+    "b200_iq_refill": ([_vp, C.c_int, _vp, C.c_uint64, C.c_uint64], C.c_int),
     "b200_trk_set_taps": ([_vp, _vp], C.c_int),
     "b200_trk_channel_set_taps": ([_vp, C.c_int, _vp], C.c_int),
+    "b200_acq_sweep_best_dev": ([_vp, _vp, _vp, C.c_uint32, _vp], C.c_int),
     "b200_acq_search_i16": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
     "b200_acq_search_step_two_i16": ([_vp, _vp, C.c_uint32, C.c_uint32, C.c_float, _vp], C.c_int),
     "b200_iq_push_i16": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
@@ -259,6 +261,9 @@ class Engine:
         n_new = C.c_uint64(0)
         _chk(lib.b200_iq_push_at(self.h, band, int(abs_index), iq.ctypes.data, iq.size, C.byref(n_new)), "b200_iq_push_at")
         return n_new.value
+
+    def iq_refill_ptr(self, band: int, host_ptr: int, n: int, first_index: int = 0):
+        _chk(lib.b200_iq_refill(self.h, band, host_ptr, n, first_index), "b200_iq_refill")
 
     def iq_window(self, band: int):
         lo, hi = C.c_uint64(0), C.c_uint64(0)
@@ -494,6 +499,10 @@ class PcpsAcquisition:
         slots = np.ascontiguousarray(slots, np.uint32)
         _chk(lib.b200_acq_search_dev(self.h, in_dev_ptr, slots.ctypes.data, slots.size, dwell_counter, results_dev_ptr),
              "b200_acq_search_dev")
+
+    def sweep_best_dev(self, results_dev_ptr: int, prn_of_result_dev_ptr: int, n_results: int, peak_dev_ptr: int):
+        """one 16-byte b200_acq_peak record of the sweep, written on the device (no host synchronisation)"""
+        _chk(lib.b200_acq_sweep_best_dev(self.h, results_dev_ptr, prn_of_result_dev_ptr, n_results, peak_dev_ptr), "b200_acq_sweep_best_dev")
 
     def read_grid(self, slot: int) -> np.ndarray:
         g = np.empty((self.conf.num_doppler_bins, self.conf.effective_fft_size), np.float32)

@@ -396,9 +396,22 @@ extern "C"
     {
         if (!a || !in_dev || !results_dev) return B200_ERR_ARG;
         B200_CUDA_TRY(cudaSetDevice(a->e->device));
-        // slot_pin is reused by every call: wait for the previous call's H2D of it
-        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        // (search_impl synchronises by itself when - and only when - the slot list changed and slot_pin must be rewritten; a
+        // repeated sweep over the same slots issues no host synchronisation and can be captured in a CUDA graph)
         return search_impl(a, reinterpret_cast<const float2*>(in_dev), slots_host, n_slots, dwell_counter, results_dev);
+    }
+
+    int b200_acq_sweep_best_dev(b200_acq* a, const b200_acq_result* results_dev, const uint32_t* prn_of_result_dev, uint32_t n_results,
+        b200_acq_peak* peak_dev)
+    {
+        if (!a || !results_dev || !prn_of_result_dev || !peak_dev) return B200_ERR_ARG;
+        const int rc = acq_launch_sweep_best(results_dev, prn_of_result_dev, static_cast<int>(n_results), peak_dev, a->stream);
+        if (rc == B200_OK)
+            {
+                std::lock_guard<std::mutex> lk(a->e->mu);
+                a->e->launches++;
+            }
+        return rc;
     }
 
     int b200_acq_read_grid(b200_acq* a, uint32_t slot, float* grid_host)

@@ -726,6 +726,46 @@ __global__ void acq_twiddle_kernel(float2* __restrict__ tw, FftPlan pl)
         }
 }
 
+// Best satellite of one sweep as ONE 16-byte record {test statistic, PRN, Doppler bin, code phase}: what a rank
+// contributes to the multi-GPU peak exchange (an all-gather of N records).  Ties go to the lowest
+// (slot order, bin, code phase) like the reference's strict '>' scans (pcps_acquisition.cc:417-426).
+__global__ void acq_sweep_best_kernel(const b200_acq_result* __restrict__ results, const unsigned int* __restrict__ prn_of_result, int n,
+    b200_acq_peak* __restrict__ out)
+{
+    const int lane = threadIdx.x;
+    float best = -1.0f;
+    int who = 0x7fffffff;
+    for (int i = lane; i < n; i += 32)
+        {
+            const float v = results[i].test_statistics;
+            if (v > best)
+                {
+                    best = v;
+                    who = i;
+                }
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+            if (ov > best || (ov == best && ow < who))
+                {
+                    best = ov;
+                    who = ow;
+                }
+        }
+    if (lane == 0)
+        {
+            b200_acq_peak p;
+            p.test_statistics = (n > 0 && who != 0x7fffffff) ? best : 0.0f;
+            p.prn = (n > 0 && who != 0x7fffffff) ? prn_of_result[who] : 0u;
+            p.index_doppler = (n > 0 && who != 0x7fffffff) ? results[who].index_doppler : 0u;
+            p.index_time = (n > 0 && who != 0x7fffffff) ? results[who].index_time : 0u;
+            *out = p;
+        }
+}
+
 DeviceOnce g_attr_once;  // per device (a second engine on another GPU needs its own opt-in), thread-safe
 int set_attrs()
 {
@@ -976,6 +1016,13 @@ int acq_launch_stats(const AcqRowStat* rowstat, int n_slots, int bins, int ne, i
 int acq_launch_finish_second_peak(const float* second_peak, int n_slots, b200_acq_result* results, cudaStream_t st)
 {
     acq_finish_second_peak_kernel<<<(n_slots + 63) / 64, 64, 0, st>>>(second_peak, n_slots, results);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_sweep_best(const b200_acq_result* results, const unsigned int* prn_of_result, int n, b200_acq_peak* out, cudaStream_t st)
+{
+    acq_sweep_best_kernel<<<1, 32, 0, st>>>(results, prn_of_result, n, out);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }

@@ -111,4 +111,5 @@ int acq_launch_stats(const AcqRowStat* rowstat, int n_slots, int bins, int ne, i
     int doppler_step, unsigned int dwell_counter, int use_cfar, void* best, b200_acq_result* results, int step_two, float center2,
     float step2, float prev_input_power, cudaStream_t st);
 int acq_launch_finish_second_peak(const float* second_peak, int n_slots, b200_acq_result* results, cudaStream_t st);
+int acq_launch_sweep_best(const b200_acq_result* results, const unsigned int* prn_of_result, int n, b200_acq_peak* out, cudaStream_t st);
 }  // namespace b200

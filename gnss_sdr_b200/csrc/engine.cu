@@ -548,6 +548,37 @@ extern "C"
         return B200_OK;
     }
 
+    int b200_iq_refill(b200_engine* e, int band, const b200_cf32* host, uint64_t n, uint64_t first_index)
+    {
+        if (!e || band < 0 || band >= kMaxBands || (!host && n)) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> lk(e->mu);
+        Band& b = e->bands[band];
+        if (!b.in_use || !b.attached)
+            {
+                set_error("band %d is not an attached device buffer (call b200_iq_attach_dev)", band);
+                return B200_ERR_STATE;
+            }
+        if (n > b.capacity)
+            {
+                set_error("refill of %llu samples exceeds the attached buffer (%llu)", (unsigned long long)n, b.capacity);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(e->device));
+        // same ordering as b200_iq_push: the copy runs on the copy stream, later launches on the compute stream wait for it;
+        // overwriting samples an in-flight launch still reads is the caller's double-buffering responsibility
+        if (n) B200_CUDA_TRY(cudaMemcpyAsync(const_cast<float2*>(b.base), host, n * sizeof(float2), cudaMemcpyHostToDevice, e->copy_stream));
+        B200_CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
+        B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->copy_done, 0));
+        if (b.first_index != first_index)
+            {
+                b.first_index = first_index;
+                e->tables_dirty = true;
+            }
+        b.valid_from = first_index;
+        b.write_index = first_index + n;
+        return B200_OK;
+    }
+
     // ---- channels ------------------------------------------------------------------------------
     int b200_trk_channel_create(b200_engine* e, int band, int n_correlators, int* channel_id)
     {

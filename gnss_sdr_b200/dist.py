@@ -4,9 +4,9 @@ The two hot paths shard without any data-path exchange except ONE step (SURVEY 8
   * tracking: channels are independent given the IQ stream -> round-robin channel ownership;
     every rank that owns a channel on a band receives that band's samples (host fan-out or
     broadcast); taps go back to the owning host thread.  No collective.
-  * acquisition: the PRN x Doppler grid is split by PRN; each rank reduces its own rows to
-    (peak, index) and the global winner is an all-reduce(MAX) over a packed 64-bit key
-    (IEEE-754 bits of a non-negative float are order-preserving as unsigned integers).
+  * acquisition: the PRN x Doppler grid is split by PRN; each rank reduces its own sweep to one
+    16-byte (statistic, PRN, Doppler bin, code phase) record on the device and the ranks
+    all-gather the records; ties resolve like the reference's scans (best_peak).
 The reference has no counterpart (multi-GPU there = cudaSetDevice(rand() % n),
 src/algorithms/tracking/libs/cuda_multicorrelator.cu:153-154).
 """
@@ -24,36 +24,35 @@ def owner_of(item: int, world: int) -> int:
     return item % world
 
 
-def pack_peak_key(peak, prn, index_doppler, index_time) -> np.ndarray:
-    """(float32 peak >= 0, prn < 256, doppler bin < 256... up to 4095, code phase < 2^20) -> int64 key.
-    Layout: [63..32] float bits | [31..24] prn | [23..... split below].
-    Bits: peak 32 | prn 8 | doppler bin 9 | index_time 15 = 64."""
-    peak = np.asarray(peak, np.float32)
-    assert np.all(peak >= 0)
-    bits = peak.view(np.uint32).astype(np.uint64)
-    prn = np.asarray(prn, np.uint64)
-    d = np.asarray(index_doppler, np.uint64)
-    t = np.asarray(index_time, np.uint64)
-    assert np.all(prn < 256) and np.all(d < 512) and np.all(t < 32768)
-    key = (bits << np.uint64(32)) | (prn << np.uint64(24)) | (d << np.uint64(15)) | t
-    return key.astype(np.uint64).view(np.int64)   # top bit is the float sign bit = 0, so int64 order == uint64 order
+PEAK_DTYPE = np.dtype([("test_statistics", "<f4"), ("prn", "<u4"), ("index_doppler", "<u4"), ("index_time", "<u4")])  # b200_acq_peak
 
 
-def unpack_peak_key(key):
-    k = np.asarray(key, np.int64).view(np.uint64)
-    peak = (k >> np.uint64(32)).astype(np.uint32).view(np.float32)
-    prn = ((k >> np.uint64(24)) & np.uint64(0xFF)).astype(np.int64)
-    d = ((k >> np.uint64(15)) & np.uint64(0x1FF)).astype(np.int64)
-    t = (k & np.uint64(0x7FFF)).astype(np.int64)
-    return peak, prn, d, t
+def best_peak(records: np.ndarray) -> np.ndarray:
+    """Winner among per-rank b200_acq_peak records: the largest statistic; among equals the lowest PRN, then the lowest
+    Doppler bin, then the lowest code phase - the order in which the reference's strict '>' scans keep the first maximum
+    (pcps_acquisition.cc:417-426), so a multi-GPU search returns what a single-GPU search returns.  Records with prn == 0
+    (a rank that searched nothing) never win."""
+    r = np.asarray(records).view(PEAK_DTYPE).reshape(-1)
+    valid = r[r["prn"] > 0]
+    if valid.size == 0:
+        return np.zeros(1, PEAK_DTYPE)[0]
+    order = np.lexsort((valid["index_time"], valid["index_doppler"], valid["prn"], -valid["test_statistics"].astype(np.float64)))
+    return valid[order[0]]
 
 
-def allreduce_best_peak(local_key_tensor):
-    """In-place MAX all-reduce of an int64 tensor of packed keys (any shape).  One collective."""
+def allgather_peaks(local_peak):
+    """One all-gather of the ranks' 16-byte b200_acq_peak records (torch uint8/int32 tensor of 16 bytes on this rank's
+    device, written by b200_acq_sweep_best_dev).  Returns a (world, 4) int32 tensor on the same device - the only
+    exchange of the PRN-sharded acquisition.  Unlike a MAX all-reduce over a packed 64-bit key this has
+    room for any code-phase index (two-level FFT sizes exceed 2^15) and leaves the tie-breaking to best_peak()."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(local_key_tensor, op=dist.ReduceOp.MAX)
-    return local_key_tensor
+    t = local_peak.view(torch.int32).reshape(1, 4)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t.clone()
+    out = torch.empty((dist.get_world_size(), 4), dtype=torch.int32, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    return out
 
 
 def gather_results(local_results: np.ndarray, slots_owned: list, n_slots: int, device=None) -> np.ndarray:

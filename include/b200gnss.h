@@ -104,6 +104,12 @@ extern "C"
      * first_index; n_samples need not be a power of two (no wrap). */
     int b200_iq_attach_dev(b200_engine* e, int band, const b200_cf32* dev, uint64_t n_samples, uint64_t first_index);
 
+    /* Refill an attached band from host memory: host[0..n) becomes samples first_index .. first_index + n of the band
+     * (asynchronous H2D on the copy stream, ordered before later launches like b200_iq_push).  For hosts that own the
+     * device buffer because something else also touches it - e.g. rank 0 of a multi-GPU receiver pushes the band once
+     * and NCCL broadcasts that buffer to the peers over NVLink (bench.py). */
+    int b200_iq_refill(b200_engine* e, int band, const b200_cf32* host, uint64_t n, uint64_t first_index);
+
     /* ---- tracking: single correlator, 1:1 with Cpu_Multicorrelator_Real_Codes ----------- */
     /* src/algorithms/tracking/libs/cpu_multicorrelator_real_codes.h:37-61 */
     /* init(max_signal_length_samples, n_correlators)                       (.cc:35-50) */
@@ -359,6 +365,20 @@ extern "C"
     /* same with the input already on the device and results left on the device (asynchronous) */
     int b200_acq_search_dev(b200_acq* a, const b200_cf32* in_dev, const uint32_t* slots_host, uint32_t n_slots,
         uint32_t dwell_counter, b200_acq_result* results_dev);
+    /* Multi-GPU cold start: the PRN x Doppler grid is sharded by PRN; each rank reduces its sweep to ONE
+     * 16-byte record on the device and the ranks exchange the records (an all-gather of N x 16 bytes over NVLink; the
+     * host or a peer then takes the best, ties to the lowest PRN / bin / code phase as the reference's strict '>' scans).
+     * results_dev: what b200_acq_search_dev left on the device; prn_of_result_dev[i] = PRN searched in results_dev[i].
+     * Asynchronous on the acquisition object's stream; no host synchronisation (CUDA-graph capturable). */
+    typedef struct b200_acq_peak
+    {
+        float test_statistics;
+        uint32_t prn;
+        uint32_t index_doppler;
+        uint32_t index_time;
+    } b200_acq_peak;
+    int b200_acq_sweep_best_dev(b200_acq* a, const b200_acq_result* results_dev, const uint32_t* prn_of_result_dev, uint32_t n_results,
+        b200_acq_peak* peak_dev);
     /* d_magnitude_grid of one slot (bins x effective_fft_size floats); needs keep_grid or max_dwells>1.
      * Replaces the grid copy in doppler_grid (:555-558) / dump_results (:354-406). */
     int b200_acq_read_grid(b200_acq* a, uint32_t slot, float* grid_host);

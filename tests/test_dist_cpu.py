@@ -30,13 +30,16 @@ truth["grid_maximum"] = rng.uniform(1, 1e9, n_prn).astype(np.float32)
 truth["index_time"] = rng.integers(0, 25000, n_prn)
 truth["index_doppler"] = rng.integers(0, 81, n_prn)
 local = truth[owned]
-keys = bd.pack_peak_key(local["grid_maximum"], np.array(owned) + 1, local["index_doppler"], local["index_time"])
-best = torch.tensor([keys.max()], dtype=torch.int64)
-bd.allreduce_best_peak(best)
-peak, prn, d, t = bd.unpack_peak_key(best.numpy())
+# what b200_acq_sweep_best_dev leaves on each rank: its own best record
+mine = np.zeros(1, bd.PEAK_DTYPE)
+k = int(np.argmax(local["grid_maximum"]))
+mine[0] = (local["grid_maximum"][k], owned[k] + 1, local["index_doppler"][k], local["index_time"][k])
+allp = bd.allgather_peaks(torch.from_numpy(mine.view(np.int32).copy()))
+assert tuple(allp.shape) == (world, 4)
+best = bd.best_peak(allp.numpy().view(bd.PEAK_DTYPE))
 w = int(np.argmax(truth["grid_maximum"]))
-assert int(prn[0]) == w + 1 and int(d[0]) == int(truth["index_doppler"][w]) and int(t[0]) == int(truth["index_time"][w])
-assert peak[0] == truth["grid_maximum"][w]
+assert int(best["prn"]) == w + 1 and int(best["index_doppler"]) == int(truth["index_doppler"][w]) and int(best["index_time"]) == int(truth["index_time"][w])
+assert best["test_statistics"] == truth["grid_maximum"][w]
 full = bd.gather_results(local, owned, n_prn)
 assert np.array_equal(full, truth)
 # band fan-out: rank 0 holds the IQ block, everybody ends up with it
@@ -69,10 +72,18 @@ def test_gloo_world2_sharding_and_peak_allreduce(tmp_path):
     assert "DIST_OK" in r.stdout
 
 
-def test_key_order_preserving():
+def test_best_peak_breaks_ties_like_the_reference_scan():
+    """Equal statistics: the lowest PRN wins, then the lowest Doppler bin, then the lowest code phase (the reference's
+    strict '>' keeps the first maximum); code phases beyond 2^15 (two-level FFT sizes) survive the exchange."""
     from gnss_sdr_b200 import dist as bd
-    peaks = np.array([0.0, 1e-30, 1.0, 1.0000001, 3.5e9, 3.4e38], np.float32)
-    keys = bd.pack_peak_key(peaks, [1] * 6, [0] * 6, [0] * 6)
-    assert np.all(np.diff(keys) > 0)
-    p, prn, d, t = bd.unpack_peak_key(bd.pack_peak_key([2.5], [17], [80], [24999]))
-    assert (p[0], prn[0], d[0], t[0]) == (2.5, 17, 80, 24999)
+    r = np.zeros(5, bd.PEAK_DTYPE)
+    r[0] = (7.5, 9, 40, 199999)
+    r[1] = (7.5, 4, 41, 5)
+    r[2] = (7.5, 4, 40, 120000)
+    r[3] = (7.5, 4, 40, 119999)
+    r[4] = (9.0, 0, 0, 0)          # a rank that searched nothing
+    b = bd.best_peak(r)
+    assert (int(b["prn"]), int(b["index_doppler"]), int(b["index_time"])) == (4, 40, 119999)
+    r[0]["test_statistics"] = 7.6
+    b = bd.best_peak(r)
+    assert int(b["prn"]) == 9 and int(b["index_time"]) == 199999
