@@ -783,21 +783,35 @@ extern "C"
                     [&](int a, int b) { return items_host[a].sample_index < items_host[b].sample_index; });
                 for (int i = 0; i < n_items; i++) sl->items_pin[i] = items_host[sl->perm[i]];
             }
-        // The work items travel on the COPY stream, queued behind the sample pushes made so far, and the compute
-        // stream waits on an event.  Issued on the compute stream instead, this small host->device copy sits in
-        // the copy engine's queue until the previous batch's kernel has finished and holds up every sample
-        // push queued behind it (measured: 41.7 instead of 54.6 GB/s of sustained host->device traffic).
-        B200_CUDA_TRY(cudaMemcpyAsync(sl->items_dev, sl->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->copy_stream));
-        B200_CUDA_TRY(cudaEventRecord(sl->items_ready, e->copy_stream));
-        B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl->items_ready, 0));
         // few items: split epochs into slices so the whole chip works on them
         int slices = 1;
         if (n_items < 592) slices = (592 + n_items - 1) / n_items;
         if (slices > 64) slices = 64;
-        const int rc = batch_dev_impl(e, sl->items_dev, n_items, reinterpret_cast<b200_cf32*>(sl->out_dev), out_stride, slices);
-        if (rc) return rc;
-        B200_CUDA_TRY(cudaMemcpyAsync(sl->out_pin, sl->out_dev, sizeof(float2) * n_items * out_stride, cudaMemcpyDeviceToHost, e->stream));
-        B200_CUDA_TRY(cudaEventRecord(sl->done, e->stream));
+        // Latency path (a handful of channels waiting for their taps, e.g. the block threads behind the coalescer): the
+        // kernel reads the work items straight from the pinned host buffer and writes the taps straight into pinned host
+        // memory (unified addressing: cudaMallocHost memory is device-accessible at the same address), so the submission
+        // is one launch + one event instead of two copies through the copy engine, two events and a stream hop.
+        sl->zero_copy = n_items <= 1024;
+        if (sl->zero_copy)
+            {
+                const int rc = batch_dev_impl(e, sl->items_pin, n_items, reinterpret_cast<b200_cf32*>(sl->out_pin), out_stride, slices);
+                if (rc) return rc;
+                B200_CUDA_TRY(cudaEventRecord(sl->done, e->stream));
+            }
+        else
+            {
+                // The work items travel on the COPY stream, queued behind the sample pushes made so far, and the compute
+                // stream waits on an event.  Issued on the compute stream instead, this small host->device copy sits in
+                // the copy engine's queue until the previous batch's kernel has finished and holds up every sample
+                // push queued behind it (measured: 41.7 instead of 54.6 GB/s of sustained host->device traffic).
+                B200_CUDA_TRY(cudaMemcpyAsync(sl->items_dev, sl->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->copy_stream));
+                B200_CUDA_TRY(cudaEventRecord(sl->items_ready, e->copy_stream));
+                B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl->items_ready, 0));
+                const int rc = batch_dev_impl(e, sl->items_dev, n_items, reinterpret_cast<b200_cf32*>(sl->out_dev), out_stride, slices);
+                if (rc) return rc;
+                B200_CUDA_TRY(cudaMemcpyAsync(sl->out_pin, sl->out_dev, sizeof(float2) * n_items * out_stride, cudaMemcpyDeviceToHost, e->stream));
+                B200_CUDA_TRY(cudaEventRecord(sl->done, e->stream));
+            }
         sl->ticket = e->next_ticket++;
         *ticket = sl->ticket;
         guard.keep = true;

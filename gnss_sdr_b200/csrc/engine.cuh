@@ -85,6 +85,7 @@ struct b200_engine
         cudaEvent_t done{nullptr};
         cudaEvent_t items_ready{nullptr};  // work items have arrived (copy stream)
         bool busy{false};
+        bool zero_copy{false};  // items read from / taps written to the pinned host buffers directly (small batches)
         uint64_t ticket{0};
         std::vector<int> perm;  // results k belong to the caller's item perm[k] (empty = identity)
     };

@@ -410,19 +410,27 @@ __global__ void trk_loop_cycle_kernel(LoopDev* loops, int n_loops, int mode, Loo
             items[i] = it;
         }
 }
-// Persistent free-running tracker: one CTA per loop runs epoch after epoch without leaving the SM - prepare
-// (thread 0) -> correlate vector_length samples (all threads, the batch kernel's per-item code with slices = 1,
-// so taps are bit-identical to b200_trk_batch_dev(..., slices = 1)) -> loop update + dump record (thread 0).
-// Loops are independent, so there is no grid-wide dependency and no launch per epoch; a CTA ends when its loop
-// has run max_epochs cycles, loses lock, or finds its next vector_length samples not resident (stall).
-__global__ void __launch_bounds__(kTrkThreads) trk_loop_persistent_kernel(LoopDev* loops, int n_loops, int max_epochs, LoopAvail avail,
+// Persistent free-running tracker: one CTA per loop runs epoch after epoch without leaving the SM - loop update of the
+// previous epoch + prepare of the next (thread 0, one serial section, one barrier) -> correlate vector_length samples (all
+// kLoopThreads threads with the batch kernel's per-item templates, slices = 1).  Loops are independent, so there is no
+// grid-wide dependency and no launch per epoch; a CTA ends when its loop has run max_epochs cycles, loses lock, or
+// finds its next vector_length samples not resident (stall).
+// Each channel is a latency chain (epoch k+1's NCO commands need epoch k's taps): the correlation part shrinks with the
+// CTA size, so the CTA is as wide as the register budget of the correlation templates allows (round 1: 256 threads,
+// 10.7 us per epoch with 32 of 148 SMs busy and most cycles spent at the barrier around thread 0's update).
+#ifndef B200_LOOP_THREADS
+#define B200_LOOP_THREADS 1024
+#endif
+constexpr int kLoopThreads = B200_LOOP_THREADS;
+
+__global__ void __launch_bounds__(kLoopThreads) trk_loop_persistent_kernel(LoopDev* loops, int n_loops, int max_epochs, LoopAvail avail,
     const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, unsigned int* records, int rec_capacity, int* n_records,
     int tbl_cap)
 {
     extern __shared__ __align__(16) float smem[];
     float* smem_tbl = smem;
     float2* smem_red = reinterpret_cast<float2*>(smem + tbl_cap);
-    LoopDev* sL = reinterpret_cast<LoopDev*>(smem_red + (kTrkThreads / 32) * B200_MAX_TAPS);
+    LoopDev* sL = reinterpret_cast<LoopDev*>(smem_red + (kLoopThreads / 32) * B200_MAX_TAPS);
     __shared__ b200_trk_item s_item;
     __shared__ int s_go;
     __shared__ int s_tbl_cache[2];  // chip-index window held in smem_tbl (process_item<.., REUSE>)
@@ -433,7 +441,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_loop_persistent_kernel(LoopDe
     {
         const unsigned int* src = reinterpret_cast<const unsigned int*>(loops + i);
         unsigned int* dst = reinterpret_cast<unsigned int*>(sL);
-        for (int w = tid; w < static_cast<int>(sizeof(LoopDev) / 4); w += kTrkThreads) dst[w] = src[w];
+        for (int w = tid; w < static_cast<int>(sizeof(LoopDev) / 4); w += kLoopThreads) dst[w] = src[w];
         if (tid == 0) s_tbl_cache[0] = s_tbl_cache[1] = 0;
     }
     __syncthreads();
@@ -442,41 +450,47 @@ __global__ void __launch_bounds__(kTrkThreads) trk_loop_persistent_kernel(LoopDe
     const int taps = sL->taps;
     const unsigned long long lo = avail.lo[sL->band & 15], hi = avail.hi[sL->band & 15];
     int k_rec = 0;
+    bool have_taps = false;
+    float2 t[B200_MAX_TAPS];
 
-    for (int k = 0; k < max_epochs; k++)
+    for (int k = 0; k <= max_epochs; k++)
         {
             if (tid == 0)
                 {
-                    b200_trk_item it;
-                    // in state 2 preparing is a pure function of the state, so an item left pending by the
-                    // per-launch path is simply recomputed
-                    s_go = loop_prepare(*sL, it, true, lo, hi) ? 1 : 0;
-                    s_item = it;
+                    if (have_taps)
+                        {
+                            unsigned int* rec = nullptr;
+                            if (records && k_rec < rec_capacity) rec = records + (static_cast<size_t>(i) * rec_capacity + k_rec) * kLoopRecordWords;
+                            if (loop_update(*sL, t, rec)) k_rec++;
+                        }
+                    int go = 0;
+                    if (k < max_epochs)
+                        {
+                            b200_trk_item it;
+                            // in state 2 preparing is a pure function of the state, so an item left pending by the
+                            // per-launch path is simply recomputed
+                            go = loop_prepare(*sL, it, true, lo, hi) ? 1 : 0;
+                            s_item = it;
+                        }
+                    s_go = go;
                 }
             __syncthreads();
             if (!s_go) break;
-            float2 t[B200_MAX_TAPS];
             if (taps == 3)
                 {
                     float2 r[3];
-                    process_item<3, true>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r, s_tbl_cache);
+                    process_item<3, true, kLoopThreads>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r, s_tbl_cache);
 #pragma unroll
                     for (int q = 0; q < 3; q++) t[q] = r[q];
                 }
             else
                 {
                     float2 r[5];
-                    process_item<5, true>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r, s_tbl_cache);
+                    process_item<5, true, kLoopThreads>(s_item, ch, bd, smem_tbl, tbl_cap, smem_red, 0, 1, r, s_tbl_cache);
 #pragma unroll
                     for (int q = 0; q < 5; q++) t[q] = r[q];
                 }
-            if (tid == 0)
-                {
-                    unsigned int* rec = nullptr;
-                    if (records && k_rec < rec_capacity) rec = records + (static_cast<size_t>(i) * rec_capacity + k_rec) * kLoopRecordWords;
-                    if (loop_update(*sL, t, rec)) k_rec++;
-                }
-            __syncthreads();
+            have_taps = true;
         }
     __syncthreads();
     if (tid == 0) sL->pending = 0;
@@ -484,7 +498,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_loop_persistent_kernel(LoopDe
     {
         unsigned int* dst = reinterpret_cast<unsigned int*>(loops + i);
         const unsigned int* src = reinterpret_cast<const unsigned int*>(sL);
-        for (int w = tid; w < static_cast<int>(sizeof(LoopDev) / 4); w += kTrkThreads) dst[w] = src[w];
+        for (int w = tid; w < static_cast<int>(sizeof(LoopDev) / 4); w += kLoopThreads) dst[w] = src[w];
     }
     if (tid == 0 && n_records) n_records[i] = k_rec;
 }
@@ -498,7 +512,7 @@ int launch_loop_persistent(LoopDev* loops, int n_loops, int max_epochs, const Lo
     const int cap_limit = (200 * 1024 - 4096) / 4;
     if (tbl_cap > cap_limit) tbl_cap = cap_limit;
     tbl_cap = (tbl_cap + 3) & ~3;
-    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kTrkThreads / 32) * B200_MAX_TAPS * sizeof(float2) + sizeof(LoopDev);
+    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kLoopThreads / 32) * B200_MAX_TAPS * sizeof(float2) + sizeof(LoopDev);
     static DeviceOnce once;
     const int once_dev = once.begin();
     if (once_dev >= 0)
@@ -506,7 +520,7 @@ int launch_loop_persistent(LoopDev* loops, int n_loops, int max_epochs, const Lo
             B200_CUDA_TRY(cudaFuncSetAttribute(trk_loop_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             once.done(once_dev);
         }
-    trk_loop_persistent_kernel<<<n_loops, kTrkThreads, smem_bytes, st>>>(loops, n_loops, max_epochs, avail, chans, bands, records, rec_capacity,
+    trk_loop_persistent_kernel<<<n_loops, kLoopThreads, smem_bytes, st>>>(loops, n_loops, max_epochs, avail, chans, bands, records, rec_capacity,
         n_records, tbl_cap);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;

@@ -55,21 +55,22 @@ __device__ __forceinline__ void accumulate_sample(float2 x, float2 z, float m, c
         }
 }
 
-template <int TAPS, class Lookup>
+template <int TAPS, class Lookup, int THREADS = kTrkThreads>
 __device__ __forceinline__ void correlate_range(const ItemCtx& cx, const float (&shifts)[TAPS], const Lookup& lut,
     int tile_begin, int tile_end, int head, bool do_remainder, int n_main_end, float2 (&acc)[TAPS])
 {
+    constexpr int kTile = 2 * THREADS;  // samples per CTA iteration (one LDG.128 per thread)
     const int tid = threadIdx.x;
     float aux2[TAPS];
 #pragma unroll
     for (int t = 0; t < TAPS; t++) aux2[t] = __fsub_rn(shifts[t], cx.rem);
 
     // ---- main tiles: all samples < body, 16-byte aligned pairs -------------------------------
-    const float2 D = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile));
+    const float2 D = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTile));
     for (int tg = tile_begin; tg < tile_end; tg += kTrkReseed)
         {
             const int tg_end = min(tg + kTrkReseed, tile_end);
-            int n0 = head + tg * kTrkTile + 2 * tid;
+            int n0 = head + tg * kTile + 2 * tid;
             float2 za = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0));
             float2 zb = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0 + 1));
             float nf = static_cast<float>(n0);
@@ -81,8 +82,8 @@ __device__ __forceinline__ void correlate_range(const ItemCtx& cx, const float (
                     accumulate_sample<TAPS>(make_float2(v.z, v.w), zb, __fmul_rn(cx.step, nf + 1.0f), aux2, lut, acc);
                     za = cmulf(za, D);
                     zb = cmulf(zb, D);
-                    n0 += kTrkTile;
-                    nf += static_cast<float>(kTrkTile);
+                    n0 += kTile;
+                    nf += static_cast<float>(kTile);
                 }
         }
 
@@ -90,7 +91,7 @@ __device__ __forceinline__ void correlate_range(const ItemCtx& cx, const float (
     if (do_remainder)
         {
             const int count = head + (cx.N - n_main_end);
-            for (int r = tid; r < count; r += kTrkThreads)
+            for (int r = tid; r < count; r += THREADS)
                 {
                     const int n = (r < head) ? 0 : n_main_end + (r - head);
                     const float2 x = ldg_stream8(cx.base + ((cx.s0 + static_cast<unsigned long long>(n)) & cx.mask));
@@ -120,10 +121,11 @@ __device__ __forceinline__ void correlate_range(const ItemCtx& cx, const float (
 // NOTE: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit rounding
 // modifiers and --fmad=false, which would change chip indices; the products step*n therefore use
 // the scalar __fmul_rn (never contracted) and only the additions are packed.
-template <int TAPS, bool WRAPS>
+template <int TAPS, bool WRAPS, int THREADS = kTrkThreads>
 __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const float (&shifts)[TAPS], unsigned int tbl_off,
     int tile_begin, int tile_end, int head, float2 (&acc)[TAPS])
 {
+    constexpr int kTile = 2 * THREADS;  // samples per CTA iteration (one LDG.128 per thread)
     const int tid = threadIdx.x;
     float2 aux2[TAPS];
 #pragma unroll
@@ -137,13 +139,13 @@ __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const fl
     for (int t = 0; t < TAPS; t++) are[t] = aim[t] = make_float2(0.f, 0.f);
 
     const float2 magic2 = make_float2(12582912.0f, 12582912.0f);
-    const float2 D = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile));
+    const float2 D = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTile));
     const float2 Dr2 = make_float2(D.x, D.x), Di2 = make_float2(D.y, D.y);
     // group-to-group phasor step: kTrkReseed tiles
-    const float2 G = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTrkTile * kTrkReseed));
+    const float2 G = phasor_from_turns(cx.DT * static_cast<unsigned long long>(kTile * kTrkReseed));
     const float2 Gr2 = make_float2(G.x, G.x), Gi2 = make_float2(G.y, G.y);
 
-    int n0 = head + tile_begin * kTrkTile + 2 * tid;
+    int n0 = head + tile_begin * kTile + 2 * tid;
     float2 zr2, zi2;   // phasors of the two samples at the start of the current group
     {
         const float2 za = phasor_from_turns(cx.T0 + cx.DT * static_cast<unsigned long long>(n0));
@@ -189,10 +191,10 @@ __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const fl
                     const float2 nzr = __ffma2_rn(zr, Dr2, make_float2(-t1.x, -t1.y));
                     zi = __ffma2_rn(zr, Di2, __fmul2_rn(zi, Dr2));
                     zr = nzr;
-                    nfa += static_cast<float>(kTrkTile);
-                    nfb += static_cast<float>(kTrkTile);
-                    n0 += kTrkTile;
-                    ptr += kTrkTile;
+                    nfa += static_cast<float>(kTile);
+                    nfb += static_cast<float>(kTile);
+                    n0 += kTile;
+                    ptr += kTile;
                 }
             // group seed advances by G (few steps per epoch: error stays ~1e-7 per step)
             const float2 t2 = __fmul2_rn(zi2, Gi2);
@@ -212,7 +214,7 @@ __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const fl
 // integer-sample shifts of tap 0's resampled sequence; carrier has a phase-rate term that lags
 // one sample (..._high_dynamic_rotator_dot_prod_32fc_xn.h:92-103).  Not the throughput path:
 // one sample per thread per step, exact phasor per sample.
-template <int TAPS, class Lookup>
+template <int TAPS, class Lookup, int THREADS = kTrkThreads>
 __device__ __forceinline__ void correlate_range_hd(const ItemCtx& cx, float rate, unsigned long long RT,
     const float (&shifts)[TAPS], const Lookup& lut, int n_begin, int n_end, float2 (&acc)[TAPS])
 {
@@ -226,7 +228,7 @@ __device__ __forceinline__ void correlate_range_hd(const ItemCtx& cx, float rate
             ss += static_cast<unsigned int>(static_cast<int>(round(static_cast<double>(__fdiv_rn(__fsub_rn(shifts[t], shifts[t - 1]), cx.step)))));
             shift_samples[t] = static_cast<int>(ss);
         }
-    for (int n = n_begin + threadIdx.x; n < n_end; n += kTrkThreads)
+    for (int n = n_begin + threadIdx.x; n < n_end; n += THREADS)
         {
             const float2 x = ldg_stream8(cx.base + ((cx.s0 + static_cast<unsigned long long>(n)) & cx.mask));
             // rate exponent: (n-1)^2 for n>=1 with the reference's uint32 wrap of k*k, as float
@@ -259,10 +261,11 @@ __device__ __forceinline__ void correlate_range_hd(const ItemCtx& cx, float rate
 
 // REUSE (persistent tracker: one CTA keeps serving the same channel): tbl_cache[0..1] = [begin, end) of the chip-index
 // window already staged in smem_tbl; an epoch whose window lies inside it skips the staging pass.
-template <int TAPS, bool REUSE = false>
+template <int TAPS, bool REUSE = false, int THREADS = kTrkThreads>
 __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const BandDesc& bd, float* smem_tbl,
     int tbl_cap, float2* smem_red, int slice, int slices, float2 (&result)[TAPS], int* tbl_cache = nullptr)
 {
+    constexpr int kTile = 2 * THREADS;  // samples per CTA iteration (one LDG.128 per thread)
     const int tid = threadIdx.x;
     ItemCtx cx;
     cx.base = bd.base;
@@ -290,14 +293,14 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
             const bool in_smem = L <= tbl_cap;
             if (in_smem)
                 {
-                    for (int j = tid; j < L; j += kTrkThreads) smem_tbl[j] = ch.code[j];
+                    for (int j = tid; j < L; j += THREADS) smem_tbl[j] = ch.code[j];
                 }
             __syncthreads();
             LookupMod lut{in_smem ? smem_tbl : ch.code, L};
             const unsigned long long RT = turns_from_rad(-static_cast<double>(it.phase_rate_step_rad));
             const int per = (cx.N + slices - 1) / slices;
             const int nb = min(cx.N, slice * per), ne = min(cx.N, nb + per);
-            correlate_range_hd<TAPS>(cx, it.code_phase_rate_step_chips, RT, shifts, lut, nb, ne, acc);
+            correlate_range_hd<TAPS, LookupMod, THREADS>(cx, it.code_phase_rate_step_chips, RT, shifts, lut, nb, ne, acc);
         }
     else
         {
@@ -330,8 +333,8 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
             const long long span = hi - lo + 5;
 
             const int head = static_cast<int>(cx.s0 & 1ULL);
-            const int ntiles = (cx.body > head) ? (cx.body - head) / kTrkTile : 0;
-            const int n_main_end = head + ntiles * kTrkTile;
+            const int ntiles = (cx.body > head) ? (cx.body - head) / kTile : 0;
+            const int n_main_end = head + ntiles * kTile;
             const int tb = static_cast<int>((static_cast<long long>(ntiles) * slice) / slices);
             const int te = static_cast<int>((static_cast<long long>(ntiles) * (slice + 1)) / slices);
             const bool rem_here = (slice == slices - 1);
@@ -361,8 +364,8 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
                     if (stage)
                         {
                             int r = mod_pos(base_i + tid, L);
-                            const int stride = kTrkThreads % L;
-                            for (int j = tid; j < span_st; j += kTrkThreads)
+                            const int stride = THREADS % L;
+                            for (int j = tid; j < span_st; j += THREADS)
                                 {
                                     smem_tbl[j] = ch.code[r];
                                     r += stride;
@@ -388,15 +391,15 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
                             // ring wrap inside the epoch? (uniform per item)
                             const bool wraps = ((cx.s0 & cx.mask) + static_cast<unsigned long long>(cx.N)) > cx.mask;
                             if (wraps)
-                                correlate_tiles_fast<TAPS, true>(cx, shifts, tbl_off, tb, te, head, acc);
+                                correlate_tiles_fast<TAPS, true, THREADS>(cx, shifts, tbl_off, tb, te, head, acc);
                             else
-                                correlate_tiles_fast<TAPS, false>(cx, shifts, tbl_off, tb, te, head, acc);
+                                correlate_tiles_fast<TAPS, false, THREADS>(cx, shifts, tbl_off, tb, te, head, acc);
                             // remainder samples only (no main tiles) through the scalar path
-                            correlate_range<TAPS>(cx, shifts, lut, 0, 0, head, rem_here, n_main_end, acc);
+                            correlate_range<TAPS, LookupExt, THREADS>(cx, shifts, lut, 0, 0, head, rem_here, n_main_end, acc);
                         }
                     else
                         {
-                            correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                            correlate_range<TAPS, LookupExt, THREADS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
                         }
                 }
             else
@@ -405,11 +408,11 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
                     if (REUSE && tid == 0) tbl_cache[1] = tbl_cache[0];  // smem_tbl no longer holds an extended window
                     if (in_smem)
                         {
-                            for (int j = tid; j < L; j += kTrkThreads) smem_tbl[j] = ch.code[j];
+                            for (int j = tid; j < L; j += THREADS) smem_tbl[j] = ch.code[j];
                         }
                     __syncthreads();
                     LookupMod lut{in_smem ? smem_tbl : ch.code, L};
-                    correlate_range<TAPS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
+                    correlate_range<TAPS, LookupMod, THREADS>(cx, shifts, lut, tb, te, head, rem_here, n_main_end, acc);
                 }
         }
 
@@ -436,7 +439,7 @@ __device__ void process_item(const b200_trk_item& it, const ChanDesc& ch, const 
         {
             float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int w = 0; w < kTrkThreads / 32; w++)
+            for (int w = 0; w < THREADS / 32; w++)
                 {
                     const float2 p = smem_red[w * B200_MAX_TAPS + t];
                     s.x += p.x;

@@ -32,6 +32,22 @@ constexpr int kShTile = 512;     // samples per tile (4 KB)
 #define SH_MINB 3
 #endif
 constexpr int kShStages = SH_STAGES;
+// SH_STRESS (test builds only, tests/test_ring_stress_gpu.py): pseudo-random delays in the producer and in every consumer
+// warp, before the tile is read and before the slot is released, so that warps drift apart by several tiles and every
+// full/empty hand-over of the TMA ring is exercised with 2, 4 and 8 stages.
+#ifndef SH_STRESS
+#define SH_STRESS 0
+#endif
+#if SH_STRESS
+__device__ __forceinline__ void stress_delay(unsigned int salt)
+{
+    unsigned int h = salt * 2654435761u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    if ((h & 3u) == 0u) __nanosleep(100u + ((h >> 4) & 1023u));
+}
+#endif
 constexpr int kShTblCap = 1152;  // floats of warp-private code storage: whole-epoch table when it fits ...
 constexpr int kShWin = 256;      // ... else two 256-entry windows (double-buffered, refilled per tile with cp.async)
 constexpr int kShThreads = (kShK + 1) * 32;
@@ -268,6 +284,9 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
                             const int s = t % kShStages;
                             const unsigned int par = static_cast<unsigned int>((t / kShStages) & 1);
                             mbar_wait(&sm.empty[s], par ^ 1u);
+#if SH_STRESS
+                            stress_delay(static_cast<unsigned int>(t) * 31u + blockIdx.x * 7u + 3u);
+#endif
                             unsigned long long src = hull_start + static_cast<unsigned long long>(t) * kShTile;
                             unsigned int n1 = kShTile, n2 = 0;
                             if (ring)
@@ -466,11 +485,18 @@ __global__ void __launch_bounds__(kShThreads, SH_MINB) trk_shared_kernel(const b
             // otherwise arrive twice on empty[s] within one phase and let the producer overwrite a slot
             // that a slower warp is still reading.
             mbar_wait(&sm.full[s], par);
+#if SH_STRESS
+            stress_delay(static_cast<unsigned int>(t) * 17u + static_cast<unsigned int>(warp) * 101u + blockIdx.x * 13u);
+#endif
             if (table_path && t >= t_first && t < t_last)
                 {
                     const SmemTileLoader ld{reinterpret_cast<const float4*>(&sm.tiles[s][0]) + lane};
                     process_tile(t, ld);
                 }
+#if SH_STRESS
+            stress_delay(static_cast<unsigned int>(t) * 29u + static_cast<unsigned int>(warp) * 53u + blockIdx.x * 5u + 1u);
+            __syncwarp();
+#endif
             if (lane == 0) mbar_arrive(&sm.empty[s]);
         }
     if (!sm.share && table_path)

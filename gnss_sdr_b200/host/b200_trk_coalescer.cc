@@ -8,6 +8,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define B200_CPU_RELAX() _mm_pause()
+#else
+#define B200_CPU_RELAX() std::this_thread::yield()
+#endif
 
 namespace b200
 {
@@ -26,8 +32,9 @@ Trk_Coalescer* Trk_Coalescer::instance()
 }
 
 
-Trk_Coalescer::Trk_Coalescer(b200_engine* engine) : d_engine(engine)
+Trk_Coalescer::Trk_Coalescer(b200_engine* engine) : d_engine(engine), d_slots(new Slot[kMaxChannels])
 {
+    for (auto& w : d_band_written) w.store(0);
     if (const char* env = std::getenv("B200_COALESCE_WINDOW_US")) d_window_us = std::atoi(env);
     d_thread = std::thread([this] { tick_loop(); });
 }
@@ -35,21 +42,18 @@ Trk_Coalescer::Trk_Coalescer(b200_engine* engine) : d_engine(engine)
 
 Trk_Coalescer::~Trk_Coalescer()
 {
-    {
-        std::lock_guard<std::mutex> lk(d_mu);
-        d_stop = true;
-    }
-    d_cv_tick.notify_all();
-    d_cv_done.notify_all();
-    d_cv_space.notify_all();
+    d_stop.store(true);
+    d_posted.fetch_add(1);  // wake the tick thread
+    d_posted.notify_all();
+    for (int b = 0; b < kMaxBands; b++) d_cv_space[b].notify_all();
     if (d_thread.joinable()) d_thread.join();
 }
 
 
 bool Trk_Coalescer::ensure_band(int band, uint64_t capacity_samples)
 {
-    if (band < 0 || band >= 16) return false;
-    std::lock_guard<std::mutex> lk(d_mu);
+    if (band < 0 || band >= kMaxBands) return false;
+    std::lock_guard<std::mutex> lk(d_admin_mu);
     if (d_band_capacity[band] != 0) return true;
     if (capacity_samples == 0)
         {
@@ -70,7 +74,7 @@ bool Trk_Coalescer::ensure_band(int band, uint64_t capacity_samples)
 
 Trk_Coalescer::Slot* Trk_Coalescer::slot_of(int id)
 {
-    if (id < 0 || id >= static_cast<int>(d_slots.size()) || d_slots[id].state == FREE) return nullptr;
+    if (id < 0 || id >= kMaxChannels || d_slots[id].state.load(std::memory_order_acquire) == FREE) return nullptr;
     return &d_slots[id];
 }
 
@@ -79,42 +83,53 @@ int Trk_Coalescer::open_channel(int band, int n_correlators)
 {
     if (!ensure_band(band)) return -1;
     int id = -1;
-    if (b200_trk_channel_create(d_engine, band, n_correlators, &id) != B200_OK)
+    if (b200_trk_channel_create(d_engine, band, n_correlators, &id) != B200_OK || id >= kMaxChannels)
         {
-            std::snprintf(d_error, sizeof(d_error), "%s", b200_last_error());
+            std::snprintf(d_error, sizeof(d_error), "%s", id >= kMaxChannels ? "more than 4096 channels" : b200_last_error());
             return -1;
         }
-    std::lock_guard<std::mutex> lk(d_mu);
-    if (id >= static_cast<int>(d_slots.size())) d_slots.resize(id + 1);
+    std::lock_guard<std::mutex> lk(d_admin_mu);
     Slot& s = d_slots[id];
-    s = Slot();
-    s.chan = id;
     s.band = band;
     s.taps = n_correlators;
-    s.state = IDLE;
+    s.active.store(false);
+    s.cursor.store(0);
+    s.state.store(IDLE, std::memory_order_release);
+    if (id + 1 > d_n_slots.load()) d_n_slots.store(id + 1);
     return id;
+}
+
+
+void Trk_Coalescer::idle(int id)
+{
+    Slot* s = slot_of(id);
+    if (s == nullptr) return;
+    if (s->active.exchange(false)) d_n_active.fetch_sub(1);
+    d_cv_space[s->band].notify_all();
+    d_posted.notify_all();  // the tick thread re-evaluates how many posts it is waiting for
 }
 
 
 void Trk_Coalescer::close_channel(int id)
 {
-    std::unique_lock<std::mutex> lk(d_mu);
     Slot* s = slot_of(id);
     if (s == nullptr) return;
     // an epoch still in flight finishes first (its result is dropped)
-    d_cv_done.wait(lk, [&] { return d_stop || (s->state != POSTED && s->state != IN_FLIGHT); });
-    s->active = false;
-    s->state = IDLE;  // engine channel ids are never reused; the slot just goes quiet
-    d_cv_space.notify_all();
+    for (;;)
+        {
+            const int st = s->state.load(std::memory_order_acquire);
+            if (st != POSTED && st != IN_FLIGHT) break;
+            if (d_stop.load()) break;
+            s->state.wait(st);
+        }
+    idle(id);
+    s->state.store(IDLE);  // engine channel ids are never reused; the slot just goes quiet
 }
 
 
 bool Trk_Coalescer::set_code(int id, int code_length_chips, const float* code, const float* shifts_chips, bool high_dynamics)
 {
-    {
-        std::lock_guard<std::mutex> lk(d_mu);
-        if (slot_of(id) == nullptr) return false;
-    }
+    if (slot_of(id) == nullptr) return false;
     return b200_trk_channel_set_code(d_engine, id, code_length_chips, code, shifts_chips, high_dynamics ? 1 : 0) == B200_OK;
 }
 
@@ -125,65 +140,75 @@ bool Trk_Coalescer::set_taps(int id, const float* shifts_chips)
 }
 
 
-void Trk_Coalescer::idle(int id)
+// would [abs_index, abs_index + n) still leave the oldest sample an active channel of this band needs in the ring?
+bool Trk_Coalescer::fits(int band, uint64_t abs_index, uint64_t n) const
 {
-    std::lock_guard<std::mutex> lk(d_mu);
-    Slot* s = slot_of(id);
-    if (s == nullptr) return;
-    s->active = false;
-    d_cv_space.notify_all();
-    d_cv_tick.notify_all();
+    const uint64_t cap = d_band_capacity[band];
+    uint64_t oldest = abs_index;
+    const int ns = d_n_slots.load(std::memory_order_acquire);
+    for (int i = 0; i < ns; i++)
+        {
+            const Slot& o = d_slots[i];
+            if (o.band == band && o.active.load(std::memory_order_relaxed))
+                {
+                    const uint64_t c = o.cursor.load(std::memory_order_relaxed);
+                    if (c < oldest) oldest = c;
+                }
+        }
+    return abs_index + n - oldest <= cap - cap / 8;
 }
 
 
 bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* samples, uint64_t n)
 {
-    int band;
-    {
-        std::unique_lock<std::mutex> lk(d_mu);
-        Slot* s = slot_of(id);
-        if (s == nullptr) return false;
-        band = s->band;
-        s->cursor = abs_index;
-        s->active = true;
-        d_cv_space.notify_all();
-        // back-pressure: never overwrite what a slower active channel of this band still needs
-        const uint64_t cap = d_band_capacity[band];
-        auto fits = [&] {
-            uint64_t oldest = abs_index;
-            for (const Slot& o : d_slots)
-                if (o.state != FREE && o.active && o.band == band && o.cursor < oldest) oldest = o.cursor;
-            return abs_index + n - oldest <= cap - cap / 8;
-        };
-        if (!fits())
-            {
-                // a channel that stopped calling (stalled test thread, block torn down without idle()) must not wedge the
-                // rest: after the timeout the laggards are declared idle
-                if (!d_cv_space.wait_for(lk, std::chrono::milliseconds(2000), [&] { return d_stop || fits(); }))
-                    {
-                        for (Slot& o : d_slots)
-                            if (o.state != FREE && o.active && o.band == band && abs_index + n - o.cursor > cap - cap / 8) o.active = false;
-                    }
-            }
-    }
+    Slot* s = slot_of(id);
+    if (s == nullptr) return false;
+    const int band = s->band;
+    s->cursor.store(abs_index, std::memory_order_relaxed);
+    if (!s->active.exchange(true)) d_n_active.fetch_add(1);
+    d_samples_offered.fetch_add(n, std::memory_order_relaxed);
+    // fast path: somebody has already put these samples into the band (every block of the flowgraph offers the same stream)
+    if (abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
+
+    std::unique_lock<std::mutex> lk(d_band_mu[band]);
+    if (abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
+    // back-pressure: never overwrite what a slower active channel of this band still needs.  A channel that stopped calling
+    // (stalled test thread, block torn down without idle()) must not wedge the rest: after the timeout laggards go idle.
+    if (!fits(band, abs_index, n))
+        {
+            if (!d_cv_space[band].wait_for(lk, std::chrono::milliseconds(2000), [&] { return d_stop.load() || fits(band, abs_index, n); }))
+                {
+                    const uint64_t cap = d_band_capacity[band];
+                    const int ns = d_n_slots.load();
+                    for (int i = 0; i < ns; i++)
+                        {
+                            Slot& o = d_slots[i];
+                            if (o.band == band && o.active.load() && abs_index + n - o.cursor.load() > cap - cap / 8)
+                                if (o.active.exchange(false)) d_n_active.fetch_sub(1);
+                        }
+                }
+        }
     uint64_t n_new = 0;
     const int rc = b200_iq_push_at(d_engine, band, abs_index, reinterpret_cast<const b200_cf32*>(samples), n, &n_new);
-    {
-        std::lock_guard<std::mutex> lk(d_mu);
-        d_stats.samples_offered += n;
-        d_stats.samples_copied += n_new;
-        if (rc != B200_OK) std::snprintf(d_error, sizeof(d_error), "%s", b200_last_error());
-    }
-    return rc == B200_OK;
+    if (rc != B200_OK)
+        {
+            std::snprintf(d_error, sizeof(d_error), "%s", b200_last_error());
+            return false;
+        }
+    d_samples_copied.fetch_add(n_new, std::memory_order_relaxed);
+    uint64_t w = d_band_written[band].load(std::memory_order_relaxed);
+    if (abs_index + n > w || abs_index > w) d_band_written[band].store(abs_index + n, std::memory_order_release);
+    return true;
 }
 
 
 bool Trk_Coalescer::post(int id, uint64_t abs_index, int n, float rem_carrier_phase_rad, float phase_step_rad, float phase_rate_step_rad,
     float rem_code_phase_chips, float code_phase_step_chips, float code_phase_rate_step_chips)
 {
-    std::lock_guard<std::mutex> lk(d_mu);
     Slot* s = slot_of(id);
-    if (s == nullptr || s->state == POSTED || s->state == IN_FLIGHT) return false;
+    if (s == nullptr) return false;
+    const int st = s->state.load(std::memory_order_acquire);
+    if (st == POSTED || st == IN_FLIGHT) return false;
     s->item.channel = id;
     s->item.n = n;
     s->item.sample_index = abs_index;
@@ -193,31 +218,46 @@ bool Trk_Coalescer::post(int id, uint64_t abs_index, int n, float rem_carrier_ph
     s->item.rem_code_phase_chips = rem_code_phase_chips;
     s->item.code_phase_step_chips = code_phase_step_chips;
     s->item.code_phase_rate_step_chips = code_phase_rate_step_chips;
-    s->state = POSTED;
-    s->active = true;
-    s->cursor = abs_index;
+    s->cursor.store(abs_index, std::memory_order_relaxed);
+    if (!s->active.exchange(true)) d_n_active.fetch_add(1);
     s->t_post = std::chrono::steady_clock::now();
-    d_posted++;
-    d_cv_tick.notify_one();
+    s->state.store(POSTED, std::memory_order_release);
+    // a slower channel may have been waiting for this cursor to move
+    d_cv_space[s->band].notify_all();
+    if (d_posted.fetch_add(1, std::memory_order_acq_rel) == 0) d_posted.notify_one();
     return true;
 }
 
 
 bool Trk_Coalescer::wait(int id, std::complex<float>* out)
 {
-    std::unique_lock<std::mutex> lk(d_mu);
     Slot* s = slot_of(id);
     if (s == nullptr) return false;
-    d_cv_done.wait(lk, [&] { return d_stop || s->state == DONE || s->state == FAILED || s->state == IDLE; });
-    const bool ok = s->state == DONE;
+    // spin briefly (the GPU round trip of a batch is tens of microseconds), then sleep on the slot's state word
+    int st;
+    int spins = 0;
+    for (;;)
+        {
+            st = s->state.load(std::memory_order_acquire);
+            if (st != POSTED && st != IN_FLIGHT) break;
+            if (d_stop.load(std::memory_order_relaxed)) return false;
+            if (++spins < 2000)
+                {
+                    B200_CPU_RELAX();
+                    continue;
+                }
+            s->state.wait(st, std::memory_order_acquire);
+        }
+    const bool ok = st == DONE;
     if (ok)
         {
             for (int k = 0; k < s->taps; k++) out[k] = s->out[k];
             const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - s->t_post).count();
+            std::lock_guard<std::mutex> lk(d_admin_mu);
             d_stats.sum_latency_us += us;
             d_stats.max_latency_us = std::max(d_stats.max_latency_us, us);
         }
-    if (s->state == DONE || s->state == FAILED) s->state = IDLE;
+    if (st == DONE || st == FAILED) s->state.store(IDLE, std::memory_order_release);
     return ok;
 }
 
@@ -227,85 +267,90 @@ void Trk_Coalescer::tick_loop()
     std::vector<b200_trk_item> items;
     std::vector<int> ids;
     std::vector<b200_cf32> taps;
-    std::unique_lock<std::mutex> lk(d_mu);
-    while (!d_stop)
+    while (!d_stop.load(std::memory_order_acquire))
         {
-            d_cv_tick.wait(lk, [&] { return d_stop || d_posted > 0; });
-            if (d_stop) break;
-            // everyone who took part in the previous batch and is still active is expected again; stragglers get
-            // d_window_us from the moment the first item of this batch was seen
+            // sleep until somebody posts
+            while (d_posted.load(std::memory_order_acquire) == 0 && !d_stop.load()) d_posted.wait(0, std::memory_order_acquire);
+            if (d_stop.load()) break;
+            // every active channel is expected to post; stragglers get d_window_us from the first post seen
             const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(d_window_us);
             bool expired = false;
-            for (;;)
+            while (d_posted.load(std::memory_order_acquire) < d_n_active.load(std::memory_order_acquire))
                 {
-                    int expected = 0;
-                    for (const Slot& s : d_slots)
-                        if (s.state != FREE && s.active) expected++;
-                    if (d_posted >= expected) break;
-                    if (d_cv_tick.wait_until(lk, deadline) == std::cv_status::timeout)
+                    if (std::chrono::steady_clock::now() >= deadline)
                         {
                             expired = true;
                             break;
                         }
-                    if (d_stop) return;
+                    B200_CPU_RELAX();
                 }
             items.clear();
             ids.clear();
-            for (Slot& s : d_slots)
-                if (s.state == POSTED)
-                    {
-                        items.push_back(s.item);
-                        ids.push_back(s.chan);
-                        s.state = IN_FLIGHT;
-                    }
-            d_posted = 0;
+            const int ns = d_n_slots.load(std::memory_order_acquire);
+            for (int i = 0; i < ns; i++)
+                {
+                    Slot& s = d_slots[i];
+                    int want = POSTED;
+                    if (s.state.load(std::memory_order_acquire) == POSTED && s.state.compare_exchange_strong(want, IN_FLIGHT))
+                        {
+                            items.push_back(s.item);
+                            ids.push_back(i);
+                        }
+                }
+            d_posted.fetch_sub(static_cast<int>(items.size()), std::memory_order_acq_rel);
             if (items.empty()) continue;
             if (expired)
                 {
-                    d_stats.window_expired++;
-                    // who did not make it is not waited for next time (it posts -> it is active again)
-                    for (Slot& s : d_slots)
-                        if (s.state != FREE && s.active && s.state != IN_FLIGHT) s.active = false;
+                    // who did not make it is not waited for next time (posting makes it active again)
+                    for (int i = 0; i < ns; i++)
+                        {
+                            Slot& s = d_slots[i];
+                            const int st = s.state.load();
+                            if (s.active.load() && st != IN_FLIGHT && st != POSTED)
+                                if (s.active.exchange(false)) d_n_active.fetch_sub(1);
+                        }
                 }
-            d_last_batch = static_cast<int>(items.size());
-            lk.unlock();
             const auto t0 = std::chrono::steady_clock::now();
             taps.resize(items.size() * B200_MAX_TAPS);
             uint64_t ticket = 0;
             int rc = b200_trk_submit(d_engine, items.data(), static_cast<int>(items.size()), B200_MAX_TAPS, &ticket);
             if (rc == B200_OK) rc = b200_trk_wait(d_engine, ticket, taps.data());
             const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-            lk.lock();
             if (rc != B200_OK) std::snprintf(d_error, sizeof(d_error), "%s", b200_last_error());
             for (size_t k = 0; k < ids.size(); k++)
                 {
                     Slot& s = d_slots[ids[k]];
                     if (rc == B200_OK)
-                        {
-                            for (int t = 0; t < s.taps; t++) s.out[t] = std::complex<float>(taps[k * B200_MAX_TAPS + t].re, taps[k * B200_MAX_TAPS + t].im);
-                            s.state = DONE;
-                        }
-                    else
-                        s.state = FAILED;
+                        for (int t = 0; t < s.taps; t++) s.out[t] = std::complex<float>(taps[k * B200_MAX_TAPS + t].re, taps[k * B200_MAX_TAPS + t].im);
+                    s.state.store(rc == B200_OK ? DONE : FAILED, std::memory_order_release);
+                    s.state.notify_all();
                 }
-            d_stats.batches++;
-            d_stats.items += items.size();
-            d_stats.sum_batch_us += us;
-            d_cv_done.notify_all();
+            {
+                std::lock_guard<std::mutex> lk(d_admin_mu);
+                d_stats.batches++;
+                d_stats.items += items.size();
+                d_stats.sum_batch_us += us;
+                if (expired) d_stats.window_expired++;
+            }
         }
 }
 
 
 Trk_Coalescer::Stats Trk_Coalescer::stats()
 {
-    std::lock_guard<std::mutex> lk(d_mu);
-    return d_stats;
+    std::lock_guard<std::mutex> lk(d_admin_mu);
+    Stats s = d_stats;
+    s.samples_copied = d_samples_copied.load();
+    s.samples_offered = d_samples_offered.load();
+    return s;
 }
 
 
 void Trk_Coalescer::reset_stats()
 {
-    std::lock_guard<std::mutex> lk(d_mu);
+    std::lock_guard<std::mutex> lk(d_admin_mu);
     d_stats = Stats();
+    d_samples_copied.store(0);
+    d_samples_offered.store(0);
 }
 }  // namespace b200

@@ -5,10 +5,14 @@
  * The reference runs one scheduler thread per tracking block and each calls its own correlator synchronously
  * once per code period (src/algorithms/tracking/gnuradio_blocks/dll_pll_veml_tracking.cc:1232-1257).  On a GPU
  * that is one copy + launch + synchronisation per channel and epoch.  Here the block threads post their work item
- * (channel, absolute sample index, the seven NCO scalars) and sleep; one tick thread turns whatever was posted
- * within a short window into ONE b200_trk_submit / b200_trk_wait pair against the shared IQ band and wakes the
- * posters with their taps.  The samples themselves are offered by every block (each has the same stream in its
+ * (channel, absolute sample index, the seven NCO scalars) and wait; one tick thread turns whatever was posted
+ * within a short window into ONE b200_trk_submit / b200_trk_wait pair against the shared IQ band and hands the
+ * posters their taps.  The samples themselves are offered by every block (each has the same stream in its
  * GNU Radio input buffer) and copied once (b200_iq_push_at).
+ *
+ * Synchronisation is per slot (one atomic state word per channel: the poster spins briefly, then sleeps on it;
+ * the tick thread never takes a lock on the hot path), because with 256 block threads a single mutex +
+ * condition variable costs more than the GPU round trip.
  *
  * Ring safety: a block that runs ahead may not overwrite samples a slower block still needs; push() blocks
  * while (newest offered index - oldest active cursor) would exceed the band's capacity (a flowgraph's upstream
@@ -23,7 +27,7 @@
 #include <complex>
 #include <condition_variable>
 #include <cstdint>
-#include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -44,6 +48,8 @@ public:
         uint64_t samples_copied{0};
         uint64_t samples_offered{0};
     };
+    static constexpr int kMaxChannels = 4096;
+    static constexpr int kMaxBands = 16;
 
     //! process-wide instance over b200::shared_engine(); nullptr when no GPU is usable
     static Trk_Coalescer* instance();
@@ -77,7 +83,7 @@ public:
     const char* last_error() const { return d_error; }
 
 private:
-    enum State
+    enum State : int
     {
         FREE = 0,
         IDLE,
@@ -86,32 +92,36 @@ private:
         DONE,
         FAILED
     };
-    struct Slot
+    struct alignas(64) Slot  // one cache line pair per channel: no false sharing between block threads
     {
-        int chan{-1};
+        std::atomic<int> state{FREE};
+        std::atomic<bool> active{false};
+        std::atomic<uint64_t> cursor{0};  // first sample the channel still needs
         int band{0};
         int taps{0};
-        State state{FREE};
-        bool active{false};
-        uint64_t cursor{0};  // first sample the channel still needs
         b200_trk_item item{};
         std::complex<float> out[B200_MAX_TAPS];
         std::chrono::steady_clock::time_point t_post;
     };
     void tick_loop();
     Slot* slot_of(int id);
+    bool fits(int band, uint64_t abs_index, uint64_t n) const;
 
     b200_engine* d_engine;
-    std::mutex d_mu;
-    std::condition_variable d_cv_tick, d_cv_done, d_cv_space;
-    std::deque<Slot> d_slots;  // indexed by engine channel id; a deque keeps references valid when channels are added
-    int d_posted{0};
-    int d_last_batch{1};
+    std::unique_ptr<Slot[]> d_slots;        // indexed by engine channel id; fixed size, never reallocated
+    std::atomic<int> d_n_slots{0};          // highest id in use + 1
+    std::atomic<int> d_posted{0};
+    std::atomic<int> d_n_active{0};
+    std::atomic<bool> d_stop{false};
+    std::atomic<uint64_t> d_band_written[kMaxBands];   // samples [.., written) are in the band (fast path of push)
+    uint64_t d_band_capacity[kMaxBands] = {0};
+    std::mutex d_band_mu[kMaxBands];        // one producer at a time per band (slow path of push)
+    std::condition_variable d_cv_space[kMaxBands];
+    std::mutex d_admin_mu;                  // open/close/ensure_band/stats
     int d_window_us{200};
-    bool d_stop{false};
     std::thread d_thread;
-    Stats d_stats;
-    uint64_t d_band_capacity[16] = {0};
+    Stats d_stats;                          // tick-thread fields; latency fields under d_admin_mu
+    std::atomic<uint64_t> d_samples_copied{0}, d_samples_offered{0};
     char d_error[256] = "";
 };
 }  // namespace b200

@@ -43,3 +43,4 @@ target_link_libraries(b200_blocks PUBLIC
     Volkgnsssdr::volkgnsssdr
 )
 target_compile_definitions(b200_blocks PUBLIC -DB200_GPU_ACCEL=1)
+target_compile_features(b200_blocks PUBLIC cxx_std_20)  # std::atomic wait/notify in the coalescer

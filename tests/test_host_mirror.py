@@ -12,7 +12,7 @@ EXE = os.path.join(ROOT, "tests", "host", "test_host_mirror")
 def build():
     libdir = os.path.join(ROOT, "gnss_sdr_b200")
     ref = os.path.join(ROOT, "oracle", "_ref", "liboracle_ref.so")
-    cmd = ["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "host", "test_host_mirror.cc"),
+    cmd = ["g++", "-std=c++20", "-O2", os.path.join(ROOT, "tests", "host", "test_host_mirror.cc"),
            os.path.join(libdir, "host", "b200_multicorrelator_real_codes.cc"),
            os.path.join(libdir, "host", "b200_trk_coalescer.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_core.cc"),
@@ -132,4 +132,4 @@ def test_class_interface_through_the_coalescer(threads, epochs):
     print(st)
     assert st["items_per_batch"] > threads / 4
     assert st["copy_ratio"] < 2.5 / threads
-    assert st["msamples_per_s"] > 1000.0  # more than real time for 32 channels at 25 Msps (800 Msamples/s)
+    assert st["msamples_per_s"] > 25.0 * threads  # faster than real time: `threads` channels at 25 Msps

