@@ -331,11 +331,28 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ s, int n, int M, 
 {
     const int m = M / R;
     const int nb = n / R;
+    // Butterfly i works on block b, offset j (pos0 = b M + j, elements pos0 + q m).  Consecutive threads normally take
+    // consecutive j: conflict-free while m >= 16.  In the late forward / early inverse stages m is small (5 for the
+    // M = 125 stage of 25 000 = 8 . 25 . 25 . 5) and consecutive threads would hop to the next block every m lanes, which
+    // put 2-3 lanes on the same bank (ncu, round 1: 2.7-way conflicts on 27 % of the shared wavefronts).  There the block
+    // length M is odd (the planner runs the even radices first), so 16 consecutive BLOCKS at the same offset j hit 16
+    // different bank pairs (M b mod 16 is a permutation): threads walk over b first.
+    const bool by_block = (m < 16) && (M & 1) && (m > 1);
+    const int nblk = by_block ? n / M : 1;
 #pragma unroll(R >= 16 ? 1 : 2)
     for (int i = threadIdx.x; i < nb; i += blockDim.x)
         {
-            const int b = fast_div(i, m, magic);
-            const int j = i - b * m;
+            int b, j;
+            if (by_block)
+                {
+                    j = i / nblk;
+                    b = i - j * nblk;
+                }
+            else
+                {
+                    b = fast_div(i, m, magic);
+                    j = i - b * m;
+                }
             const int pos0 = b * M + j;
             float2* p = s + pos0;
             float2 v[R];

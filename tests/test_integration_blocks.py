@@ -315,6 +315,48 @@ def test_b200_galileo_e1_pilot_veml_matches_reference(reflib, b200lib):
 
 
 @pytest.mark.gpu
+def test_b200_gps_l5_pilot_block_follows_reference_through_secondary_code_lock(reflib, b200lib):
+    """GPS L5 at 12 Msps with real L5I / L5Q codes (the reference's generators compiled in place), pilot tracking: three
+    taps on the L5Q replica, the NH20 secondary-code search, then the data prompt on the L5I replica with the NH10 code
+    removed, 10 ms symbols with I/Q interchanged.  Checked: both blocks find the secondary code at the same epoch and their
+    first symbols agree.  (Later symbols are not compared: on this synthetic signal the reference's own loop degrades after
+    the lock - C/N0 estimate 33 dB-Hz for a 48 dB-Hz signal - and two diverging loops amplify last-bit differences.)"""
+    rng = np.random.default_rng(31)
+    prn, fs = 6, 12_000_000
+    l5i = bi.code_table(reflib, "G", "5I", prn)
+    l5q = bi.code_table(reflib, "G", "5Q", prn)
+    nh10 = np.array([1.0 if c == "0" else -1.0 for c in "0000110101"])             # GPS_L5I_NH_CODE_STR (GPS_L5.h:171)
+    nh20 = np.array([1.0 if c == "0" else -1.0 for c in "00000100110101001110"])   # GPS_L5Q_NH_CODE_STR (:172)
+    data = rng.choice([-1.0, 1.0], 200)
+    sym_i = np.repeat(data, 10) * np.tile(nh10, len(data))   # one value per 1 ms code period
+    n = int(fs * 0.45)
+    delay = 4321
+    cp = (-delay * 10.23e6 / fs) % 10230
+    # make_iq's rate parameter is in table entries per C/A chip time: L5 runs 10 x faster
+    svs = [dict(prn="i", doppler=2100.0, code_phase_chips=cp, cn0=48.0, symbols=sym_i, periods_per_symbol=1),
+           dict(prn="q", doppler=2100.0, code_phase_chips=cp, cn0=48.0, symbols=nh20, periods_per_symbol=1, phase0=np.pi / 2)]
+    iq = make_iq({"i": l5i, "q": l5q}, float(fs), n, svs, seed=8, chips_per_table_chip=10.0)
+    conf = {"GNSS-SDR.internal_fs_sps": fs, "Tracking_L5.item_type": "gr_complex", "Tracking_L5.pll_bw_hz": 20.0, "Tracking_L5.dll_bw_hz": 1.5,
+            "Tracking_L5.early_late_space_chips": 0.5, "Tracking_L5.pull_in_time_s": 1, "Tracking_L5.track_pilot": True}
+    outs = {}
+    for name, lib, impl in [("ref", reflib, "GPS_L5_DLL_PLL_Tracking"), ("b200", b200lib, "GPS_L5_DLL_PLL_Tracking_B200")]:
+        ch = bi.Channel(lib, conf, "", impl, trk_role="Tracking_L5")
+        ch.set_satellite("G", "L5", prn)
+        ch.set_acq_result(float(delay), 2080.0, 12000)
+        ch.trk_start()
+        outs[name] = ch.trk_run(iq)
+        assert ch.events("trk") == []
+        ch.close()
+    r, g = outs["ref"], outs["b200"]
+    assert len(r) >= 6 and len(g) >= 6
+    assert abs(int(r["Tracking_sample_counter"][0]) - int(g["Tracking_sample_counter"][0])) <= 1   # same lock epoch
+    assert np.all(r["correlation_length_ms"][:6] == 1) and np.array_equal(r["Flag_PLL_180_deg_phase_locked"][:6], g["Flag_PLL_180_deg_phase_locked"][:6])
+    assert np.max(np.abs(r["Carrier_Doppler_hz"][:6] - g["Carrier_Doppler_hz"][:6])) < 3.0
+    scale = np.mean(np.hypot(r["Prompt_I"][:6], r["Prompt_Q"][:6]))
+    assert np.max(np.hypot(r["Prompt_I"][:6] - g["Prompt_I"][:6], r["Prompt_Q"][:6] - g["Prompt_Q"][:6])) < 0.1 * scale
+
+
+@pytest.mark.gpu
 def test_b200_cshort_acquisition_matches_reference(reflib, b200lib, gps_signal):
     """Acquisition_1C.item_type=cshort: the reference converts on the host (pcps_acquisition.cc:653-656), the B200 block
     ships the int16 pairs and converts on the device; same decision, same code phase, same Doppler bin."""
