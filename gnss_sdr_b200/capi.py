@@ -59,6 +59,10 @@ _SIGS = {
     "b200_iq_window": ([_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_refill": ([_vp, C.c_int, _vp, C.c_uint64, C.c_uint64], C.c_int),
     "b200_trk_set_taps": ([_vp, _vp], C.c_int),
+    "b200_trk_set_local_code_and_taps_cplx": ([_vp, C.c_int, _vp, _vp], C.c_int),
+    "b200_trk_correlate_cplx": ([_vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _vp], C.c_int),
+    "b200_trk_set_local_code_and_taps_16sc": ([_vp, C.c_int, _vp, _vp], C.c_int),
+    "b200_trk_correlate_16sc": ([_vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _vp], C.c_int),
     "b200_trk_channel_set_taps": ([_vp, C.c_int, _vp], C.c_int),
     "b200_acq_sweep_best_dev": ([_vp, _vp, _vp, C.c_uint32, _vp], C.c_int),
     "b200_acq_search_i16": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
@@ -417,6 +421,32 @@ class Multicorrelator:
         _chk(lib.b200_trk_correlate(self.h, sig_in.ctypes.data, rem_carrier_phase_in_rad, phase_step_rad,
                                     phase_rate_step_rad, rem_code_phase_chips, code_phase_step_chips,
                                     code_phase_rate_step_chips, n, out.ctypes.data), "b200_trk_correlate")
+        return out
+
+    # Cpu_Multicorrelator (complex local code)
+    def set_local_code_and_taps_cplx(self, code, shifts):
+        code = np.ascontiguousarray(code, np.complex64)
+        shifts = np.ascontiguousarray(shifts, np.float32)
+        _chk(lib.b200_trk_set_local_code_and_taps_cplx(self.h, code.size, code.ctypes.data, shifts.ctypes.data), "set_local_code_and_taps_cplx")
+
+    def correlate_cplx(self, sig_in, rem_carrier_phase_in_rad, phase_step_rad, rem_code_phase_chips, code_phase_step_chips) -> np.ndarray:
+        sig_in = np.ascontiguousarray(sig_in, np.complex64)
+        out = np.zeros(self.taps, np.complex64)
+        _chk(lib.b200_trk_correlate_cplx(self.h, sig_in.ctypes.data, rem_carrier_phase_in_rad, phase_step_rad, rem_code_phase_chips,
+                                         code_phase_step_chips, sig_in.size, out.ctypes.data), "b200_trk_correlate_cplx")
+        return out
+
+    # Cpu_Multicorrelator_16sc (interleaved int16 I,Q)
+    def set_local_code_and_taps_16sc(self, code_iq, shifts):
+        code_iq = np.ascontiguousarray(code_iq, np.int16)
+        shifts = np.ascontiguousarray(shifts, np.float32)
+        _chk(lib.b200_trk_set_local_code_and_taps_16sc(self.h, code_iq.size // 2, code_iq.ctypes.data, shifts.ctypes.data), "set_local_code_and_taps_16sc")
+
+    def correlate_16sc(self, sig_iq, rem_carrier_phase_in_rad, phase_step_rad, rem_code_phase_chips, code_phase_step_chips) -> np.ndarray:
+        sig_iq = np.ascontiguousarray(sig_iq, np.int16)
+        out = np.zeros(2 * self.taps, np.int16)
+        _chk(lib.b200_trk_correlate_16sc(self.h, sig_iq.ctypes.data, rem_carrier_phase_in_rad, phase_step_rad, rem_code_phase_chips,
+                                         code_phase_step_chips, sig_iq.size // 2, out.ctypes.data), "b200_trk_correlate_16sc")
         return out
 
     def free(self):

@@ -82,6 +82,11 @@ size_t trk_partial_elems(int n_items, int slices);
 int launch_trk_shared(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands, float2* out,
     int out_stride, int taps_uniform, cudaStream_t stream);
 int trk_shared_max_code_len();
+// legacy correlator variants (trk_variants.cu): complex local code, 16-bit samples and code
+int launch_trk_cplx_code(const float2* x, const float2* code, int n, int L, int taps, const float* shifts, float rem_carr, float dphi, float rem_code,
+    float step, float2* out, cudaStream_t st);
+int launch_trk_16sc(const short* x_iq, const short* code_iq, int n, int L, int taps, const float* shifts, float rem_carr, float dphi, float rem_code,
+    float step, short* out_iq, cudaStream_t st);
 
 }  // namespace b200
 

@@ -885,6 +885,15 @@ struct b200_trk
     unsigned int* counter{nullptr};
     int slices_cap{0};
     bool have_code{false};
+    // legacy variants (trk_variants.cu): complex local code / 16-bit samples and code
+    float2* cplx_code_dev{nullptr};
+    int cplx_code_len{0};
+    short* code16_dev{nullptr};
+    int code16_len{0};
+    short* sig16_dev{nullptr};
+    short* out16_dev{nullptr};
+    float2* out_cplx_dev{nullptr};
+    float var_shifts[B200_MAX_TAPS] = {0};
 };
 
 extern "C"
@@ -1015,6 +1024,105 @@ extern "C"
         return B200_OK;
     }
 
+    // ---- Cpu_Multicorrelator (complex local code), cpu_multicorrelator.cc:53-100 --------------------------------------
+    int b200_trk_set_local_code_and_taps_cplx(b200_trk* t, int code_length_chips, const b200_cf32* local_code_in, const float* shifts_chips)
+    {
+        if (!t || !local_code_in || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        if (code_length_chips > t->cplx_code_len)
+            {
+                if (t->cplx_code_dev) B200_CUDA_TRY(cudaFree(t->cplx_code_dev));
+                t->cplx_code_dev = nullptr;
+                B200_CUDA_TRY(cudaMalloc(&t->cplx_code_dev, sizeof(float2) * code_length_chips));
+            }
+        if (!t->out_cplx_dev) B200_CUDA_TRY(cudaMalloc(&t->out_cplx_dev, sizeof(float2) * B200_MAX_TAPS));
+        t->cplx_code_len = code_length_chips;
+        B200_CUDA_TRY(cudaMemcpyAsync(t->cplx_code_dev, local_code_in, sizeof(float2) * code_length_chips, cudaMemcpyHostToDevice, t->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        for (int k = 0; k < t->taps; k++) t->var_shifts[k] = shifts_chips[k];
+        return B200_OK;
+    }
+
+    int b200_trk_correlate_cplx(b200_trk* t, const b200_cf32* sig_in_host, float rem_carrier_phase_in_rad, float phase_step_rad,
+        float rem_code_phase_chips, float code_phase_step_chips, int signal_length_samples, b200_cf32* corr_out_host)
+    {
+        if (!t || !sig_in_host || !corr_out_host) return B200_ERR_ARG;
+        if (!t->cplx_code_dev)
+            {
+                set_error("correlate before set_local_code_and_taps_cplx");
+                return B200_ERR_STATE;
+            }
+        const int n = signal_length_samples;
+        if (n < 0 || n > t->max_len)
+            {
+                set_error("signal_length_samples %d outside 0..%d", n, t->max_len);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        if (n > 0) B200_CUDA_TRY(cudaMemcpyAsync(t->sig_dev, sig_in_host, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
+        const int rc = launch_trk_cplx_code(t->sig_dev, t->cplx_code_dev, n, t->cplx_code_len, t->taps, t->var_shifts, rem_carrier_phase_in_rad,
+            phase_step_rad, rem_code_phase_chips, code_phase_step_chips, t->out_cplx_dev, t->stream);
+        if (rc) return rc;
+        {
+            std::lock_guard<std::mutex> lk(t->e->mu);
+            t->e->launches++;
+        }
+        B200_CUDA_TRY(cudaMemcpyAsync(corr_out_host, t->out_cplx_dev, sizeof(float2) * t->taps, cudaMemcpyDeviceToHost, t->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        return B200_OK;
+    }
+
+    // ---- Cpu_Multicorrelator_16sc (16-bit samples and code), cpu_multicorrelator_16sc.cc:47-91 -------------------------
+    int b200_trk_set_local_code_and_taps_16sc(b200_trk* t, int code_length_chips, const int16_t* local_code_iq, const float* shifts_chips)
+    {
+        if (!t || !local_code_iq || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
+        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        if (code_length_chips > t->code16_len)
+            {
+                if (t->code16_dev) B200_CUDA_TRY(cudaFree(t->code16_dev));
+                t->code16_dev = nullptr;
+                B200_CUDA_TRY(cudaMalloc(&t->code16_dev, sizeof(short) * 2 * code_length_chips));
+            }
+        if (!t->sig16_dev) B200_CUDA_TRY(cudaMalloc(&t->sig16_dev, sizeof(short) * 2 * (static_cast<size_t>(t->max_len) + 2)));
+        if (!t->out16_dev) B200_CUDA_TRY(cudaMalloc(&t->out16_dev, sizeof(short) * 2 * B200_MAX_TAPS));
+        t->code16_len = code_length_chips;
+        B200_CUDA_TRY(cudaMemcpyAsync(t->code16_dev, local_code_iq, sizeof(short) * 2 * code_length_chips, cudaMemcpyHostToDevice, t->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        for (int k = 0; k < t->taps; k++) t->var_shifts[k] = shifts_chips[k];
+        return B200_OK;
+    }
+
+    int b200_trk_correlate_16sc(b200_trk* t, const int16_t* sig_in_iq_host, float rem_carrier_phase_in_rad, float phase_step_rad,
+        float rem_code_phase_chips, float code_phase_step_chips, int signal_length_samples, int16_t* corr_out_iq_host)
+    {
+        if (!t || !sig_in_iq_host || !corr_out_iq_host) return B200_ERR_ARG;
+        if (!t->code16_dev)
+            {
+                set_error("correlate before set_local_code_and_taps_16sc");
+                return B200_ERR_STATE;
+            }
+        const int n = signal_length_samples;
+        if (n < 0 || n > t->max_len)
+            {
+                set_error("signal_length_samples %d outside 0..%d", n, t->max_len);
+                return B200_ERR_RANGE;
+            }
+        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        if (n > 0) B200_CUDA_TRY(cudaMemcpyAsync(t->sig16_dev, sig_in_iq_host, sizeof(short) * 2 * n, cudaMemcpyHostToDevice, t->stream));
+        const int rc = launch_trk_16sc(t->sig16_dev, t->code16_dev, n, t->code16_len, t->taps, t->var_shifts, rem_carrier_phase_in_rad, phase_step_rad,
+            rem_code_phase_chips, code_phase_step_chips, t->out16_dev, t->stream);
+        if (rc) return rc;
+        {
+            std::lock_guard<std::mutex> lk(t->e->mu);
+            t->e->launches++;
+        }
+        B200_CUDA_TRY(cudaMemcpyAsync(corr_out_iq_host, t->out16_dev, sizeof(short) * 2 * t->taps, cudaMemcpyDeviceToHost, t->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
+        return B200_OK;
+    }
+
     int b200_trk_destroy(b200_trk* t)
     {
         if (!t) return B200_ERR_ARG;
@@ -1025,6 +1133,11 @@ extern "C"
         if (t->ctl) cudaFreeHost(t->ctl);
         if (t->partial) cudaFree(t->partial);
         if (t->counter) cudaFree(t->counter);
+        if (t->cplx_code_dev) cudaFree(t->cplx_code_dev);
+        if (t->code16_dev) cudaFree(t->code16_dev);
+        if (t->sig16_dev) cudaFree(t->sig16_dev);
+        if (t->out16_dev) cudaFree(t->out16_dev);
+        if (t->out_cplx_dev) cudaFree(t->out_cplx_dev);
         if (t->stream) cudaStreamDestroy(t->stream);
         delete t;
         return B200_OK;

@@ -134,6 +134,24 @@ extern "C"
         float rem_carrier_phase_in_rad, float phase_step_rad, float phase_rate_step_rad,
         float rem_code_phase_chips, float code_phase_step_chips, float code_phase_rate_step_chips,
         int signal_length_samples, b200_cf32* corr_out_host);
+    /* ---- the reference's two other correlator classes (same handle type; one CTA per call, latency-oriented) ----------
+     * Cpu_Multicorrelator - COMPLEX local code (src/algorithms/tracking/libs/cpu_multicorrelator.cc: set_local_code_and_taps
+     * :53-63, Carrier_wipeoff_multicorrelator_resampler :86-100 = volk_gnsssdr_32fc_xn_resampler_32fc_xn +
+     * volk_gnsssdr_32fc_x2_rotator_dot_prod_32fc_xn): corr_out[k] = sum_n sig[n] e^{-j(rem + n step)} code[idx_k(n)].
+     * The class has no phase-rate / code-rate arguments. */
+    int b200_trk_set_local_code_and_taps_cplx(b200_trk* t, int code_length_chips, const b200_cf32* local_code_in, const float* shifts_chips);
+    int b200_trk_correlate_cplx(b200_trk* t, const b200_cf32* sig_in_host, float rem_carrier_phase_in_rad, float phase_step_rad,
+        float rem_code_phase_chips, float code_phase_step_chips, int signal_length_samples, b200_cf32* corr_out_host);
+    /* Cpu_Multicorrelator_16sc - 16-bit complex samples AND code (cpu_multicorrelator_16sc.cc:47-91 =
+     * volk_gnsssdr_16ic_xn_resampler_16ic_xn + volk_gnsssdr_16ic_x2_rotator_dot_prod_16ic_xn): per sample the rotated
+     * sample is rounded to int16, multiplied by the int16 code value (16-bit wrap of each product component, as
+     * std::complex<int16_t> does) and accumulated; the reference saturates its 16-bit accumulator at every add, this sum is
+     * exact and saturated once at the end (identical while the running sum stays inside int16, the class's operating range;
+     * the reference's own QA tolerance between implementations is +-16 LSB, VG lib/kernel_tests.h).
+     * Arrays are interleaved (I,Q) int16: 2 * code_length_chips, 2 * signal_length_samples, 2 * n_correlators values. */
+    int b200_trk_set_local_code_and_taps_16sc(b200_trk* t, int code_length_chips, const int16_t* local_code_iq, const float* shifts_chips);
+    int b200_trk_correlate_16sc(b200_trk* t, const int16_t* sig_in_iq_host, float rem_carrier_phase_in_rad, float phase_step_rad,
+        float rem_code_phase_chips, float code_phase_step_chips, int signal_length_samples, int16_t* corr_out_iq_host);
     /* free()                                                               (.cc:147-160) */
     int b200_trk_destroy(b200_trk* t);
 

@@ -27,6 +27,8 @@
 #include <gnuradio/shim_runner.h>
 #include <gnuradio/top_block.h>
 #include <pmt/pmt.h>
+#include "cpu_multicorrelator.h"
+#include "cpu_multicorrelator_16sc.h"
 #include "galileo_e1_signal_replica.h"
 #include "gps_l5_signal_replica.h"
 #include "gps_sdr_signal_replica.h"
@@ -501,5 +503,41 @@ extern "C"
         for (void* c : chans) itf_channel_destroy(c);
         if (positives) *positives = pos.load();
         return dt;
+    }
+
+    // The reference's two other correlator classes, compiled where they lie: one call = init, set_local_code_and_taps,
+    // set_input_output_vectors, Carrier_wipeoff_multicorrelator_resampler, free.  arch selects the VG dispatch first.
+    int ref_mc_cplx_code(const float* sig_iq, int n, const float* code_iq, int code_len, const float* shifts, int taps, float rem_carr, float dphi,
+        float rem_code, float step, float* out_iq)
+    {
+        Cpu_Multicorrelator mc;
+        std::vector<float> sh(shifts, shifts + taps);
+        volk_gnsssdr::vector<std::complex<float>> in(n), code(code_len), out(taps);
+        std::memcpy(static_cast<void*>(in.data()), sig_iq, sizeof(float) * 2 * n);
+        std::memcpy(static_cast<void*>(code.data()), code_iq, sizeof(float) * 2 * code_len);
+        mc.init(n, taps);
+        mc.set_local_code_and_taps(code_len, code.data(), sh.data());
+        mc.set_input_output_vectors(out.data(), in.data());
+        mc.Carrier_wipeoff_multicorrelator_resampler(rem_carr, dphi, rem_code, step, n);
+        std::memcpy(out_iq, out.data(), sizeof(float) * 2 * taps);
+        mc.free();
+        return 0;
+    }
+
+    int ref_mc_16sc(const int16_t* sig_iq, int n, const int16_t* code_iq, int code_len, const float* shifts, int taps, float rem_carr, float dphi,
+        float rem_code, float step, int16_t* out_iq)
+    {
+        Cpu_Multicorrelator_16sc mc;
+        std::vector<float> sh(shifts, shifts + taps);
+        volk_gnsssdr::vector<lv_16sc_t> in(n), code(code_len), out(taps);
+        std::memcpy(in.data(), sig_iq, sizeof(int16_t) * 2 * n);
+        std::memcpy(code.data(), code_iq, sizeof(int16_t) * 2 * code_len);
+        mc.init(n, taps);
+        mc.set_local_code_and_taps(code_len, code.data(), sh.data());
+        mc.set_input_output_vectors(out.data(), in.data());
+        mc.Carrier_wipeoff_multicorrelator_resampler(rem_carr, dphi, rem_code, step, n);
+        std::memcpy(out_iq, out.data(), sizeof(int16_t) * 2 * taps);
+        mc.free();
+        return 0;
     }
 }

@@ -210,3 +210,25 @@ def acq_bench(lib, conf: dict, impl: str, samples: np.ndarray, threads: int, sea
                            samples.ctypes.data, len(samples), 1 if pin else 0, C.byref(pos))
     lib.itf_config_destroy(cfg)
     return float(dt), int(pos.value)
+
+
+def ref_mc_cplx_code(lib, sig, code, shifts, rem_carr, dphi, rem_code, step):
+    """Cpu_Multicorrelator (complex local code) of the reference, compiled in place."""
+    sig = np.ascontiguousarray(sig, np.complex64)
+    code = np.ascontiguousarray(code, np.complex64)
+    sh = np.ascontiguousarray(shifts, np.float32)
+    out = np.zeros(len(sh), np.complex64)
+    lib.ref_mc_cplx_code(C.c_void_p(sig.ctypes.data), len(sig), C.c_void_p(code.ctypes.data), len(code), C.c_void_p(sh.ctypes.data), len(sh),
+                         C.c_float(rem_carr), C.c_float(dphi), C.c_float(rem_code), C.c_float(step), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def ref_mc_16sc(lib, sig_iq, code_iq, shifts, rem_carr, dphi, rem_code, step):
+    """Cpu_Multicorrelator_16sc of the reference, compiled in place (interleaved int16 I,Q in and out)."""
+    sig_iq = np.ascontiguousarray(sig_iq, np.int16)
+    code_iq = np.ascontiguousarray(code_iq, np.int16)
+    sh = np.ascontiguousarray(shifts, np.float32)
+    out = np.zeros(2 * len(sh), np.int16)
+    lib.ref_mc_16sc(C.c_void_p(sig_iq.ctypes.data), len(sig_iq) // 2, C.c_void_p(code_iq.ctypes.data), len(code_iq) // 2, C.c_void_p(sh.ctypes.data),
+                    len(sh), C.c_float(rem_carr), C.c_float(dphi), C.c_float(rem_code), C.c_float(step), C.c_void_p(out.ctypes.data))
+    return out

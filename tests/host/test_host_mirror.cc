@@ -130,7 +130,7 @@ static void shift_pointer_semantics(const std::vector<float>& code, const std::v
 static void coalescer_throughput(int n_threads, int epochs, int window_us)
 {
     const int n = 25000;  // 1 ms at 25 Msps
-    const uint64_t total = static_cast<uint64_t>(n) * epochs + n;
+    const uint64_t total = static_cast<uint64_t>(n) * (epochs + 2) + n;
     std::vector<std::complex<float>> iq(total);
     std::mt19937 rng(3);
     std::uniform_real_distribution<float> ud(-1.0F, 1.0F);
@@ -148,6 +148,8 @@ static void coalescer_throughput(int n_threads, int epochs, int window_us)
     co->reset_stats();
     std::vector<double> lat_sum(n_threads, 0.0), lat_max(n_threads, 0.0);
     std::atomic<int> failed{0};
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
     const uint64_t base = 0;
     auto worker = [&](int t) {
         B200_Multicorrelator_Real_Codes mc;
@@ -161,9 +163,15 @@ static void coalescer_throughput(int n_threads, int epochs, int window_us)
         mc.set_high_dynamics_resampler(false);
         mc.set_local_code_and_taps(1023, code.data(), shifts);
         const float step = 1.023e6F / 25.0e6F;
+        // one untimed epoch opens the coalescer channel and uploads the code table; the clock starts when all threads are there
+        mc.set_input_output_vectors(out, iq.data());
+        mc.set_stream_position(3, base, n);
+        if (!mc.Carrier_wipeoff_multicorrelator_resampler(0.0F, 0.001F, 0.0F, 0.0F, step, 0.0F, n)) failed++;
+        ready++;
+        while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
         for (int k = 0; k < epochs; k++)
             {
-                const uint64_t pos = static_cast<uint64_t>(k) * n;
+                const uint64_t pos = static_cast<uint64_t>(k + 1) * n;
                 mc.set_input_output_vectors(out, iq.data() + pos);
                 mc.set_stream_position(3, base + pos, n);
                 const auto t0 = std::chrono::steady_clock::now();
@@ -174,9 +182,12 @@ static void coalescer_throughput(int n_threads, int epochs, int window_us)
             }
         mc.free();
     };
-    const auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
     for (int t = 0; t < n_threads; t++) pool.emplace_back(worker, t);
+    while (ready.load() < n_threads) std::this_thread::yield();
+    co->reset_stats();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
     for (auto& t : pool) t.join();
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const auto st = co->stats();

@@ -15,6 +15,7 @@ def build():
     cmd = ["g++", "-std=c++20", "-O2", os.path.join(ROOT, "tests", "host", "test_host_mirror.cc"),
            os.path.join(libdir, "host", "b200_multicorrelator_real_codes.cc"),
            os.path.join(libdir, "host", "b200_trk_coalescer.cc"),
+           os.path.join(libdir, "host", "b200_multicorrelator_variants.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_core.cc"),
            os.path.join(libdir, "host", "b200_pcps_acquisition_fine_doppler_core.cc"),
            os.path.join(libdir, "host", "b200_dll_pll_veml_loop.cc"),
