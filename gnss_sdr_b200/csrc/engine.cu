@@ -383,10 +383,14 @@ extern "C"
                     set_error("band %d is not an owned ring (call b200_iq_create)", band);
                     return B200_ERR_STATE;
                 }
-            if (abs_index + n <= b.write_index) return B200_OK;  // every sample of this block is already in the band
-            if (abs_index > b.write_index)
+            // what the ring holds right now
+            const unsigned long long oldest = b.write_index > b.capacity ? b.write_index - b.capacity : 0ULL;
+            const unsigned long long lo = b.valid_from > oldest ? b.valid_from : oldest;
+            if (abs_index >= lo && abs_index + n <= b.write_index) return B200_OK;  // every sample of this block is already in the band
+            if (abs_index > b.write_index || abs_index < lo)
                 {
-                    // a gap (e.g. the first block to track starts long after sample 0): what the ring held is history
+                    // a gap (the first block to track starts long after sample 0) or a stream that starts over at an older
+                    // index (a new capture, a test): what the ring held is history, the band restarts at abs_index
                     b.valid_from = abs_index;
                     b.write_index = abs_index;
                 }

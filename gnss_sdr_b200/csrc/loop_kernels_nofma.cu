@@ -415,11 +415,12 @@ __global__ void trk_loop_cycle_kernel(LoopDev* loops, int n_loops, int mode, Loo
 // kLoopThreads threads with the batch kernel's per-item templates, slices = 1).  Loops are independent, so there is no
 // grid-wide dependency and no launch per epoch; a CTA ends when its loop has run max_epochs cycles, loses lock, or
 // finds its next vector_length samples not resident (stall).
-// Each channel is a latency chain (epoch k+1's NCO commands need epoch k's taps): the correlation part shrinks with the
-// CTA size, so the CTA is as wide as the register budget of the correlation templates allows (round 1: 256 threads,
-// 10.7 us per epoch with 32 of 148 SMs busy and most cycles spent at the barrier around thread 0's update).
+// Each channel is a latency chain (epoch k+1's NCO commands need epoch k's taps); the CTA width is a build parameter.
+// Measured on B200 (tools/loop_ab.sh, 32 / 256 loops): 256 threads 10.9 / 19.1 us per epoch, 512 threads 10.5 / 26.3,
+// 1024 threads 12.9 / 30.9 - the serial double-precision loop update of thread 0, not the correlation, sets the epoch
+// time, and wider CTAs cost residency when many loops run.
 #ifndef B200_LOOP_THREADS
-#define B200_LOOP_THREADS 1024
+#define B200_LOOP_THREADS 256
 #endif
 constexpr int kLoopThreads = B200_LOOP_THREADS;
 

@@ -35,6 +35,7 @@ Trk_Coalescer* Trk_Coalescer::instance()
 Trk_Coalescer::Trk_Coalescer(b200_engine* engine) : d_engine(engine), d_slots(new Slot[kMaxChannels])
 {
     for (auto& w : d_band_written) w.store(0);
+    for (auto& w : d_band_lo) w.store(0);
     if (const char* env = std::getenv("B200_COALESCE_WINDOW_US")) d_window_us = std::atoi(env);
     d_thread = std::thread([this] { tick_loop(); });
 }
@@ -168,10 +169,10 @@ bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* 
     if (!s->active.exchange(true)) d_n_active.fetch_add(1);
     d_samples_offered.fetch_add(n, std::memory_order_relaxed);
     // fast path: somebody has already put these samples into the band (every block of the flowgraph offers the same stream)
-    if (abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
+    if (abs_index >= d_band_lo[band].load(std::memory_order_acquire) && abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
 
     std::unique_lock<std::mutex> lk(d_band_mu[band]);
-    if (abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
+    if (abs_index >= d_band_lo[band].load(std::memory_order_acquire) && abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
     // back-pressure: never overwrite what a slower active channel of this band still needs.  A channel that stopped calling
     // (stalled test thread, block torn down without idle()) must not wedge the rest: after the timeout laggards go idle.
     if (!fits(band, abs_index, n))
@@ -196,8 +197,15 @@ bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* 
             return false;
         }
     d_samples_copied.fetch_add(n_new, std::memory_order_relaxed);
-    uint64_t w = d_band_written[band].load(std::memory_order_relaxed);
-    if (abs_index + n > w || abs_index > w) d_band_written[band].store(abs_index + n, std::memory_order_release);
+    // the band's window after this push (a gap or a stream that started over moves its lower edge)
+    uint64_t lo = 0, hi = 0;
+    if (b200_iq_window(d_engine, band, &lo, &hi) == B200_OK)
+        {
+            // order matters for the lock-free fast path: shrink first (lo up / hi down), then grow
+            d_band_written[band].store(std::min<uint64_t>(hi, d_band_written[band].load(std::memory_order_relaxed)), std::memory_order_release);
+            d_band_lo[band].store(lo, std::memory_order_release);
+            d_band_written[band].store(hi, std::memory_order_release);
+        }
     return true;
 }
 

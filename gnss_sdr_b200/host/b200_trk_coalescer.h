@@ -113,7 +113,8 @@ private:
     std::atomic<int> d_posted{0};
     std::atomic<int> d_n_active{0};
     std::atomic<bool> d_stop{false};
-    std::atomic<uint64_t> d_band_written[kMaxBands];   // samples [.., written) are in the band (fast path of push)
+    std::atomic<uint64_t> d_band_written[kMaxBands];   // samples [lo, written) are in the band (fast path of push)
+    std::atomic<uint64_t> d_band_lo[kMaxBands];
     uint64_t d_band_capacity[kMaxBands] = {0};
     std::mutex d_band_mu[kMaxBands];        // one producer at a time per band (slow path of push)
     std::condition_variable d_cv_space[kMaxBands];

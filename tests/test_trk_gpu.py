@@ -712,3 +712,27 @@ def test_16bit_correlator_matches_reference_class(capi):
     assert np.max(np.abs(got.astype(int) - want.astype(int))) <= 16
     mc.free()
     eng.close()
+
+
+def test_push_at_restarts_when_the_stream_starts_over(capi, oracle):
+    """A stream that begins again at an OLDER absolute index than anything the ring still holds (a new capture, the next
+    test in the same process): b200_iq_push_at must not answer "already there" - the band restarts at the offered index."""
+    eng = capi.Engine(0)
+    rng = np.random.default_rng(8)
+    iq = (rng.integers(-50, 50, 40000) + 1j * rng.integers(-50, 50, 40000)).astype(np.complex64)
+    eng.iq_create(1, 1 << 14)                       # 16384-sample ring
+    assert eng.iq_push_at(1, 5_000_000, iq[:12000]) == 12000
+    assert eng.iq_push_at(1, 5_012_000, iq[12000:30000]) == 18000      # wraps: the ring now holds [5 013 616, 5 030 000)
+    assert eng.iq_window(1) == (5_030_000 - 16384, 5_030_000)
+    assert eng.iq_push_at(1, 0, iq[:8000]) == 8000                     # the stream starts over
+    assert eng.iq_window(1) == (0, 8000)
+    assert eng.iq_push_at(1, 4000, iq[4000:10000]) == 2000
+    code = np.where(rng.integers(0, 2, 1023) > 0, 1.0, -1.0).astype(np.float32)
+    ch = eng.channel_create(1, 3)
+    eng.channel_set_code(ch, code, [-0.5, 0.0, 0.5])
+    items = np.zeros(1, capi.TRK_ITEM_DTYPE)
+    items[0] = (ch, 4000, 5000, 0.0, 0.0, 0.0, 0.3, 0.2557, 0.0)
+    got = eng.trk_batch(items, 3)[0]
+    want = oracle.port.multicorrelator(1, iq[5000:9000], code, [-0.5, 0.0, 0.5], 0.0, 0.0, 0.3, 0.2557)
+    assert np.array_equal(got, want)
+    eng.close()
