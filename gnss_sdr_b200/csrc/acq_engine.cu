@@ -5,6 +5,7 @@
 #include "acq_fft.cuh"
 #include "engine.cuh"
 
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -58,10 +59,33 @@ struct b200_acq
     uint32_t pending_slots{0};
     bool pending{false};
     std::vector<int> slots_on_device;  // slot list last uploaded (sweeps usually repeat it)
+    // Bluestein (chirp-z) path for transform sizes the mixed-radix planner cannot factor (e.g. 16 368 = 2^4 * 3 * 11 * 31):
+    // every N-point DFT is a circular convolution with a chirp, done with M-point transforms (M >= 2N-1, two-level plan).
+    struct Bluestein
+    {
+        int M{0};
+        FftPlan plM{};
+        float2* twM{nullptr};
+        float2* chirp{nullptr};        // w[k] = exp(+j pi k^2 / N), k < N
+        float2* chirp_conj_M{nullptr}; // conj(w[k]) / M
+        float2* chirp_M{nullptr};      // w[k] / M
+        float2* chirp_conj{nullptr};   // conj(w[k])
+        float2* filt{nullptr};         // 2 x M: FFT_M(h), FFT_M(conj h), h = w extended symmetrically
+        float2* mult{nullptr};         // bins x N: wipe-off . conj(w)
+        float2* A{nullptr};            // bins x M spectra of the padded, chirped rows
+        float2* Zw{nullptr};           // bins x M inverse workspace
+        float2* Xs{nullptr};           // bins x N: DFT_N(signal . wipe-off)
+        float2* CW{nullptr};           // slots x N: conj(DFT_N(code)) . w / M
+        int* slot_ids{nullptr};        // device {0, 1}
+        AcqRowStat* partial{nullptr};
+    };
+    Bluestein* bl{nullptr};
 };
 
 namespace
 {
+int bluestein_search(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32_t n_slots, uint32_t dwell_counter, b200_acq_result* results_dev);
+
 int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32_t n_slots, uint32_t dwell_counter,
     b200_acq_result* results_dev, int step_two = 0, float prev_input_power = 0.f)
 {
@@ -81,6 +105,15 @@ int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32
                     set_error("slot %u has no local code", slots[i]);
                     return B200_ERR_STATE;
                 }
+        }
+    if (a->bl)
+        {
+            if (step_two)
+                {
+                    set_error("two-step acquisition is not available for chirp-z transform sizes");
+                    return B200_ERR_STATE;
+                }
+            return bluestein_search(a, in_dev, slots, n_slots, dwell_counter, results_dev);
         }
     cudaStream_t st = a->stream;
     bool same = a->slots_on_device.size() == n_slots;
@@ -130,6 +163,161 @@ int search_impl(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32
 }
 }  // namespace
 
+namespace
+{
+// smallest M >= 2N - 1 that the two-level planner accepts
+int bluestein_size(int n, FftPlan* pl)
+{
+    for (long long m = 2LL * n - 1; m <= 10LL * kAcqMaxSmemPoints; m++)
+        {
+            long long r = m;
+            for (int p : {2, 3, 5, 7})
+                while (r % p == 0) r /= p;
+            if (r != 1) continue;
+            if (acq_plan_make_two_level(static_cast<int>(m), pl) == B200_OK) return static_cast<int>(m);
+        }
+    return 0;
+}
+
+int bluestein_refresh_mult(b200_acq* a)
+{
+    // mult[d][i] = wipe[d][i] * conj(w[i]): the wipe-off grid keeps the reference's float32 sincos values, the chirp is extra
+    b200_acq::Bluestein* b = a->bl;
+    const int n = static_cast<int>(a->c.fft_size);
+    return acq_launch_rows_times_vector(a->wipe, n, b->chirp_conj, n, 0, b->mult, n, static_cast<int>(a->c.num_doppler_bins), a->stream);
+}
+
+int bluestein_setup(b200_acq* a)
+{
+    const b200_acq_conf& c = a->c;
+    const int n = static_cast<int>(c.fft_size);
+    auto* b = new (std::nothrow) b200_acq::Bluestein();
+    if (!b) return B200_ERR_NOMEM;
+    a->bl = b;
+    b->M = bluestein_size(n, &b->plM);
+    if (b->M == 0)
+        {
+            set_error("fft_size %d: no chirp-z size M >= 2N-1 within %d points", n, 10 * kAcqMaxSmemPoints);
+            return B200_ERR_RANGE;
+        }
+    const size_t M = static_cast<size_t>(b->M), bins = c.num_doppler_bins, slots = c.n_code_slots;
+    B200_CUDA_TRY(cudaMalloc(&b->twM, sizeof(float2) * M));
+    B200_CUDA_TRY(cudaMalloc(&b->chirp, sizeof(float2) * n));
+    B200_CUDA_TRY(cudaMalloc(&b->chirp_conj, sizeof(float2) * n));
+    B200_CUDA_TRY(cudaMalloc(&b->chirp_conj_M, sizeof(float2) * n));
+    B200_CUDA_TRY(cudaMalloc(&b->chirp_M, sizeof(float2) * n));
+    B200_CUDA_TRY(cudaMalloc(&b->filt, sizeof(float2) * 2 * M));
+    B200_CUDA_TRY(cudaMalloc(&b->mult, sizeof(float2) * bins * n));
+    B200_CUDA_TRY(cudaMalloc(&b->A, sizeof(float2) * bins * M));
+    B200_CUDA_TRY(cudaMalloc(&b->Zw, sizeof(float2) * bins * M));
+    B200_CUDA_TRY(cudaMalloc(&b->Xs, sizeof(float2) * bins * n));
+    B200_CUDA_TRY(cudaMalloc(&b->CW, sizeof(float2) * slots * n));
+    B200_CUDA_TRY(cudaMalloc(&b->slot_ids, sizeof(int) * 2));
+    B200_CUDA_TRY(cudaMalloc(&b->partial, sizeof(AcqRowStat) * bins * acq_final_chunks(b->plM)));
+    const int ids[2] = {0, 1};
+    B200_CUDA_TRY(cudaMemcpy(b->slot_ids, ids, sizeof(ids), cudaMemcpyHostToDevice));
+    int rc = acq_launch_twiddles(b->twM, b->plM, a->stream);
+    if (rc) return rc;
+    // chirp tables in double: w[k] = exp(j pi k^2 / N) with k^2 reduced mod 2N
+    std::vector<float2> w(n), wc(n), wcm(n), wm(n), h(M), hc(M);
+    const double inv_m = 1.0 / static_cast<double>(M);
+    for (size_t i = 0; i < M; i++) h[i] = hc[i] = make_float2(0.f, 0.f);
+    for (int k = 0; k < n; k++)
+        {
+            const long long k2 = (static_cast<long long>(k) * k) % (2LL * n);
+            const double ang = 3.14159265358979323846 * static_cast<double>(k2) / static_cast<double>(n);
+            const double cr = std::cos(ang), ci = std::sin(ang);
+            w[k] = make_float2(static_cast<float>(cr), static_cast<float>(ci));
+            wc[k] = make_float2(static_cast<float>(cr), static_cast<float>(-ci));
+            wcm[k] = make_float2(static_cast<float>(cr * inv_m), static_cast<float>(-ci * inv_m));
+            wm[k] = make_float2(static_cast<float>(cr * inv_m), static_cast<float>(ci * inv_m));
+            h[k] = w[k];
+            hc[k] = wc[k];
+            if (k > 0)
+                {
+                    h[M - k] = w[k];
+                    hc[M - k] = wc[k];
+                }
+        }
+    B200_CUDA_TRY(cudaMemcpy(b->chirp, w.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpy(b->chirp_conj, wc.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpy(b->chirp_conj_M, wcm.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpy(b->chirp_M, wm.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    // filter spectra through the code-spectrum kernel, which stores conj(FFT(.)): for a symmetric h, conj(FFT(conj h)) = FFT(h)
+    B200_CUDA_TRY(cudaMemcpy(b->A, hc.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    rc = acq_launch_code_fft(b->A, b->M, 0, b->filt, b->plM, b->twM, a->stream);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaMemcpy(b->Zw, h.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    rc = acq_launch_code_fft(b->Zw, b->M, 0, b->filt + M, b->plM, b->twM, a->stream);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return B200_OK;
+}
+
+void bluestein_free(b200_acq* a)
+{
+    b200_acq::Bluestein* b = a->bl;
+    if (!b) return;
+    cudaFree(b->twM);
+    cudaFree(b->chirp);
+    cudaFree(b->chirp_conj);
+    cudaFree(b->chirp_conj_M);
+    cudaFree(b->chirp_M);
+    cudaFree(b->filt);
+    cudaFree(b->mult);
+    cudaFree(b->A);
+    cudaFree(b->Zw);
+    cudaFree(b->Xs);
+    cudaFree(b->CW);
+    cudaFree(b->slot_ids);
+    cudaFree(b->partial);
+    delete b;
+    a->bl = nullptr;
+}
+
+// rows x N: out[r] = DFT_N(in[r * in_stride .. ] . mult[r * mult_stride ..])   (forward chirp-z, natural order)
+int bluestein_forward_rows(b200_acq* a, const float2* in, size_t in_stride, const float2* mult, size_t mult_stride, int rows, float2* out)
+{
+    b200_acq::Bluestein* b = a->bl;
+    const int n = static_cast<int>(a->c.fft_size);
+    int rc = acq_launch_fwd_rows(in, in_stride, n, mult, mult_stride, b->A, rows, b->plM, b->twM, a->stream);
+    if (rc) return rc;
+    return acq_launch_inverse_store_rows(b->A, b->filt, b->slot_ids, rows, b->plM, b->twM, b->Zw, b->chirp_conj_M, n, out, n, a->stream);
+}
+
+int bluestein_search(b200_acq* a, const float2* in_dev, const uint32_t* slots, uint32_t n_slots, uint32_t dwell_counter, b200_acq_result* results_dev)
+{
+    b200_acq::Bluestein* b = a->bl;
+    const b200_acq_conf& c = a->c;
+    const int n = static_cast<int>(c.fft_size);
+    const int bins = static_cast<int>(c.num_doppler_bins);
+    // X_d = DFT_N(x . wipe_d) for every Doppler bin, once per sweep
+    int rc = bluestein_forward_rows(a, in_dev, 0, b->mult, n, bins, b->Xs);
+    if (rc) return rc;
+    uint64_t launched = 4;
+    for (uint32_t i = 0; i < n_slots; i++)
+        {
+            // rows of this PRN: y = IDFT_N(X_d . C) = w . IFFT_M(FFT_M(pad(X_d . C . w)) . FFT_M(conj h)) / M ; |w| = 1
+            rc = acq_launch_fwd_rows(b->Xs, n, n, b->CW + static_cast<size_t>(slots[i]) * n, 0, b->A, bins, b->plM, b->twM, a->stream);
+            if (rc) return rc;
+            // the correlation kernel addresses the grid by code-slot id, and the "code" here is filter slot 1
+            float* grid = a->grid ? a->grid + (static_cast<ptrdiff_t>(slots[i]) - 1) * static_cast<ptrdiff_t>(bins) * n : nullptr;
+            rc = acq_launch_corr(b->A, b->filt, b->slot_ids + 1, 1, bins, b->plM, b->twM, 0, n, a->rowstat + static_cast<size_t>(i) * bins, grid,
+                dwell_counter > 1 ? 1 : 0, 0, nullptr, 0, nullptr, b->Zw, b->partial, a->stream);
+            if (rc) return rc;
+            launched += 5;
+        }
+    rc = acq_launch_stats(a->rowstat, static_cast<int>(n_slots), bins, n, c.doppler_max, a->doppler_center, c.doppler_step, dwell_counter, c.use_cfar,
+        a->best, results_dev, 0, 0.f, 0.f, 0.f, a->stream);
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk(a->e->mu);
+        a->e->launches += launched + 1;
+    }
+    return B200_OK;
+}
+}  // namespace
+
 extern "C"
 {
     int b200_acq_create(b200_engine* e, const b200_acq_conf* conf, b200_acq** out)
@@ -146,10 +334,28 @@ extern "C"
         if (c.bit_transition_flag && 2 * c.effective_fft_size > c.fft_size) return B200_ERR_ARG;
         FftPlan pl{};
         int rc = acq_plan_make(static_cast<int>(c.fft_size), &pl);
+        bool use_bluestein = false;
         if (rc)
             {
-                set_error("fft_size %u unsupported: prime factors must be 2,3,5,7 and fft_size <= 10 x %d", c.fft_size, kAcqMaxSmemPoints);
-                return rc;
+                // sizes with prime factors > 7 (16 368 = 16.368 Msps x 1 ms, a standard front-end rate): chirp-z through M-point
+                // transforms; plain layout and the CFAR statistic only
+                FftPlan probe{};
+                if (c.code_layout == 0 && !c.bit_transition_flag && c.effective_fft_size == c.fft_size && c.consumed_samples == c.fft_size &&
+                    c.use_cfar && bluestein_size(static_cast<int>(c.fft_size), &probe) != 0)
+                    {
+                        use_bluestein = true;
+                        pl = FftPlan{};
+                        pl.n = static_cast<int>(c.fft_size);
+                        pl.n_total = pl.n;
+                        pl.n1 = 1;
+                    }
+                else
+                    {
+                        set_error("fft_size %u unsupported: prime factors must be 2,3,5,7 and fft_size <= 10 x %d (sizes with larger prime "
+                                  "factors are supported up to %d points for the plain layout with the CFAR statistic)",
+                            c.fft_size, kAcqMaxSmemPoints, 5 * kAcqMaxSmemPoints);
+                        return rc;
+                    }
             }
         B200_CUDA_TRY(cudaSetDevice(e->device));
         b200_acq* a = new (std::nothrow) b200_acq();
@@ -205,7 +411,19 @@ extern "C"
                     }
                 B200_CUDA_TRY(cudaMemsetAsync(a->grid, 0, sizeof(float) * ne * bins * slots, a->stream));
             }
-        int r2 = acq_launch_twiddles(a->tw, a->plan, a->stream);
+        int r2 = B200_OK;
+        if (use_bluestein)
+            {
+                r2 = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, 0, 0.f, 0.f, a->stream);
+                if (r2) return r2;
+                r2 = bluestein_setup(a);
+                if (r2) return r2;
+                r2 = bluestein_refresh_mult(a);
+                if (r2) return r2;
+                B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+                return B200_OK;
+            }
+        r2 = acq_launch_twiddles(a->tw, a->plan, a->stream);
         if (r2) return r2;
         r2 = acq_launch_wipeoff(a->wipe, static_cast<int>(n), static_cast<int>(bins), c.doppler_max, 0, c.doppler_step, 0, c.fs_in, 0, 0.f, 0.f, a->stream);
         if (r2) return r2;
@@ -229,6 +447,19 @@ extern "C"
         const b200_acq_conf& c = a->c;
         const size_t need = (c.code_layout == 1) ? c.fft_size / 2 : c.consumed_samples;
         B200_CUDA_TRY(cudaMemcpyAsync(a->code_stage, code_host, sizeof(float2) * need, cudaMemcpyHostToDevice, a->stream));
+        if (a->bl)
+            {
+                // CW = conj(DFT_N(code)) . w / M  (volk_32fc_conjugate_32fc of set_local_code :250, then the inverse chirp-z pre-multiplier)
+                b200_acq::Bluestein* b = a->bl;
+                const int n = static_cast<int>(c.fft_size);
+                int rcb = bluestein_forward_rows(a, a->code_stage, 0, b->chirp_conj, 0, 1, b->Xs);
+                if (rcb) return rcb;
+                rcb = acq_launch_rows_times_vector(b->Xs, n, b->chirp_M, n, 1, b->CW + static_cast<size_t>(slot) * n, n, 1, a->stream);
+                if (rcb) return rcb;
+                B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+                a->slot_set[slot] = 1;
+                return B200_OK;
+            }
         int rc = acq_launch_code_fft(a->code_stage, static_cast<int>(c.consumed_samples), static_cast<int>(c.code_layout),
             a->codes + static_cast<size_t>(slot) * c.fft_size, a->plan, a->tw, a->stream);
         if (rc) return rc;
@@ -247,6 +478,11 @@ extern "C"
         int rc = acq_launch_wipeoff(a->wipe, static_cast<int>(c.fft_size), static_cast<int>(c.num_doppler_bins), c.doppler_max,
             doppler_center, c.doppler_step, doppler_bias, c.fs_in, 0, 0.f, 0.f, a->stream);
         if (rc) return rc;
+        if (a->bl)
+            {
+                rc = bluestein_refresh_mult(a);
+                if (rc) return rc;
+            }
         B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
         return B200_OK;
     }
@@ -443,6 +679,7 @@ extern "C"
         if (!a) return B200_ERR_ARG;
         cudaSetDevice(a->e->device);
         if (a->stream) cudaStreamSynchronize(a->stream);
+        bluestein_free(a);
         cudaFree(a->tw);
         cudaFree(a->wipe);
         cudaFree(a->wipe2);

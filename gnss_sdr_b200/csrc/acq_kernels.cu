@@ -417,15 +417,17 @@ __device__ __forceinline__ float2 acq_source(const float2* __restrict__ in, cons
     return v;
 }
 
+// in_stride / wipe_stride: elements between the inputs / multiplier tables of consecutive rows (0 = one shared by all rows)
 template <int R>
 __global__ void acq_global_fwd_stage(const float2* __restrict__ in, int consumed, int layout, const float2* __restrict__ wipe,
-    float2* __restrict__ X, FftPlan pl, const float2* __restrict__ tw)
+    float2* __restrict__ X, FftPlan pl, const float2* __restrict__ tw, size_t in_stride, size_t wipe_stride)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int n2 = pl.n;
     if (j >= n2) return;
     const int d = blockIdx.y;
-    const float2* w = wipe ? wipe + static_cast<size_t>(d) * pl.n_total : nullptr;
+    const float2* w = wipe ? wipe + static_cast<size_t>(d) * wipe_stride : nullptr;
+    in += static_cast<size_t>(d) * in_stride;
     float2 v[R];
 #pragma unroll
     for (int q = 0; q < R; q++) v[q] = acq_source(in, w, j + q * n2, consumed, layout, pl.n_total);
@@ -590,6 +592,55 @@ __global__ void __launch_bounds__(256) acq_global_final_stage(const float2* __re
             st.sum = sm;
             st.pad = 0.f;
             partial[static_cast<size_t>(r) * gridDim.x + blockIdx.x] = st;
+        }
+}
+
+// ---- Bluestein (chirp-z) support: sizes the mixed-radix planner cannot factor (prime factors > 7, e.g. 16 368) --------
+// Final radix-n1 DIT stage of a two-level inverse transform whose first n_out natural-order outputs are multiplied by
+// post[k] and STORED (complex) instead of being reduced to statistics: out[r][k] = y[k] * post[k], k < n_out.
+template <int R>
+__global__ void __launch_bounds__(256) acq_global_final_store_stage(const float2* __restrict__ Z, FftPlan pl, const float2* __restrict__ tw,
+    const float2* __restrict__ post, int n_out, float2* __restrict__ out, size_t out_stride)
+{
+    const int r = blockIdx.y;
+    const int n2 = pl.n;
+    const float2* z = Z + static_cast<size_t>(r) * pl.n_total;
+    float2* o = out + static_cast<size_t>(r) * out_stride;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += gridDim.x * blockDim.x)
+        {
+            float2 v[R];
+#pragma unroll
+            for (int q = 0; q < R; q++) v[q] = z[q * n2 + j];
+            const float2 w1 = __ldg(tw + pl.tw_goff + j);
+            float2 wp = w1;
+#pragma unroll
+            for (int q = 1; q < R; q++)
+                {
+                    v[q] = cmul_conj(v[q], wp);
+                    if (q + 1 < R) wp = cmul(wp, w1);
+                }
+#pragma unroll
+            for (int q = 0; q < R; q++) v[q] = swap_ri(v[q]);
+            Bfly<R>::fwd(v);
+#pragma unroll
+            for (int q = 0; q < R; q++)
+                {
+                    const int k = j + q * n2;
+                    if (k < n_out) o[k] = cmul(swap_ri(v[q]), __ldg(post + k));
+                }
+        }
+}
+
+// out[r][i] = a[r][i] * b[i] (conj_a: conj(a[r][i]) * b[i]), i < n; rows r < rows
+__global__ void acq_rows_times_vector_kernel(const float2* __restrict__ a, size_t a_stride, const float2* __restrict__ b, int n, int conj_a,
+    float2* __restrict__ out, size_t out_stride)
+{
+    const int r = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        {
+            float2 x = a[static_cast<size_t>(r) * a_stride + i];
+            if (conj_a) x.y = -x.y;
+            out[static_cast<size_t>(r) * out_stride + i] = cmul(x, __ldg(b + i));
         }
 }
 
@@ -940,7 +991,7 @@ int acq_launch_code_fft(const float2* code, int consumed, int layout, float2* ou
     else
         {
             const dim3 g((pl.n + 255) / 256, 1);
-            rc = dispatch_radix(pl.n1, [&](auto R) { acq_global_fwd_stage<decltype(R)::value><<<g, 256, 0, st>>>(code, consumed, layout, nullptr, out, pl, tw); });
+            rc = dispatch_radix(pl.n1, [&](auto R) { acq_global_fwd_stage<decltype(R)::value><<<g, 256, 0, st>>>(code, consumed, layout, nullptr, out, pl, tw, 0, 0); });
             if (rc) return rc;
             acq_block_fft_kernel<<<dim3(pl.n1, 1), kAcqThreads, pl.n * sizeof(float2), st>>>(out, pl, tw, 1);
         }
@@ -962,7 +1013,7 @@ int acq_launch_fwd(const float2* in, int consumed, const float2* wipe, float2* X
     else
         {
             const dim3 g((pl.n + 255) / 256, bins);
-            rc = dispatch_radix(pl.n1, [&](auto R) { acq_global_fwd_stage<decltype(R)::value><<<g, 256, 0, st>>>(in, consumed, 0, wipe, X, pl, tw); });
+            rc = dispatch_radix(pl.n1, [&](auto R) { acq_global_fwd_stage<decltype(R)::value><<<g, 256, 0, st>>>(in, consumed, 0, wipe, X, pl, tw, 0, static_cast<size_t>(pl.n_total)); });
             if (rc) return rc;
             acq_block_fft_kernel<<<dim3(pl.n1, bins), kAcqThreads, pl.n * sizeof(float2), st>>>(X, pl, tw, 0);
         }
@@ -1023,6 +1074,72 @@ int acq_launch_finish_second_peak(const float* second_peak, int n_slots, b200_ac
 int acq_launch_sweep_best(const b200_acq_result* results, const unsigned int* prn_of_result, int n, b200_acq_peak* out, cudaStream_t st)
 {
     acq_sweep_best_kernel<<<1, 32, 0, st>>>(results, prn_of_result, n, out);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+// ---- Bluestein building blocks (acq_engine.cu composes them) --------------------------------------------------------
+// two-level plan for EXACTLY m points with a global radix n1 >= 2 even when m would fit shared memory (the chirp-z path is
+// written on the through-global-memory kernels only)
+int acq_plan_make_two_level(int m, FftPlan* pl)
+{
+    const int cand[7] = {2, 4, 8, 3, 5, 7, 10};
+    for (int n1 : cand)
+        {
+            if (m % n1) continue;
+            const int n2 = m / n1;
+            if (n2 > kAcqMaxSmemPoints || n2 < 2) continue;
+            if (acq_plan_make_smem(n2, pl, false) != B200_OK) continue;
+            pl->n1 = n1;
+            pl->n_total = m;
+            int off = 0, M = n2;
+            for (int st = 0; st < pl->n_stages; st++)
+                {
+                    M /= pl->radix[st];
+                    off += M;
+                }
+            pl->tw_goff = off;
+            return B200_OK;
+        }
+    return B200_ERR_RANGE;
+}
+
+// X[r] = FFT_M( pad( in[r * in_stride + i] * mult[r * mult_stride + i], i < consumed ) ), rows r < rows (two-level plan)
+int acq_launch_fwd_rows(const float2* in, size_t in_stride, int consumed, const float2* mult, size_t mult_stride, float2* X, int rows,
+    const FftPlan& pl, const float2* tw, cudaStream_t st)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    if (pl.n1 < 2) return B200_ERR_ARG;
+    const dim3 g((pl.n + 255) / 256, rows);
+    rc = dispatch_radix(pl.n1, [&](auto R) { acq_global_fwd_stage<decltype(R)::value><<<g, 256, 0, st>>>(in, consumed, 0, mult, X, pl, tw, in_stride, mult_stride); });
+    if (rc) return rc;
+    acq_block_fft_kernel<<<dim3(pl.n1, rows), kAcqThreads, pl.n * sizeof(float2), st>>>(X, pl, tw, 0);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+// out[r][k] = IFFT_M( X[r] . filt )[k] * post[k], k < n_out   (Z: rows x M workspace; one_slot_dev: device int == 0)
+int acq_launch_inverse_store_rows(const float2* X, const float2* filt, const int* one_slot_dev, int rows, const FftPlan& pl, const float2* tw,
+    float2* Z, const float2* post, int n_out, float2* out, size_t out_stride, cudaStream_t st)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    if (pl.n1 < 2) return B200_ERR_ARG;
+    acq_corr_block_kernel<<<dim3(pl.n1, rows), kAcqThreads, pl.n * sizeof(float2), st>>>(X, filt, one_slot_dev, rows, pl, tw, Z, 0, nullptr);
+    const int chunks = acq_final_chunks(pl);
+    rc = dispatch_radix(pl.n1, [&](auto R) {
+        acq_global_final_store_stage<decltype(R)::value><<<dim3(chunks, rows), 256, 0, st>>>(Z, pl, tw, post, n_out, out, out_stride);
+    });
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int acq_launch_rows_times_vector(const float2* a, size_t a_stride, const float2* b, int n, int conj_a, float2* out, size_t out_stride, int rows,
+    cudaStream_t st)
+{
+    acq_rows_times_vector_kernel<<<dim3((n + 255) / 256, rows), 256, 0, st>>>(a, a_stride, b, n, conj_a, out, out_stride);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }

@@ -116,5 +116,12 @@ int acq_launch_stats(const AcqRowStat* rowstat, int n_slots, int bins, int ne, i
     int doppler_step, unsigned int dwell_counter, int use_cfar, void* best, b200_acq_result* results, int step_two, float center2,
     float step2, float prev_input_power, cudaStream_t st);
 int acq_launch_finish_second_peak(const float* second_peak, int n_slots, b200_acq_result* results, cudaStream_t st);
+int acq_plan_make_two_level(int m, FftPlan* pl);
+int acq_launch_fwd_rows(const float2* in, size_t in_stride, int consumed, const float2* mult, size_t mult_stride, float2* X, int rows,
+    const FftPlan& pl, const float2* tw, cudaStream_t st);
+int acq_launch_inverse_store_rows(const float2* X, const float2* filt, const int* one_slot_dev, int rows, const FftPlan& pl, const float2* tw,
+    float2* Z, const float2* post, int n_out, float2* out, size_t out_stride, cudaStream_t st);
+int acq_launch_rows_times_vector(const float2* a, size_t a_stride, const float2* b, int n, int conj_a, float2* out, size_t out_stride, int rows,
+    cudaStream_t st);
 int acq_launch_sweep_best(const b200_acq_result* results, const unsigned int* prn_of_result, int n, b200_acq_peak* out, cudaStream_t st);
 }  // namespace b200

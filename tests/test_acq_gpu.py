@@ -246,8 +246,9 @@ def test_fft_round_trip_property_all_supported_radices(capi, engine, oracle):
 
 
 def test_acq_error_paths(capi, engine):
-    with pytest.raises(capi.B200Error):   # 16368 = 2^4*3*11*31: unsupported primes
-        capi.PcpsAcquisition(engine, fs_in=16368000, samples_per_ms=16368.0, samples_per_chip=16, doppler_max=5000, doppler_step=250)
+    with pytest.raises(capi.B200Error):   # 16368 = 2^4*3*11*31 goes through chirp-z, which has the CFAR statistic only
+        capi.PcpsAcquisition(engine, fs_in=16368000, samples_per_ms=16368.0, samples_per_chip=16, doppler_max=5000, doppler_step=250,
+                             use_CFAR_algorithm_flag=False)
     with pytest.raises(capi.B200Error):   # beyond 8 x 27648 points
         capi.PcpsAcquisition(engine, fs_in=300000000, samples_per_ms=300000.0, samples_per_chip=290, doppler_max=1000, doppler_step=500)
     acq = capi.PcpsAcquisition(engine, fs_in=4000000, samples_per_ms=4000.0, samples_per_chip=3, doppler_max=5000, doppler_step=250)
@@ -324,6 +325,62 @@ def test_two_level_fft_sizes(capi, engine, oracle, fs, sampled_ms, dmax, dstep, 
     ref_g = o.magnitude_grid[:, :acq.conf.effective_fft_size]
     assert np.max(np.abs(g - ref_g)) / ref_g.max() < 2e-5
     assert abs(want["doppler"] - svs[0]["doppler"]) <= max(dstep, 666 / sampled_ms)
+    acq.close()
+
+
+@pytest.mark.parametrize("fs,sampled_ms,dmax,dstep", [
+    (16.368e6, 1, 5000, 250),     # N = 16368 = 2^4 * 3 * 11 * 31   (the classic 16.368 Msps front end)  -> M = 32768
+    (5.456e6, 1, 5000, 500),      # N = 5456  = 2^4 * 11 * 31
+    (16.368e6, 2, 2000, 250),     # N = 32736 -> M = 65536: two-level M
+    (13e6, 1, 4000, 500),         # N = 13000 = 2^3 * 5^3 * 13
+])
+def test_chirp_z_sizes_with_large_prime_factors(capi, engine, oracle, fs, sampled_ms, dmax, dstep):
+    """fft_size with prime factors above 7: every N-point transform becomes a circular convolution with a chirp, done with
+    M-point transforms (M >= 2N - 1).  Same contract as the other sizes (exact indices, statistics 1e-4, grid 2e-5 of the
+    peak), plus two dwells and a Doppler-centre change through the same path."""
+    spms = fs / 1000.0
+    n = int(spms) * sampled_ms
+    spchip = int(fs / 1.023e6)
+    prn = 7
+    codes = {p: oracle.port.gps_ca_code(p) for p in (7, 21)}
+    svs = [dict(prn=7, doppler=dstep * round(0.6 * dmax / dstep) + 10.0, code_phase_chips=321.4, cn0=43.0, phase0=1.0),
+           dict(prn=21, doppler=-0.3 * dmax, code_phase_chips=77.7, cn0=43.0, phase0=2.0)]
+    iq = make_iq(codes, fs, 2 * n, svs, seed=int(fs / 1e3) + sampled_ms)
+    kw = dict(sampled_ms=sampled_ms, ms_per_code=sampled_ms) if sampled_ms > 1 else {}
+    o = _oracle_acq(oracle, fs, spms, spchip, dmax, dstep, prn, iq, cfar=True, dwells=2, **kw)
+    want = o.acquisition_core(iq[:n])
+    acq = capi.PcpsAcquisition(engine, fs_in=int(fs), samples_per_ms=spms, samples_per_chip=spchip, doppler_max=dmax,
+                               doppler_step=dstep, use_CFAR_algorithm_flag=True, keep_grid=True, max_dwells=2, n_code_slots=2, **kw)
+    assert acq.conf.fft_size == n
+    local = oracle.port.gps_ca_code_complex_sampled(prn, int(fs))
+    acq.set_local_code(1, np.tile(local, sampled_ms))
+    acq.set_local_code(0, np.tile(oracle.port.gps_ca_code_complex_sampled(21, int(fs)), sampled_ms))
+    both = acq.search(iq[:n], [0, 1])
+    got = both[1]
+    assert int(got["index_time"]) % int(spms) == want["index_time"] % int(spms)
+    assert int(got["index_doppler"]) == want["index_doppler"]
+    assert int(got["doppler"]) == want["doppler"]
+    assert abs(got["grid_maximum"] - want["grid_maximum"]) / want["grid_maximum"] < 1e-4
+    assert abs(got["test_statistics"] - want["test_statistics"]) / want["test_statistics"] < 1e-4
+    assert abs(got["input_power"] - want["input_power"]) / want["input_power"] < 1e-4
+    g = acq.read_grid(1)
+    ref_g = o.magnitude_grid[:, :acq.conf.effective_fft_size]
+    assert np.max(np.abs(g - ref_g)) / ref_g.max() < 2e-5
+    assert abs(want["doppler"] - svs[0]["doppler"]) <= max(dstep, 666 / sampled_ms)
+    assert abs(int(both[0]["doppler"]) - svs[1]["doppler"]) <= max(dstep, 666 / sampled_ms)
+    # second dwell accumulates on the grid
+    o.num_noncoherent_integrations_counter = 1   # keep accumulating whatever the threshold decided
+    want2 = o.acquisition_core(iq[n:])
+    got2 = acq.search(iq[n:], [1], dwell_counter=2)[0]
+    assert int(got2["index_doppler"]) == want2["index_doppler"]
+    assert abs(got2["test_statistics"] - want2["test_statistics"]) / want2["test_statistics"] < 1e-4
+    # assisted acquisition: moving the Doppler centre rebuilds the chirped wipe-off rows
+    o3 = _oracle_acq(oracle, fs, spms, spchip, dmax, dstep, prn, iq, cfar=True, center=875, **kw)
+    want3 = o3.acquisition_core(iq[:n])
+    acq.set_doppler_center(875)
+    got3 = acq.search(iq[:n], [1])[0]
+    assert int(got3["doppler"]) == want3["doppler"]
+    assert abs(got3["test_statistics"] - want3["test_statistics"]) / want3["test_statistics"] < 1e-4
     acq.close()
 
 

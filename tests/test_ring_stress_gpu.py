@@ -59,7 +59,9 @@ def build_variant(stages, stress):
     from gnss_sdr_b200 import build as b
     os.makedirs(os.path.join(ROOT, "gnss_sdr_b200", "variants"), exist_ok=True)
     out = os.path.join(ROOT, "gnss_sdr_b200", "variants", f"libb200gnss_ring{stages}_{'stress' if stress else 'plain'}.so")
-    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(os.path.join(ROOT, "gnss_sdr_b200", "csrc", "trk_shared_kernel.cu")):
+    import glob
+    newest = max(os.path.getmtime(f) for pat in ("csrc/*", "../include/*.h") for f in glob.glob(os.path.join(ROOT, "gnss_sdr_b200", pat)))
+    if not os.path.exists(out) or os.path.getmtime(out) < newest:
         b.build(extra=[f"-DSH_STAGES={stages}", f"-DSH_STRESS={1 if stress else 0}"], out=out)
     return out
 

@@ -722,7 +722,8 @@ def test_push_at_restarts_when_the_stream_starts_over(capi, oracle):
     iq = (rng.integers(-50, 50, 40000) + 1j * rng.integers(-50, 50, 40000)).astype(np.complex64)
     eng.iq_create(1, 1 << 14)                       # 16384-sample ring
     assert eng.iq_push_at(1, 5_000_000, iq[:12000]) == 12000
-    assert eng.iq_push_at(1, 5_012_000, iq[12000:30000]) == 18000      # wraps: the ring now holds [5 013 616, 5 030 000)
+    assert eng.iq_push_at(1, 5_012_000, iq[12000:22000]) == 10000
+    assert eng.iq_push_at(1, 5_022_000, iq[22000:30000]) == 8000       # wrapped: the ring now holds [5 013 616, 5 030 000)
     assert eng.iq_window(1) == (5_030_000 - 16384, 5_030_000)
     assert eng.iq_push_at(1, 0, iq[:8000]) == 8000                     # the stream starts over
     assert eng.iq_window(1) == (0, 8000)
