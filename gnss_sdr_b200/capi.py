@@ -57,6 +57,7 @@ _SIGS = {
     "b200_iq_push": ([_vp, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_push_at": ([_vp, C.c_int, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_window": ([_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
+    "b200_iq_forget": ([_vp, C.c_int], C.c_int),
     "b200_iq_refill": ([_vp, C.c_int, _vp, C.c_uint64, C.c_uint64], C.c_int),
     "b200_trk_set_taps": ([_vp, _vp], C.c_int),
     "b200_trk_set_local_code_and_taps_cplx": ([_vp, C.c_int, _vp, _vp], C.c_int),
@@ -268,6 +269,9 @@ class Engine:
 
     def iq_refill_ptr(self, band: int, host_ptr: int, n: int, first_index: int = 0):
         _chk(lib.b200_iq_refill(self.h, band, host_ptr, n, first_index), "b200_iq_refill")
+
+    def iq_forget(self, band: int):
+        _chk(lib.b200_iq_forget(self.h, band), "b200_iq_forget")
 
     def iq_window(self, band: int):
         lo, hi = C.c_uint64(0), C.c_uint64(0)

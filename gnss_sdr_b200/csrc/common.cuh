@@ -22,6 +22,7 @@ const char* get_error();
             if (_e != cudaSuccess)                                                                     \
                 {                                                                                      \
                     ::b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+                    (void)cudaGetLastError(); /* reported here: must not surface again after a later launch */ \
                     return B200_ERR_CUDA;                                                              \
                 }                                                                                      \
         }                                                                                              \

@@ -402,6 +402,17 @@ extern "C"
         return rc;
     }
 
+    int b200_iq_forget(b200_engine* e, int band)
+    {
+        if (!e || band < 0 || band >= kMaxBands) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> plk(e->push_mu[band]);
+        std::lock_guard<std::mutex> lk(e->mu);
+        Band& b = e->bands[band];
+        if (!b.in_use || b.attached) return B200_ERR_STATE;
+        b.valid_from = b.write_index;
+        return B200_OK;
+    }
+
     int b200_iq_window(b200_engine* e, int band, uint64_t* valid_from, uint64_t* write_index)
     {
         if (!e || band < 0 || band >= kMaxBands) return B200_ERR_ARG;

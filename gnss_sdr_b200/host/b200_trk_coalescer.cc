@@ -36,6 +36,7 @@ Trk_Coalescer::Trk_Coalescer(b200_engine* engine) : d_engine(engine), d_slots(ne
 {
     for (auto& w : d_band_written) w.store(0);
     for (auto& w : d_band_lo) w.store(0);
+    for (auto& w : d_band_active) w.store(0);
     if (const char* env = std::getenv("B200_COALESCE_WINDOW_US")) d_window_us = std::atoi(env);
     d_thread = std::thread([this] { tick_loop(); });
 }
@@ -101,11 +102,39 @@ int Trk_Coalescer::open_channel(int band, int n_correlators)
 }
 
 
+// A channel starts offering samples.  When it is the only active one of its band, nothing says that the stream it is in
+// continues the one the band last saw (a flowgraph restarted in the same process starts its sample counter over): what
+// the band holds is forgotten, and the channel's own push refills it.  Never loses data a channel needs - every channel
+// offers its whole epoch before it posts.
+void Trk_Coalescer::activate(Slot& s, bool stream_may_be_new)
+{
+    std::lock_guard<std::mutex> lk(d_band_mu[s.band]);
+    if (s.active.exchange(true)) return;
+    d_n_active.fetch_add(1);
+    if (d_band_active[s.band].fetch_add(1) == 0 && stream_may_be_new)
+        {
+            d_band_written[s.band].store(0, std::memory_order_release);
+            d_band_lo[s.band].store(0, std::memory_order_release);
+            b200_iq_forget(d_engine, s.band);
+        }
+}
+
+
+void Trk_Coalescer::deactivate(Slot& s)
+{
+    if (s.active.exchange(false))
+        {
+            d_n_active.fetch_sub(1);
+            d_band_active[s.band].fetch_sub(1);
+        }
+}
+
+
 void Trk_Coalescer::idle(int id)
 {
     Slot* s = slot_of(id);
     if (s == nullptr) return;
-    if (s->active.exchange(false)) d_n_active.fetch_sub(1);
+    deactivate(*s);
     d_cv_space[s->band].notify_all();
     d_posted.notify_all();  // the tick thread re-evaluates how many posts it is waiting for
 }
@@ -166,7 +195,7 @@ bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* 
     if (s == nullptr) return false;
     const int band = s->band;
     s->cursor.store(abs_index, std::memory_order_relaxed);
-    if (!s->active.exchange(true)) d_n_active.fetch_add(1);
+    if (!s->active.load(std::memory_order_acquire)) activate(*s, true);
     d_samples_offered.fetch_add(n, std::memory_order_relaxed);
     // fast path: somebody has already put these samples into the band (every block of the flowgraph offers the same stream)
     if (abs_index >= d_band_lo[band].load(std::memory_order_acquire) && abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
@@ -184,8 +213,7 @@ bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* 
                     for (int i = 0; i < ns; i++)
                         {
                             Slot& o = d_slots[i];
-                            if (o.band == band && o.active.load() && abs_index + n - o.cursor.load() > cap - cap / 8)
-                                if (o.active.exchange(false)) d_n_active.fetch_sub(1);
+                            if (o.band == band && o.active.load() && abs_index + n - o.cursor.load() > cap - cap / 8) deactivate(o);
                         }
                 }
         }
@@ -227,7 +255,7 @@ bool Trk_Coalescer::post(int id, uint64_t abs_index, int n, float rem_carrier_ph
     s->item.code_phase_step_chips = code_phase_step_chips;
     s->item.code_phase_rate_step_chips = code_phase_rate_step_chips;
     s->cursor.store(abs_index, std::memory_order_relaxed);
-    if (!s->active.exchange(true)) d_n_active.fetch_add(1);
+    if (!s->active.load(std::memory_order_acquire)) activate(*s, false);
     s->t_post = std::chrono::steady_clock::now();
     s->state.store(POSTED, std::memory_order_release);
     // a slower channel may have been waiting for this cursor to move
@@ -318,8 +346,7 @@ void Trk_Coalescer::tick_loop()
                         {
                             Slot& s = d_slots[i];
                             const int st = s.state.load();
-                            if (s.active.load() && st != IN_FLIGHT && st != POSTED)
-                                if (s.active.exchange(false)) d_n_active.fetch_sub(1);
+                            if (s.active.load() && st != IN_FLIGHT && st != POSTED) deactivate(s);
                         }
                 }
             const auto t0 = std::chrono::steady_clock::now();

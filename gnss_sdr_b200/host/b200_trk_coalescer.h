@@ -104,6 +104,8 @@ private:
         std::chrono::steady_clock::time_point t_post;
     };
     void tick_loop();
+    void activate(Slot& s, bool stream_may_be_new);
+    void deactivate(Slot& s);
     Slot* slot_of(int id);
     bool fits(int band, uint64_t abs_index, uint64_t n) const;
 
@@ -112,6 +114,7 @@ private:
     std::atomic<int> d_n_slots{0};          // highest id in use + 1
     std::atomic<int> d_posted{0};
     std::atomic<int> d_n_active{0};
+    std::atomic<int> d_band_active[kMaxBands];         // active channels per band
     std::atomic<bool> d_stop{false};
     std::atomic<uint64_t> d_band_written[kMaxBands];   // samples [lo, written) are in the band (fast path of push)
     std::atomic<uint64_t> d_band_lo[kMaxBands];

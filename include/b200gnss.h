@@ -85,6 +85,11 @@ extern "C"
     int b200_iq_push_at(b200_engine* e, int band, uint64_t abs_index, const b200_cf32* host, uint64_t n, uint64_t* n_new);
     /* [valid_from, write_index): absolute indices of the samples a work item may address right now */
     int b200_iq_window(b200_engine* e, int band, uint64_t* valid_from, uint64_t* write_index);
+    /* Declare what the band holds stale (the window becomes empty; the write index stays).  For hosts that start a new
+     * stream whose indices overlap the previous one's (a flowgraph restarted inside one process): without this,
+     * b200_iq_push_at would answer "already there" for indices the old stream had covered.  Launches already queued keep
+     * reading what they were given. */
+    int b200_iq_forget(b200_engine* e, int band);
     /* Same for front ends that deliver interleaved 16-bit / 8-bit (I,Q) integers (lv_16sc_t / lv_8sc_t):
      * the raw integers cross PCIe and are converted to float on the device, replacing the CPU
      * adapters src/algorithms/data_type_adapter/gnuradio_blocks/cshort_to_gr_complex.cc:48

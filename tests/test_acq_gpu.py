@@ -343,8 +343,8 @@ def test_chirp_z_sizes_with_large_prime_factors(capi, engine, oracle, fs, sample
     spchip = int(fs / 1.023e6)
     prn = 7
     codes = {p: oracle.port.gps_ca_code(p) for p in (7, 21)}
-    svs = [dict(prn=7, doppler=dstep * round(0.6 * dmax / dstep) + 10.0, code_phase_chips=321.4, cn0=43.0, phase0=1.0),
-           dict(prn=21, doppler=-0.3 * dmax, code_phase_chips=77.7, cn0=43.0, phase0=2.0)]
+    svs = [dict(prn=7, doppler=dstep * round(0.6 * dmax / dstep) + 10.0, code_phase_chips=321.4, cn0=47.0, phase0=1.0),
+           dict(prn=21, doppler=-dstep * round(0.3 * dmax / dstep) + 20.0, code_phase_chips=77.7, cn0=47.0, phase0=2.0)]
     iq = make_iq(codes, fs, 2 * n, svs, seed=int(fs / 1e3) + sampled_ms)
     kw = dict(sampled_ms=sampled_ms, ms_per_code=sampled_ms) if sampled_ms > 1 else {}
     o = _oracle_acq(oracle, fs, spms, spchip, dmax, dstep, prn, iq, cfar=True, dwells=2, **kw)

@@ -728,6 +728,13 @@ def test_push_at_restarts_when_the_stream_starts_over(capi, oracle):
     assert eng.iq_push_at(1, 0, iq[:8000]) == 8000                     # the stream starts over
     assert eng.iq_window(1) == (0, 8000)
     assert eng.iq_push_at(1, 4000, iq[4000:10000]) == 2000
+    # a new stream whose indices overlap the old one's cannot be told apart by index: the host says so (b200_iq_forget)
+    assert eng.iq_push_at(1, 2000, iq[20000:24000]) == 0               # "already there" - the old samples
+    eng.iq_forget(1)
+    assert eng.iq_window(1) == (10000, 10000)
+    assert eng.iq_push_at(1, 2000, iq[20000:24000]) == 4000
+    assert eng.iq_window(1) == (2000, 6000)
+    assert eng.iq_push_at(1, 0, iq[:10000]) == 10000                   # and back (older index: restart)
     code = np.where(rng.integers(0, 2, 1023) > 0, 1.0, -1.0).astype(np.float32)
     ch = eng.channel_create(1, 3)
     eng.channel_set_code(ch, code, [-0.5, 0.0, 0.5])
