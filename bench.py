@@ -203,7 +203,7 @@ def bind_to_gpu_numa(torch, local_rank):
         return {"numa_node": None, "bound": False, "why": repr(ex)}
 
 
-def run_trk_config(torch, capi, dev, name, fs, groups, seconds, steps=20, warmup=3, layout="shared", stream=None):
+def run_trk_config(torch, capi, dev, name, fs, groups, seconds, steps=20, warmup=3, layout="shared", stream=None, kernel=None):
     """Device-resident throughput of the tracking correlator on one workload.
     groups: list of dict(n_ch, N, L, shifts, table_rate[, pilot_data]); table_rate = table values per second;
     pilot_data=True adds, per channel, the 1-tap data-prompt correlator of a tracked pilot (dll_pll_veml_tracking.cc:1246-1256).
@@ -211,6 +211,8 @@ def run_trk_config(torch, capi, dev, name, fs, groups, seconds, steps=20, warmup
     region of a channels-times-larger band, so that 8 B per channel-sample really cross HBM (the roofline run of SURVEY 8d)."""
     st = stream or torch.cuda.current_stream(dev)
     eng = capi.Engine(dev.index, st.cuda_stream)
+    if kernel is not None:
+        eng.trk_kernel_choice(kernel)
     n_ch_total = sum(g["n_ch"] for g in groups)
     n_iq = int(fs * seconds)
     g = torch.Generator(device=dev)
@@ -290,8 +292,12 @@ def other_configs(torch, capi, dev, stream, steps):
         50e6, [dict(n_ch=12, N=50000, L=1023, shifts=SHIFTS, table_rate=1.023e6),
                dict(n_ch=12, N=200000, L=8184, shifts=E1_SHIFTS, table_rate=2 * 1.023e6),
                dict(n_ch=8, N=50000, L=10230, shifts=SHIFTS, table_rate=10.23e6)], 1.0)
-    leg("C2_distinct_iq", "C2 arithmetic, but every (channel, epoch) reads its own samples: 32 ch x 25 Msps x 0.5 s from a 3.2 GB band",
-        FS, [dict(n_ch=N_CH, N=EPOCH, L=1023, shifts=SHIFTS, table_rate=1.023e6)], 0.5, layout="distinct")
+    # nothing is shared in this layout: the per-item kernel (one CTA per item) is the one b200_trk_submit picks for it (it sees
+    # the items); b200_trk_batch_dev cannot look at device-resident items, so the choice is made explicitly here
+    leg("C2_distinct_iq", "C2 arithmetic, but every (channel, epoch) reads its own samples: 32 ch x 25 Msps x 0.5 s from a 3.2 GB band; per-item kernel",
+        FS, [dict(n_ch=N_CH, N=EPOCH, L=1023, shifts=SHIFTS, table_rate=1.023e6)], 0.5, layout="distinct", kernel=0)
+    leg("C2_distinct_iq_shared_window_kernel", "the same through the shared-window kernel (no window to share: each warp streams its own item)",
+        FS, [dict(n_ch=N_CH, N=EPOCH, L=1023, shifts=SHIFTS, table_rate=1.023e6)], 0.5, layout="distinct", kernel=1)
     return out
 
 
@@ -1031,6 +1037,7 @@ def main():
         d = extra["C2_distinct_iq"]
         hbm_true = {"workload": d["workload"], "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s", "frac": d["algorithmic_GBps"] / peak,
                     "ms_per_launch": d["ms_per_step"], "value": d["value"],
+                    "kernel": "trk_correlate_kernel<3> (per-item)",
                     "note": "band = channels x samples: no sharing between channels, DRAM traffic == algorithmic bytes (+ items/taps)"}
     roofline = {"bound": "hbm", "kernel": "trk_shared_kernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic_bytes(),

@@ -58,6 +58,7 @@ _SIGS = {
     "b200_iq_push_at": ([_vp, C.c_int, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_window": ([_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], C.c_int),
     "b200_iq_forget": ([_vp, C.c_int], C.c_int),
+    "b200_trk_kernel_choice": ([_vp, C.c_int], C.c_int),
     "b200_iq_refill": ([_vp, C.c_int, _vp, C.c_uint64, C.c_uint64], C.c_int),
     "b200_trk_set_taps": ([_vp, _vp], C.c_int),
     "b200_trk_set_local_code_and_taps_cplx": ([_vp, C.c_int, _vp, _vp], C.c_int),
@@ -117,6 +118,7 @@ _SIGS.update({
     "b200_acq_search_step_two": ([_vp, _vp, C.c_uint32, C.c_uint32, C.c_float, _vp], C.c_int),
     "b200_acq_search_dev": ([_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
     "b200_acq_read_grid": ([_vp, C.c_uint32, _vp], C.c_int),
+    "b200_acq_selftest_dft": ([_vp, _vp, _vp], C.c_int),
     "b200_acq_read_wipeoffs": ([_vp, _vp], C.c_int),
     "b200_acq_destroy": ([_vp], C.c_int),
 })
@@ -269,6 +271,9 @@ class Engine:
 
     def iq_refill_ptr(self, band: int, host_ptr: int, n: int, first_index: int = 0):
         _chk(lib.b200_iq_refill(self.h, band, host_ptr, n, first_index), "b200_iq_refill")
+
+    def trk_kernel_choice(self, mode: int):
+        _chk(lib.b200_trk_kernel_choice(self.h, mode), "b200_trk_kernel_choice")
 
     def iq_forget(self, band: int):
         _chk(lib.b200_iq_forget(self.h, band), "b200_iq_forget")
@@ -537,6 +542,13 @@ class PcpsAcquisition:
     def sweep_best_dev(self, results_dev_ptr: int, prn_of_result_dev_ptr: int, n_results: int, peak_dev_ptr: int):
         """one 16-byte b200_acq_peak record of the sweep, written on the device (no host synchronisation)"""
         _chk(lib.b200_acq_sweep_best_dev(self.h, results_dev_ptr, prn_of_result_dev_ptr, n_results, peak_dev_ptr), "b200_acq_sweep_best_dev")
+
+    def selftest_dft(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        assert x.size == self.conf.fft_size
+        out = np.empty(x.size, np.complex64)
+        _chk(lib.b200_acq_selftest_dft(self.h, x.ctypes.data, out.ctypes.data), "b200_acq_selftest_dft")
+        return out
 
     def read_grid(self, slot: int) -> np.ndarray:
         g = np.empty((self.conf.num_doppler_bins, self.conf.effective_fft_size), np.float32)

@@ -357,7 +357,7 @@ extern "C"
                         return rc;
                     }
             }
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         b200_acq* a = new (std::nothrow) b200_acq();
         if (!a) return B200_ERR_NOMEM;
         a->e = e;
@@ -443,7 +443,7 @@ extern "C"
     int b200_acq_set_local_code(b200_acq* a, uint32_t slot, const b200_cf32* code_host)
     {
         if (!a || !code_host || slot >= a->c.n_code_slots) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         const b200_acq_conf& c = a->c;
         const size_t need = (c.code_layout == 1) ? c.fft_size / 2 : c.consumed_samples;
         B200_CUDA_TRY(cudaMemcpyAsync(a->code_stage, code_host, sizeof(float2) * need, cudaMemcpyHostToDevice, a->stream));
@@ -471,7 +471,7 @@ extern "C"
     int b200_acq_set_doppler_center(b200_acq* a, int32_t doppler_center, int32_t doppler_bias)
     {
         if (!a) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         a->doppler_center = doppler_center;
         a->doppler_bias = doppler_bias;
         const b200_acq_conf& c = a->c;
@@ -495,7 +495,7 @@ extern "C"
                 set_error("a search is already in flight on this acquisition object: call b200_acq_search_wait");
                 return B200_ERR_STATE;
             }
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         if (!a->in_pin) B200_CUDA_TRY(cudaMallocHost(&a->in_pin, sizeof(float2) * a->c.fft_size));
         if (!a->done) B200_CUDA_TRY(cudaEventCreateWithFlags(&a->done, cudaEventDisableTiming));
         // the caller's buffer is free as soon as this returns: stage it in pinned memory so that the copy is truly asynchronous
@@ -518,7 +518,7 @@ extern "C"
                 set_error("no search in flight on this acquisition object");
                 return B200_ERR_STATE;
             }
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         B200_CUDA_TRY(cudaEventSynchronize(a->done));
         std::memcpy(results_host, a->results_pin, sizeof(b200_acq_result) * a->pending_slots);
         a->pending = false;
@@ -562,7 +562,7 @@ extern "C"
                 set_error("a search is already in flight on this acquisition object: call b200_acq_search_wait");
                 return B200_ERR_STATE;
             }
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         int rc = upload_i16(a, in_host_iq);
         if (rc) return rc;
         rc = search_impl(a, a->in_dev, slots, n_slots, dwell_counter, a->results_dev);
@@ -577,7 +577,7 @@ extern "C"
         b200_acq_result* result_host)
     {
         if (!a || !in_host_iq || !result_host) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         int rc = upload_i16(a, in_host_iq);
         if (rc) return rc;
         rc = search_impl(a, a->in_dev, &slot, 1, dwell_counter, a->results_dev, 1, prev_input_power);
@@ -596,7 +596,7 @@ extern "C"
                 set_error("step-two bins %u exceed the grid's %u rows", num_doppler_bins_step2, a->c.num_doppler_bins);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         if (!a->wipe2 || a->bins2 < num_doppler_bins_step2)
             {
                 B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
@@ -617,7 +617,7 @@ extern "C"
         b200_acq_result* result_host)
     {
         if (!a || !in_host || !result_host) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         B200_CUDA_TRY(cudaMemcpyAsync(a->in_dev, in_host, sizeof(float2) * a->c.consumed_samples, cudaMemcpyHostToDevice, a->stream));
         int rc = search_impl(a, a->in_dev, &slot, 1, dwell_counter, a->results_dev, 1, prev_input_power);
         if (rc) return rc;
@@ -631,7 +631,7 @@ extern "C"
         uint32_t dwell_counter, b200_acq_result* results_dev)
     {
         if (!a || !in_dev || !results_dev) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         // (search_impl synchronises by itself when - and only when - the slot list changed and slot_pin must be rewritten; a
         // repeated sweep over the same slots issues no host synchronisation and can be captured in a CUDA graph)
         return search_impl(a, reinterpret_cast<const float2*>(in_dev), slots_host, n_slots, dwell_counter, results_dev);
@@ -650,6 +650,24 @@ extern "C"
         return rc;
     }
 
+    int b200_acq_selftest_dft(b200_acq* a, const b200_cf32* in_host, b200_cf32* out_host)
+    {
+        if (!a || !in_host || !out_host) return B200_ERR_ARG;
+        if (!a->bl)
+            {
+                set_error("selftest_dft: not a chirp-z object");
+                return B200_ERR_STATE;
+            }
+        B200_ENTER_DEVICE(a->e->device);
+        const size_t n = a->c.fft_size;
+        B200_CUDA_TRY(cudaMemcpyAsync(a->code_stage, in_host, sizeof(float2) * n, cudaMemcpyHostToDevice, a->stream));
+        const int rc = bluestein_forward_rows(a, a->code_stage, 0, a->bl->chirp_conj, 0, 1, a->bl->Xs);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaMemcpyAsync(out_host, a->bl->Xs, sizeof(float2) * n, cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return B200_OK;
+    }
+
     int b200_acq_read_grid(b200_acq* a, uint32_t slot, float* grid_host)
     {
         if (!a || !grid_host || slot >= a->c.n_code_slots) return B200_ERR_ARG;
@@ -658,7 +676,7 @@ extern "C"
                 set_error("no magnitude grid: create with keep_grid or max_dwells > 1");
                 return B200_ERR_STATE;
             }
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         const size_t row = static_cast<size_t>(a->c.num_doppler_bins) * a->c.effective_fft_size;
         B200_CUDA_TRY(cudaMemcpyAsync(grid_host, a->grid + row * slot, sizeof(float) * row, cudaMemcpyDeviceToHost, a->stream));
         B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
@@ -668,7 +686,7 @@ extern "C"
     int b200_acq_read_wipeoffs(b200_acq* a, b200_cf32* wipe_host)
     {
         if (!a || !wipe_host) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(a->e->device));
+        B200_ENTER_DEVICE(a->e->device);
         B200_CUDA_TRY(cudaMemcpyAsync(wipe_host, a->wipe, sizeof(float2) * a->c.fft_size * a->c.num_doppler_bins, cudaMemcpyDeviceToHost, a->stream));
         B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
         return B200_OK;

@@ -176,7 +176,7 @@ extern "C"
                 set_error("fine Doppler: 10 x %u points unsupported (prime factors 2,3,5,7; 10 x fft_size <= 10 x %d)", fft_size, kAcqMaxSmemPoints);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         b200_acq_fine* f = new (std::nothrow) b200_acq_fine();
         if (!f) return B200_ERR_NOMEM;
         f->e = e;
@@ -228,7 +228,7 @@ extern "C"
     {
         if (!f || !buffer_10ms_host || !code_replica_host || !index_freq) return B200_ERR_ARG;
         std::lock_guard<std::mutex> lk(f->e->mu);
-        B200_CUDA_TRY(cudaSetDevice(f->e->device));
+        B200_ENTER_DEVICE(f->e->device);
         B200_CUDA_TRY(cudaMemcpyAsync(f->in_dev, buffer_10ms_host, sizeof(float2) * f->m, cudaMemcpyHostToDevice, f->stream));
         B200_CUDA_TRY(cudaMemcpyAsync(f->code_dev, code_replica_host, sizeof(float2) * f->n1ms, cudaMemcpyHostToDevice, f->stream));
         const dim3 g((f->m + 255) / 256, kZeroPadding);
@@ -252,7 +252,7 @@ extern "C"
     {
         if (!f || !mag_host) return B200_ERR_ARG;
         std::lock_guard<std::mutex> lk(f->e->mu);
-        B200_CUDA_TRY(cudaSetDevice(f->e->device));
+        B200_ENTER_DEVICE(f->e->device);
         std::vector<float2> x(static_cast<size_t>(f->m) * kZeroPadding);
         B200_CUDA_TRY(cudaMemcpyAsync(x.data(), f->X, sizeof(float2) * x.size(), cudaMemcpyDeviceToHost, f->stream));
         B200_CUDA_TRY(cudaStreamSynchronize(f->stream));

@@ -28,6 +28,17 @@ const char* get_error();
         }                                                                                              \
     while (0)
 
+// First statement of every entry point that touches the device.  The runtime keeps ONE last-error slot per host thread,
+// shared with every other CUDA user in the process (torch leaves "invalid device ordinal" there while it initialises): an
+// error somebody else left must not be reported by the cudaGetLastError() after our next launch.
+#define B200_ENTER_DEVICE(dev)              \
+    do                                      \
+        {                                   \
+            (void)cudaGetLastError();       \
+            B200_CUDA_TRY(cudaSetDevice(dev)); \
+        }                                   \
+    while (0)
+
 // Function attributes (opt-in dynamic shared memory) are per device: remember per device, thread-safe, which
 // kernels have been prepared.  Usage:
 //   static DeviceOnce once;  const int d = once.begin();  if (d >= 0) { cudaFuncSetAttribute(...); once.done(d); }

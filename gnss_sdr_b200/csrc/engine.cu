@@ -149,7 +149,7 @@ extern "C"
                 set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
                 return B200_ERR_NODEV;
             }
-        B200_CUDA_TRY(cudaSetDevice(device));
+        B200_ENTER_DEVICE(device);
         b200_engine* e = new (std::nothrow) b200_engine();
         if (!e) return B200_ERR_NOMEM;
         e->device = device;
@@ -259,7 +259,7 @@ extern "C"
     {
         if (!e || band < 0 || band >= kMaxBands || capacity_samples == 0) return B200_ERR_ARG;
         std::lock_guard<std::mutex> lk(e->mu);
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         Band& b = e->bands[band];
         if (b.dev)
             {
@@ -301,7 +301,7 @@ extern "C"
                 set_error("push of %llu samples exceeds ring capacity %llu", (unsigned long long)n, b.capacity);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         if (first_index) *first_index = b.write_index;
         // copies run on the copy stream; later launches on the compute stream wait on copy_done.
         // (Overwriting samples that an in-flight launch still reads is the caller's ring-sizing
@@ -332,7 +332,7 @@ extern "C"
                 set_error("push of %llu samples exceeds ring capacity %llu", (unsigned long long)n, b.capacity);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         if (first_index) *first_index = b.write_index;
         const unsigned long long bytes = n * 2ULL * static_cast<unsigned long long>(bytes_per_component);
         const int k = b.raw_next;
@@ -465,7 +465,7 @@ extern "C"
         }
         if (chunk_samples == 0) chunk_samples = 1ULL << 20;
         if (chunk_samples > capacity / 2) chunk_samples = capacity / 2 ? capacity / 2 : 1;
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         FILE* f = std::fopen(path, "rb");
         if (!f)
             {
@@ -546,7 +546,7 @@ extern "C"
         Band& b = e->bands[band];
         if (b.dev)
             {
-                B200_CUDA_TRY(cudaSetDevice(e->device));
+                B200_ENTER_DEVICE(e->device);
                 B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
                 B200_CUDA_TRY(cudaFree(b.dev));
                 b.dev = nullptr;
@@ -578,7 +578,7 @@ extern "C"
                 set_error("refill of %llu samples exceeds the attached buffer (%llu)", (unsigned long long)n, b.capacity);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         // same ordering as b200_iq_push: the copy runs on the copy stream, later launches on the compute stream wait for it;
         // overwriting samples an in-flight launch still reads is the caller's double-buffering responsibility
         if (n) B200_CUDA_TRY(cudaMemcpyAsync(const_cast<float2*>(b.base), host, n * sizeof(float2), cudaMemcpyHostToDevice, e->copy_stream));
@@ -622,7 +622,7 @@ extern "C"
         if (!e || !local_code_in || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
         std::lock_guard<std::mutex> lk(e->mu);
         if (channel_id < 0 || channel_id >= static_cast<int>(e->chans.size())) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         Channel& c = e->chans[channel_id];
         // a new table may be read by launches already queued: allocate fresh if it must grow
         if (code_length_chips > c.code_cap)
@@ -660,9 +660,12 @@ extern "C"
     }
 
     // caller holds e->mu
-    static int batch_dev_impl(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices)
+    // layout_hint: 1 = consecutive items overlap in the band (a receiver's channels on one stream), 0 = they do not (every
+    // item reads its own samples: nothing to share, the per-item kernel streams them faster), -1 = unknown (device items)
+    static int batch_dev_impl(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices,
+        int layout_hint = -1)
     {
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         int rc = upload_tables(e);
         if (rc) return rc;
         if (slices < 1) slices = 1;
@@ -674,7 +677,7 @@ extern "C"
                 e->shared_mode = env ? std::atoi(env) : 2;  // 2 = automatic
             }
         const bool shared_legal = (e->taps_uniform == 1 || e->taps_uniform == 3 || e->taps_uniform == 5) && !e->any_high_dyn && slices == 1;
-        const bool use_shared = shared_legal && (e->shared_mode == 1 || (e->shared_mode == 2 && n_items >= 1024 &&
+        const bool use_shared = shared_legal && (e->shared_mode == 1 || (e->shared_mode == 2 && n_items >= 1024 && layout_hint != 0 &&
                                                                             e->max_code_len <= trk_shared_max_code_len()));
         if (use_shared)
             rc = launch_trk_shared(items_dev, n_items, e->chans_dev, e->bands_dev, reinterpret_cast<float2*>(out_dev), out_stride,
@@ -684,6 +687,14 @@ extern "C"
                 slices, e->partial, e->counters, e->max_code_len, e->taps_uniform, e->stream);
         if (rc == B200_OK) e->launches++;
         return rc;
+    }
+
+    int b200_trk_kernel_choice(b200_engine* e, int mode)
+    {
+        if (!e || mode < -1 || mode > 2) return B200_ERR_ARG;
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->shared_mode = mode;
+        return B200_OK;
     }
 
     int b200_trk_batch_dev(b200_engine* e, const b200_trk_item* items_dev, int n_items, b200_cf32* out_dev, int out_stride, int slices)
@@ -700,7 +711,7 @@ extern "C"
         // one lock for the whole submission: concurrent submitters (the reference runs one thread per tracking block)
         // queue whole batches, never interleave the item copy of one with the launch of another
         std::lock_guard<std::mutex> lk(e->mu);
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         for (int i = 0; i < n_items; i++)
             {
                 const int ch = items_host[i].channel;
@@ -822,7 +833,23 @@ extern "C"
                 B200_CUDA_TRY(cudaMemcpyAsync(sl->items_dev, sl->items_pin, sizeof(b200_trk_item) * n_items, cudaMemcpyHostToDevice, e->copy_stream));
                 B200_CUDA_TRY(cudaEventRecord(sl->items_ready, e->copy_stream));
                 B200_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl->items_ready, 0));
-                const int rc = batch_dev_impl(e, sl->items_dev, n_items, reinterpret_cast<b200_cf32*>(sl->out_dev), out_stride, slices);
+                // do the groups of consecutive (sorted) items the shared-window kernel would form really overlap?
+                unsigned long long sum_n = 0, sum_hull = 0;
+                for (int g = 0; g < n_items; g += 8)
+                    {
+                        unsigned long long lo = ~0ULL, hi = 0;
+                        for (int i = g; i < n_items && i < g + 8; i++)
+                            {
+                                const b200_trk_item& it = sl->items_pin[i];
+                                const unsigned long long a = it.sample_index + (static_cast<unsigned long long>(e->chans[it.channel].desc.band) << 48);
+                                lo = a < lo ? a : lo;
+                                hi = a + it.n > hi ? a + it.n : hi;
+                                sum_n += it.n > 0 ? it.n : 0;
+                            }
+                        sum_hull += hi - lo;
+                    }
+                const int layout_hint = (sum_n > 2 * sum_hull) ? 1 : 0;
+                const int rc = batch_dev_impl(e, sl->items_dev, n_items, reinterpret_cast<b200_cf32*>(sl->out_dev), out_stride, slices, layout_hint);
                 if (rc) return rc;
                 B200_CUDA_TRY(cudaMemcpyAsync(sl->out_pin, sl->out_dev, sizeof(float2) * n_items * out_stride, cudaMemcpyDeviceToHost, e->stream));
                 B200_CUDA_TRY(cudaEventRecord(sl->done, e->stream));
@@ -847,7 +874,7 @@ extern "C"
                 set_error("unknown ticket %llu", static_cast<unsigned long long>(ticket));
                 return B200_ERR_ARG;
             }
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         B200_CUDA_TRY(cudaEventSynchronize(sl->done));
         if (sl->perm.empty())
             {
@@ -921,7 +948,7 @@ extern "C"
                 set_error("n_correlators %d outside 1..%d", n_correlators, B200_MAX_TAPS);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         b200_trk* t = new (std::nothrow) b200_trk();
         if (!t) return B200_ERR_NOMEM;
         t->e = e;
@@ -957,7 +984,7 @@ extern "C"
     int b200_trk_set_local_code_and_taps(b200_trk* t, int code_length_chips, const float* local_code_in, const float* shifts_chips)
     {
         if (!t || !local_code_in || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_ENTER_DEVICE(t->e->device);
         B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
         if (code_length_chips > t->code_cap)
             {
@@ -1002,7 +1029,7 @@ extern "C"
                 set_error("signal_length_samples %d outside 0..%d", signal_length_samples, t->max_len);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_ENTER_DEVICE(t->e->device);
         const int n = signal_length_samples;
         if (n > 0) B200_CUDA_TRY(cudaMemcpyAsync(t->sig_dev, sig_in_host, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
         b200_trk::Ctl* c = t->ctl;
@@ -1043,7 +1070,7 @@ extern "C"
     int b200_trk_set_local_code_and_taps_cplx(b200_trk* t, int code_length_chips, const b200_cf32* local_code_in, const float* shifts_chips)
     {
         if (!t || !local_code_in || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_ENTER_DEVICE(t->e->device);
         B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
         if (code_length_chips > t->cplx_code_len)
             {
@@ -1074,7 +1101,7 @@ extern "C"
                 set_error("signal_length_samples %d outside 0..%d", n, t->max_len);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_ENTER_DEVICE(t->e->device);
         if (n > 0) B200_CUDA_TRY(cudaMemcpyAsync(t->sig_dev, sig_in_host, sizeof(float2) * n, cudaMemcpyHostToDevice, t->stream));
         const int rc = launch_trk_cplx_code(t->sig_dev, t->cplx_code_dev, n, t->cplx_code_len, t->taps, t->var_shifts, rem_carrier_phase_in_rad,
             phase_step_rad, rem_code_phase_chips, code_phase_step_chips, t->out_cplx_dev, t->stream);
@@ -1092,7 +1119,7 @@ extern "C"
     int b200_trk_set_local_code_and_taps_16sc(b200_trk* t, int code_length_chips, const int16_t* local_code_iq, const float* shifts_chips)
     {
         if (!t || !local_code_iq || !shifts_chips || code_length_chips < 1) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_ENTER_DEVICE(t->e->device);
         B200_CUDA_TRY(cudaStreamSynchronize(t->stream));
         if (code_length_chips > t->code16_len)
             {
@@ -1124,7 +1151,7 @@ extern "C"
                 set_error("signal_length_samples %d outside 0..%d", n, t->max_len);
                 return B200_ERR_RANGE;
             }
-        B200_CUDA_TRY(cudaSetDevice(t->e->device));
+        B200_ENTER_DEVICE(t->e->device);
         if (n > 0) B200_CUDA_TRY(cudaMemcpyAsync(t->sig16_dev, sig_in_iq_host, sizeof(short) * 2 * n, cudaMemcpyHostToDevice, t->stream));
         const int rc = launch_trk_16sc(t->sig16_dev, t->code16_dev, n, t->code16_len, t->taps, t->var_shifts, rem_carrier_phase_in_rad, phase_step_rad,
             rem_code_phase_chips, code_phase_step_chips, t->out16_dev, t->stream);

@@ -249,7 +249,7 @@ extern "C"
         L.state = 0;
         e->loops.push_back(L);
         *loop_id = static_cast<int>(e->loops.size()) - 1;
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         int rc = ensure_loop_buffers(e, 1);
         if (rc) return rc;
         B200_CUDA_TRY(cudaMemcpyAsync(e->loops_dev + *loop_id, &e->loops[*loop_id], sizeof(LoopDev), cudaMemcpyHostToDevice, e->stream));
@@ -309,7 +309,7 @@ extern "C"
         L.pending = 0;
         // the device copy is replaced by the start-of-tracking state (what start_tracking leaves alone -
         // d_P_accu_old, the error terms - was zeroed by clear_tracking_vars when the previous run ended)
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         int rc = ensure_loop_buffers(e, 1);
         if (rc) return rc;
         B200_CUDA_TRY(cudaMemcpyAsync(e->loops_dev + loop_id, &L, sizeof(LoopDev), cudaMemcpyHostToDevice, e->stream));
@@ -323,7 +323,7 @@ extern "C"
         std::lock_guard<std::mutex> lk(e->mu);
         const int n = static_cast<int>(e->loops.size());
         if (n == 0 || max_epochs == 0) return B200_OK;
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         int rc = upload_tables(e);
         if (rc) return rc;
         rc = ensure_loop_buffers(e, max_epochs);
@@ -386,7 +386,7 @@ extern "C"
         std::lock_guard<std::mutex> lk(e->mu);
         const int n = static_cast<int>(e->loops.size());
         if (n == 0) return B200_OK;
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         int rc = ensure_loop_buffers(e, 1);
         if (rc) return rc;
         const LoopAvail avail{};
@@ -404,7 +404,7 @@ extern "C"
         std::lock_guard<std::mutex> lk(e->mu);
         const int n = static_cast<int>(e->loops.size());
         if (n == 0) return B200_OK;
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         int rc = ensure_loop_buffers(e, 1);
         if (rc) return rc;
         const LoopAvail avail{};
@@ -428,7 +428,7 @@ extern "C"
         if (!e || !out) return B200_ERR_ARG;
         std::lock_guard<std::mutex> lk(e->mu);
         if (loop_id < 0 || loop_id >= static_cast<int>(e->loops.size())) return B200_ERR_ARG;
-        B200_CUDA_TRY(cudaSetDevice(e->device));
+        B200_ENTER_DEVICE(e->device);
         LoopDev L;
         B200_CUDA_TRY(cudaMemcpyAsync(&L, e->loops_dev + loop_id, sizeof(LoopDev), cudaMemcpyDeviceToHost, e->stream));
         B200_CUDA_TRY(cudaStreamSynchronize(e->stream));

@@ -191,6 +191,11 @@ extern "C"
      * the launch is ordered after every b200_iq_push made so far), wait blocks until that batch's
      * taps are in out_host.  Up to 16 batches may be in flight, so IQ pushes (copy engine) and
      * correlation (SMs) overlap.  These are the trk_submit / trk_wait of SURVEY 8b. */
+    /* Which correlator kernel a batch runs on.  2 (default): the shared-window kernel (one TMA-staged sample window per group
+     * of 8 items) for batches of >= 1024 items with C/A-sized code tables whose consecutive items overlap in the band -
+     * known for b200_trk_submit, which sees the items; assumed for b200_trk_batch_dev - and the per-item kernel otherwise.
+     * 1: shared-window whenever legal; 0: always per-item; -1: back to the B200_TRK_SHARED environment variable / default. */
+    int b200_trk_kernel_choice(b200_engine* e, int mode);
     int b200_trk_submit(b200_engine* e, const b200_trk_item* items_host, int n_items, int out_stride, uint64_t* ticket);
     int b200_trk_wait(b200_engine* e, uint64_t ticket, b200_cf32* out_host);
     /* ---- tracking: free-running DLL/PLL loops on the device -------------------- */
@@ -405,6 +410,10 @@ extern "C"
     /* d_magnitude_grid of one slot (bins x effective_fft_size floats); needs keep_grid or max_dwells>1.
      * Replaces the grid copy in doppler_grid (:555-558) / dump_results (:354-406). */
     int b200_acq_read_grid(b200_acq* a, uint32_t slot, float* grid_host);
+    /* Self-test hook of the transform under the search: out = DFT_fft_size(in) in natural order, computed the way this
+     * object computes its spectra (chirp-z objects only; B200_ERR_STATE otherwise).  No reference counterpart: the
+     * reference calls gr::fft, whose outputs no reference test holds either. */
+    int b200_acq_selftest_dft(b200_acq* a, const b200_cf32* in_host, b200_cf32* out_host);
     /* the wipe-off grid (bins x fft_size complex), for parity tests against volk_gnsssdr_s32f_sincos_32fc */
     int b200_acq_read_wipeoffs(b200_acq* a, b200_cf32* wipe_host);
     int b200_acq_destroy(b200_acq* a);

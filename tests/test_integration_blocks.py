@@ -312,7 +312,7 @@ def test_b200_galileo_e1_pilot_veml_matches_reference(reflib, b200lib):
     for name, lib, impl in [("ref", reflib, "Galileo_E1_DLL_PLL_VEML_Tracking"), ("b200", b200lib, "Galileo_E1_DLL_PLL_VEML_Tracking_B200")]:
         ch = bi.Channel(lib, conf, "", impl, trk_role="Tracking_1B")
         ch.set_satellite("E", "1B", prn)
-        ch.set_acq_result(float(delay), -800.0, 16000)
+        ch.set_acq_result(float(delay), -840.0, 16000)   # 4 ms epochs: the Costas loop pulls in from 10 Hz, not from 50
         ch.trk_start()
         outs[name] = ch.trk_run(iq)
         assert ch.events("trk") == []

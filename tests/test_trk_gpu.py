@@ -542,6 +542,51 @@ def test_shared_kernel_groups_that_cannot_share(capi, oracle):
         assert np.all(got[i, :, 1] == 0)
 
 
+@pytest.mark.parametrize("layout", ["shared", "distinct"])
+def test_kernel_choice_by_layout_is_integer_exact(capi, oracle, layout):
+    """1536 host-submitted items: with overlapping neighbours (a receiver: all channels on one stream) b200_trk_submit takes
+    the shared-window kernel, with disjoint sample ranges (every item its own samples) the per-item kernel; forcing either
+    kernel (b200_trk_kernel_choice) gives the same integers."""
+    n, L, shifts, step = 2000, 1023, [-0.5, 0.0, 0.5], 0.5115
+    rng = np.random.default_rng(77)
+    n_ch, n_ep = 48, 32
+    span = n * n_ep + 64
+    total = span * (n_ch if layout == "distinct" else 1)
+    x = rng.integers(-9, 10, total)
+    codes = [np.where(rng.integers(0, 2, L) > 0, 1, -1) for _ in range(n_ch)]
+    e = capi.Engine(0)
+    e.iq_create(0, total)
+    first = e.iq_push(0, x.astype(np.complex64))
+    items = np.zeros(n_ch * n_ep, capi.TRK_ITEM_DTYPE)
+    where = []
+    for k in range(n_ep):
+        for c in range(n_ch):
+            if k == 0:
+                cid = e.channel_create(0, 3)
+                e.channel_set_code(cid, codes[c].astype(np.float32), shifts)
+            it = items[len(where)]
+            it["channel"] = c
+            it["n"] = n
+            s0 = k * n + (c % 5) + (c * span if layout == "distinct" else 0)
+            it["sample_index"] = first + s0
+            it["rem_code_phase_chips"] = 0.25 + c
+            it["code_phase_step_chips"] = step
+            where.append((c, s0))
+    results = {}
+    for mode in (2, 0, 1):
+        e.trk_kernel_choice(mode)
+        results[mode] = e.trk_batch(items, 3)
+    e.close()
+    assert np.array_equal(results[2], results[0]) and np.array_equal(results[2], results[1])
+    got = results[2]
+    for i in range(0, len(where), 7):
+        c, s0 = where[i]
+        _, idx = oracle.port.resampler(1, codes[c].astype(np.float32), 0.25 + c, step, shifts, n, return_idx=True)
+        want = int_oracle(x[s0:s0 + n], codes[c], idx)
+        assert np.array_equal(got[i].real.astype(np.int64), want), (c, s0)
+        assert np.all(got[i].imag == 0)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("item_type", ["gr_complex", "ishort", "ibyte"])
 def test_file_source_push_matches_array_push(oracle, tmp_path, item_type):

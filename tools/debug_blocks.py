@@ -33,7 +33,7 @@ def run(which, coalesce):
                 f"{role}.early_late_space_chips": 0.15, f"{role}.very_early_late_space_chips": 0.6, f"{role}.pull_in_time_s": 1,
                 f"{role}.track_pilot": True}
         impls = ("Galileo_E1_DLL_PLL_VEML_Tracking", "Galileo_E1_DLL_PLL_VEML_Tracking_B200")
-        acq = (float(delay), -800.0, 16000)
+        acq = (float(delay), -840.0, 16000)
     else:
         rng = np.random.default_rng(31)
         prn, fs, role, sysc, sig = 6, 12_000_000, "Tracking_L5", "G", "L5"

@@ -43,3 +43,21 @@ for fs, ms in [(16.368e6, 1), (16.368e6, 2), (20.46e6, 1), (30.69e6, 1), (65.536
           f"want t={want['index_time'] % int(spms)} d={want['index_doppler']} stat={want['test_statistics']:.3f} | grid err {err:.2e}", flush=True)
     acq.close()
 eng.close()
+
+# the transform alone: chirp-z DFT of random vectors against numpy
+eng = capi.Engine(0)
+rng = np.random.default_rng(1)
+for fs in [5.456e6, 13e6, 16.368e6, 17.391e6, 20.46e6, 30.69e6, 32.736e6, 40.92e6]:
+    n = int(fs / 1000)
+    try:
+        acq = capi.PcpsAcquisition(eng, fs_in=int(fs), samples_per_ms=fs / 1000.0, samples_per_chip=int(fs / 1.023e6), doppler_max=500, doppler_step=250)
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        got = acq.selftest_dft(x)
+        ref = np.fft.fft(x.astype(np.complex128))
+        e = np.abs(got - ref)
+        print(f"DFT N={n}: max err {e.max() / np.abs(ref).max():.2e}; first bad index {np.argmax(e > 1e-3 * np.abs(ref).max()) if (e > 1e-3 * np.abs(ref).max()).any() else -1}, "
+              f"bad count {(e > 1e-3 * np.abs(ref).max()).sum()}", flush=True)
+        acq.close()
+    except capi.B200Error as ex:
+        print(n, "failed", ex)
+eng.close()
