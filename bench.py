@@ -175,6 +175,24 @@ def ncu_limiter():
         return None
 
 
+_AFFINITY_BEFORE_BINDING = None
+
+
+class whole_host:
+    """The CPU arms get every CPU the process was started with, not only the GPU's NUMA node."""
+    def __enter__(self):
+        self.saved = None
+        if _AFFINITY_BEFORE_BINDING is not None:
+            self.saved = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, _AFFINITY_BEFORE_BINDING)
+        return self
+
+    def __exit__(self, *a):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
+
+
 def bind_to_gpu_numa(torch, local_rank):
     """Bind this rank (and with it the first-touch placement of its pinned buffers) to the NUMA node its GPU hangs off.
     Round 1: eight unbound ranks pushing 54 GB/s each halved the 8-GPU end-to-end efficiency."""
@@ -196,6 +214,9 @@ def bind_to_gpu_numa(torch, local_rank):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
         allowed = os.sched_getaffinity(0)
+        global _AFFINITY_BEFORE_BINDING
+        if _AFFINITY_BEFORE_BINDING is None:
+            _AFFINITY_BEFORE_BINDING = set(allowed)
         use = sorted(cpus & allowed) or sorted(allowed)
         os.sched_setaffinity(0, use)
         return {"numa_node": node, "bound": True, "cpus": len(use)}
@@ -275,11 +296,13 @@ def run_trk_config(torch, capi, dev, name, fs, groups, seconds, steps=20, warmup
 E1_SHIFTS = [-1.2, -0.3, 0.0, 0.3, 1.2]     # VE/E/P/L/VL at -0.6,-0.15,0,0.15,0.6 chips x 2 table values per chip (:632-636)
 
 
-def other_configs(torch, capi, dev, stream, steps):
+def other_configs(torch, capi, dev, stream, steps, only=None):
     """BASELINE configs[2] (C3) with and without the pilot's data tap, the per-GPU share of configs[4] (C5), and the C2
     workload laid out so that the algorithmic bytes really come from HBM."""
     out = {}
     def leg(key, *a, **kw):
+        if only and key not in only:
+            return
         try:
             out[key] = run_trk_config(torch, capi, dev, *a, steps=steps, stream=stream, **kw)
         except Exception as ex:
@@ -467,7 +490,8 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
            "n_gpus": world, "sharding": ("PRNs round-robin over ranks; per sweep one CUDA-graph launch per rank and one all-gather of 16-byte peak records "
                         "(b200_acq_sweep_best_dev)") if world > 1 else "single GPU"}
     if with_cpu:
-        out["cpu_baseline"] = cpu_baseline_acq(iq)
+        with whole_host():
+            out["cpu_baseline"] = cpu_baseline_acq(iq)
     acq.close()
     return out
 
@@ -569,14 +593,15 @@ def cpu_baseline(budget_s=12.0, sweep=False):
     # (AVX units and L2 shared by sibling threads; round 1's 2 919 vs 15 675 Msamples/s on two boxes was this).  The arm
     # uses the thread count that is FASTEST among {nproc, nproc/2, nproc/4} and says which.
     best = None
+    probe = 2000   # epochs per thread: >= 0.15 s per probe, long enough for sibling-thread contention to show
     for T in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
-        t0 = run(20, threads=T)
-        rate = T * 20 * EPOCH / t0
+        t0 = run(probe, threads=T)
+        rate = T * probe * EPOCH / t0
         if best is None or rate > best[0]:
             best = (rate, T, t0)
     threads = best[1]
     t = best[2]
-    iters = int(max(20, min(400000, 20 * budget_s / max(t, 1e-6))))
+    iters = int(max(20, min(400000, probe * budget_s / max(t, 1e-6))))
     t = run(iters, threads=threads)
     samples = threads * iters * EPOCH
     out = {"value": samples / t / 1e6, "unit": UNIT, "cores": threads, "host_cpus": cores, "kind": kind, "per_thread": samples / t / 1e6 / threads,
@@ -1049,7 +1074,8 @@ def main():
                         "what ncu names as the bound of the C2 launch (FP32 instruction issue / FMA pipe)"}
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        cb, _ = cpu_baseline(sweep=True)
+        with whole_host():
+            cb, _ = cpu_baseline(sweep=True)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -668,6 +668,18 @@ extern "C"
         return B200_OK;
     }
 
+    int b200_acq_selftest_read(b200_acq* a, int what, b200_cf32* out_host)
+    {
+        if (!a || !out_host || what < 0 || what > 1) return B200_ERR_ARG;
+        if (!a->bl) return B200_ERR_STATE;
+        B200_ENTER_DEVICE(a->e->device);
+        const size_t n = a->c.fft_size;
+        const size_t rows = what == 0 ? a->c.num_doppler_bins : a->c.n_code_slots;
+        B200_CUDA_TRY(cudaMemcpyAsync(out_host, what == 0 ? a->bl->Xs : a->bl->CW, sizeof(float2) * n * rows, cudaMemcpyDeviceToHost, a->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return B200_OK;
+    }
+
     int b200_acq_read_grid(b200_acq* a, uint32_t slot, float* grid_host)
     {
         if (!a || !grid_host || slot >= a->c.n_code_slots) return B200_ERR_ARG;

@@ -17,5 +17,6 @@ if __name__ == "__main__":
     dev = torch.device("cuda", 0)
     st = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(st)
-    for k, v in bench.other_configs(torch, capi, dev, st, steps=20).items():
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
+    for k, v in bench.other_configs(torch, capi, dev, st, steps=20, only=only).items():
         print(json.dumps({k: v}), flush=True)
