@@ -187,7 +187,18 @@ int bluestein_refresh_mult(b200_acq* a)
     return acq_launch_rows_times_vector(a->wipe, n, b->chirp_conj, n, 0, b->mult, n, static_cast<int>(a->c.num_doppler_bins), a->stream);
 }
 
+int bluestein_setup_queue(b200_acq* a, std::vector<float2> (&host)[6]);
+
 int bluestein_setup(b200_acq* a)
+{
+    // the host tables must outlive the asynchronous copies queued from them, on the error paths too
+    std::vector<float2> host[6];
+    const int rc = bluestein_setup_queue(a, host);
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    return rc;
+}
+
+int bluestein_setup_queue(b200_acq* a, std::vector<float2> (&host)[6])
 {
     const b200_acq_conf& c = a->c;
     const int n = static_cast<int>(c.fft_size);
@@ -214,12 +225,21 @@ int bluestein_setup(b200_acq* a)
     B200_CUDA_TRY(cudaMalloc(&b->CW, sizeof(float2) * slots * n));
     B200_CUDA_TRY(cudaMalloc(&b->slot_ids, sizeof(int) * 2));
     B200_CUDA_TRY(cudaMalloc(&b->partial, sizeof(AcqRowStat) * bins * acq_final_chunks(b->plM)));
-    const int ids[2] = {0, 1};
-    B200_CUDA_TRY(cudaMemcpy(b->slot_ids, ids, sizeof(ids), cudaMemcpyHostToDevice));
+    // every copy below goes through a->stream: a synchronous cudaMemcpy from pageable memory may return before its DMA has
+    // landed and is ordered only against the legacy default stream, which a->stream (non-blocking) does not wait for - the
+    // filter kernels launched right after it read a half-written chirp (found on sizes with M > 32768)
+    static const int ids[2] = {0, 1};
+    B200_CUDA_TRY(cudaMemcpyAsync(b->slot_ids, ids, sizeof(ids), cudaMemcpyHostToDevice, a->stream));
     int rc = acq_launch_twiddles(b->twM, b->plM, a->stream);
     if (rc) return rc;
     // chirp tables in double: w[k] = exp(j pi k^2 / N) with k^2 reduced mod 2N
-    std::vector<float2> w(n), wc(n), wcm(n), wm(n), h(M), hc(M);
+    std::vector<float2>&w = host[0], &wc = host[1], &wcm = host[2], &wm = host[3], &h = host[4], &hc = host[5];
+    w.resize(n);
+    wc.resize(n);
+    wcm.resize(n);
+    wm.resize(n);
+    h.resize(M);
+    hc.resize(M);
     const double inv_m = 1.0 / static_cast<double>(M);
     for (size_t i = 0; i < M; i++) h[i] = hc[i] = make_float2(0.f, 0.f);
     for (int k = 0; k < n; k++)
@@ -239,19 +259,17 @@ int bluestein_setup(b200_acq* a)
                     hc[M - k] = wc[k];
                 }
         }
-    B200_CUDA_TRY(cudaMemcpy(b->chirp, w.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
-    B200_CUDA_TRY(cudaMemcpy(b->chirp_conj, wc.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
-    B200_CUDA_TRY(cudaMemcpy(b->chirp_conj_M, wcm.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
-    B200_CUDA_TRY(cudaMemcpy(b->chirp_M, wm.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpyAsync(b->chirp, w.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, a->stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(b->chirp_conj, wc.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, a->stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(b->chirp_conj_M, wcm.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, a->stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(b->chirp_M, wm.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, a->stream));
     // filter spectra through the code-spectrum kernel, which stores conj(FFT(.)): for a symmetric h, conj(FFT(conj h)) = FFT(h)
-    B200_CUDA_TRY(cudaMemcpy(b->A, hc.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpyAsync(b->A, hc.data(), sizeof(float2) * M, cudaMemcpyHostToDevice, a->stream));
     rc = acq_launch_code_fft(b->A, b->M, 0, b->filt, b->plM, b->twM, a->stream);
     if (rc) return rc;
-    B200_CUDA_TRY(cudaMemcpy(b->Zw, h.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpyAsync(b->Zw, h.data(), sizeof(float2) * M, cudaMemcpyHostToDevice, a->stream));
     rc = acq_launch_code_fft(b->Zw, b->M, 0, b->filt + M, b->plM, b->twM, a->stream);
-    if (rc) return rc;
-    B200_CUDA_TRY(cudaStreamSynchronize(a->stream));
-    return B200_OK;
+    return rc;
 }
 
 void bluestein_free(b200_acq* a)

@@ -305,7 +305,7 @@ extern "C"
     int b200_trk_loop_run(b200_engine* e, int max_epochs, b200_trk_dump_record* records_host, int* n_records_host);
     /* How b200_trk_loop_run schedules the work: 0 (default) one persistent kernel, one CTA per loop, free-running
      * for max_epochs cycles with no launch per epoch; 1 a correlator launch + a loop-update launch per epoch with
-     * one CTA per loop (bit-identical records to mode 0); 2 the same with each epoch split over several CTAs
+     * one CTA per loop (same integers as mode 0, floats within an ulp of atanf/log10f: the correlator sums in a different order); 2 the same with each epoch split over several CTAs
      * (lowest latency for a handful of channels).  Env B200_LOOP_MODE sets the initial value. */
     int b200_trk_loop_set_mode(b200_engine* e, int mode);
     /* Prepare (if not already pending) and return the next work item of every loop: the seven scalars
