@@ -109,7 +109,16 @@ int Pcps_Acquisition_Fine_Doppler_Core::work(const std::complex<float>* in, int 
             {
                 const uint32_t slot = 0;
                 b200_acq_result r{};
-                if (b200_acq_search(d_acq, reinterpret_cast<const b200_cf32*>(in), &slot, 1, static_cast<uint32_t>(d_well_count + 1), &r) != B200_OK) return 0;
+                if (b200_acq_search(d_acq, reinterpret_cast<const b200_cf32*>(in), &slot, 1, static_cast<uint32_t>(d_well_count + 1), &r) != B200_OK)
+                    {
+                        // a device failure is a negative acquisition (as in Pcps_Acquisition_Core): consume the block, or a
+                        // scheduler would offer the same input for ever
+                        d_sample_counter += static_cast<uint64_t>(d_fft_size);
+                        *consumed = d_fft_size;
+                        d_n_samples_in_buffer = 0;
+                        d_state = 5;
+                        break;
+                    }
                 std::copy(in, in + d_fft_size, &d_10_ms_buffer[d_n_samples_in_buffer]);
                 d_n_samples_in_buffer += d_fft_size;
                 d_well_count++;
@@ -156,9 +165,9 @@ int Pcps_Acquisition_Fine_Doppler_Core::work(const std::complex<float>* in, int 
                                 d_sample_counter += static_cast<uint64_t>(samples_remaining);
                                 *consumed = samples_remaining;
                             }
-                        estimate_Doppler();
+                        // a failed estimate must not be reported as a positive acquisition
+                        d_state = (estimate_Doppler() < 0) ? 5 : 4;
                         d_n_samples_in_buffer = 0;
-                        d_state = 4;
                     }
                 break;
             }

@@ -47,6 +47,8 @@ Trk_Coalescer::~Trk_Coalescer()
     d_stop.store(true);
     d_posted.fetch_add(1);  // wake the tick thread
     d_posted.notify_all();
+    d_done_gen.fetch_add(1);
+    d_done_gen.notify_all();
     for (int b = 0; b < kMaxBands; b++) d_cv_space[b].notify_all();
     if (d_thread.joinable()) d_thread.join();
 }
@@ -147,10 +149,11 @@ void Trk_Coalescer::close_channel(int id)
     // an epoch still in flight finishes first (its result is dropped)
     for (;;)
         {
+            const uint32_t gen = d_done_gen.load(std::memory_order_acquire);
             const int st = s->state.load(std::memory_order_acquire);
             if (st != POSTED && st != IN_FLIGHT) break;
             if (d_stop.load()) break;
-            s->state.wait(st);
+            d_done_gen.wait(gen, std::memory_order_acquire);
         }
     idle(id);
     s->state.store(IDLE);  // engine channel ids are never reused; the slot just goes quiet
@@ -278,6 +281,8 @@ bool Trk_Coalescer::wait(int id, std::complex<float>* out)
     int spins = 0;
     for (;;)
         {
+            // generation first: a batch that completes between the two loads changes it and the wait below returns at once
+            const uint32_t gen = d_done_gen.load(std::memory_order_acquire);
             st = s->state.load(std::memory_order_acquire);
             if (st != POSTED && st != IN_FLIGHT) break;
             if (d_stop.load(std::memory_order_relaxed)) return false;
@@ -286,16 +291,15 @@ bool Trk_Coalescer::wait(int id, std::complex<float>* out)
                     B200_CPU_RELAX();
                     continue;
                 }
-            s->state.wait(st, std::memory_order_acquire);
+            d_done_gen.wait(gen, std::memory_order_acquire);
         }
     const bool ok = st == DONE;
     if (ok)
         {
             for (int k = 0; k < s->taps; k++) out[k] = s->out[k];
             const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - s->t_post).count();
-            std::lock_guard<std::mutex> lk(d_admin_mu);
-            d_stats.sum_latency_us += us;
-            d_stats.max_latency_us = std::max(d_stats.max_latency_us, us);
+            s->lat_sum_us += us;   // per slot: 256 threads woken together must not queue on one mutex for a statistic
+            s->lat_max_us = std::max(s->lat_max_us, us);
         }
     if (st == DONE || st == FAILED) s->state.store(IDLE, std::memory_order_release);
     return ok;
@@ -362,8 +366,11 @@ void Trk_Coalescer::tick_loop()
                     if (rc == B200_OK)
                         for (int t = 0; t < s.taps; t++) s.out[t] = std::complex<float>(taps[k * B200_MAX_TAPS + t].re, taps[k * B200_MAX_TAPS + t].im);
                     s.state.store(rc == B200_OK ? DONE : FAILED, std::memory_order_release);
-                    s.state.notify_all();
                 }
+            // ONE wake call for the whole batch: all waiters sleep on the generation word (a futex wake per slot costs the
+            // tick thread ~2 us each - with 256 channels that was most of the time between batches)
+            d_done_gen.fetch_add(1, std::memory_order_release);
+            d_done_gen.notify_all();
             {
                 std::lock_guard<std::mutex> lk(d_admin_mu);
                 d_stats.batches++;
@@ -379,6 +386,12 @@ Trk_Coalescer::Stats Trk_Coalescer::stats()
 {
     std::lock_guard<std::mutex> lk(d_admin_mu);
     Stats s = d_stats;
+    const int ns = d_n_slots.load();
+    for (int i = 0; i < ns; i++)
+        {
+            s.sum_latency_us += d_slots[i].lat_sum_us;
+            s.max_latency_us = std::max(s.max_latency_us, d_slots[i].lat_max_us);
+        }
     s.samples_copied = d_samples_copied.load();
     s.samples_offered = d_samples_offered.load();
     return s;
@@ -389,6 +402,8 @@ void Trk_Coalescer::reset_stats()
 {
     std::lock_guard<std::mutex> lk(d_admin_mu);
     d_stats = Stats();
+    const int ns = d_n_slots.load();
+    for (int i = 0; i < ns; i++) d_slots[i].lat_sum_us = d_slots[i].lat_max_us = 0.0;
     d_samples_copied.store(0);
     d_samples_offered.store(0);
 }

@@ -102,6 +102,7 @@ private:
         b200_trk_item item{};
         std::complex<float> out[B200_MAX_TAPS];
         std::chrono::steady_clock::time_point t_post;
+        double lat_sum_us{0.0}, lat_max_us{0.0};  // post -> result, written by the channel's own thread only
     };
     void tick_loop();
     void activate(Slot& s, bool stream_may_be_new);
@@ -113,6 +114,7 @@ private:
     std::unique_ptr<Slot[]> d_slots;        // indexed by engine channel id; fixed size, never reallocated
     std::atomic<int> d_n_slots{0};          // highest id in use + 1
     std::atomic<int> d_posted{0};
+    std::atomic<uint32_t> d_done_gen{0};    // batches completed: every waiter sleeps on this one word (one wake call per batch)
     std::atomic<int> d_n_active{0};
     std::atomic<int> d_band_active[kMaxBands];         // active channels per band
     std::atomic<bool> d_stop{false};
@@ -124,7 +126,7 @@ private:
     std::mutex d_admin_mu;                  // open/close/ensure_band/stats
     int d_window_us{200};
     std::thread d_thread;
-    Stats d_stats;                          // tick-thread fields; latency fields under d_admin_mu
+    Stats d_stats;                          // tick-thread fields (latencies are kept per slot)
     std::atomic<uint64_t> d_samples_copied{0}, d_samples_offered{0};
     char d_error[256] = "";
 };
