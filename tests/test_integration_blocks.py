@@ -391,6 +391,31 @@ def test_b200_cshort_acquisition_matches_reference(reflib, b200lib, gps_signal):
 
 
 @pytest.mark.gpu
+def test_b200_acquisition_at_16368_ksps_matches_reference(reflib, b200lib):
+    """A 16.368 Msps front end: 16 368 samples per code period = 2^4 * 3 * 11 * 31.  The reference's FFT (FFTW) takes any
+    size - the gr::fft stand-in of the oracle build goes through Bluestein for this one - and so does the B200 block
+    (chirp-z on the mixed-radix kernels): same decision, same code phase and Doppler bin through general_work."""
+    fs = 16_368_000
+    code = bi.code_table(reflib, "G", "1C", 9)
+    delay = 7777
+    sv = dict(prn=9, doppler=-2310.0, code_phase_chips=(-delay * 1.023e6 / fs) % 1023, cn0=47.0)
+    iq = make_iq({9: code}, float(fs), 6 * 16368, [sv], seed=12)
+    conf = {"GNSS-SDR.internal_fs_sps": fs, "Acquisition_1C.item_type": "gr_complex", "Acquisition_1C.doppler_max": 5000,
+            "Acquisition_1C.doppler_step": 250, "Acquisition_1C.pfa": 0.001, "Acquisition_1C.blocking": True}
+    res = {}
+    for name, lib, impl in [("ref", reflib, "GPS_L1_CA_PCPS_Acquisition"), ("b200", b200lib, "GPS_L1_CA_PCPS_Acquisition_B200")]:
+        ch = bi.Channel(lib, conf, impl, "")
+        ch.set_satellite("G", "1C", 9)
+        ch.acq_start()
+        ch.acq_run(iq)
+        s = ch.synchro()
+        res[name] = (s.Acq_delay_samples, s.Acq_doppler_hz, s.Acq_samplestamp_samples, ch.events("acq"))
+        ch.close()
+    assert res["ref"] == res["b200"], res
+    assert res["ref"][3] == [1] and abs(res["ref"][0] - delay) <= 1 and abs(res["ref"][1] + 2310.0) <= 250
+
+
+@pytest.mark.gpu
 def test_b200_negative_acquisition_event(reflib, b200lib):
     """Noise only: both blocks publish message 2 (negative acquisition) after max_dwells and go inactive."""
     rng = np.random.default_rng(9)
