@@ -165,6 +165,17 @@ def ncu_traffic_bytes():
         return None
 
 
+def ncu_acq_traffic_bytes():
+    """DRAM bytes of one acq_corr_kernel launch (C4 sweep) from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f).get("acq_corr_kernel<512>", {})
+            return int(d.get("dram__bytes_read.sum", 0)) + int(d.get("dram__bytes_write.sum", 0))
+    except Exception:
+        return None
+
+
 def ncu_limiter():
     """What ncu says bounds the dominant kernel (committed summary of the --set full capture)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -480,7 +491,7 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
                    "path": "b200_acq_search_submit / _wait alternating over two acquisition objects"},
            "gpu_launches_per_sweep": launches / steps, "cuda_graph": graph is not None,
            "roofline": {"bound": "hbm", "kernel": "acq_corr_kernel", "achieved": abytes / (ms * 1e-3) / 1e9, "peak": peak,
-                        "unit": "GB/s", "frac": abytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                        "unit": "GB/s", "frac": abytes / (ms * 1e-3) / 1e9 / peak, "traffic": ncu_acq_traffic_bytes(),
                         "algorithmic_bytes_per_sweep": abytes, "algorithmic_gflop_per_sweep": aflops / 1e9,
                         "achieved_tflops": aflops / (ms * 1e-3) / 1e12, "peak_source": peak_src,
                         "note": "16N bytes per (PRN,bin) row (SURVEY 8d); operands are L2-resident, the kernel is "
@@ -565,7 +576,7 @@ def usable_cpus():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(budget_s=12.0, sweep=False):
+def cpu_baseline(budget_s=12.0, sweep=False, threads=None):
     """The reference's Cpu_Multicorrelator_Real_Codes (u_avx kernels) compiled in place: one correlator per host thread,
     threads PINNED round robin over the process's CPUs and started together (oracle/ref_engine.cc ref_mc_bench_pinned),
     shaped like cpu_multicorrelator_real_codes_test.cc:41-62,135-169.  sweep=True adds the T in {1, nproc/2, nproc} x
@@ -594,7 +605,7 @@ def cpu_baseline(budget_s=12.0, sweep=False):
     # uses the thread count that is FASTEST among {nproc, nproc/2, nproc/4} and says which.
     best = None
     probe = 2000   # epochs per thread: >= 0.15 s per probe, long enough for sibling-thread contention to show
-    for T in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+    for T in (sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True) if threads is None else [threads]):
         t0 = run(probe, threads=T)
         rate = T * probe * EPOCH / t0
         if best is None or rate > best[0]:
@@ -682,8 +693,11 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     vals, times = [], []
+    threads = None
     for k in range(args.warmup + args.steps):
-        cb, t = cpu_baseline(budget_s=max(0.3, 60.0 / max(1, args.warmup + args.steps)))   # whole arm ~1-2 min for any K
+        # the thread count is chosen once (first step); whole arm ~1-2 min for any K
+        cb, t = cpu_baseline(budget_s=max(0.15, 60.0 / max(1, args.warmup + args.steps)), threads=threads)
+        threads = cb["cores"]
         if k >= args.warmup:
             vals.append(cb["value"])
             times.append(t)
@@ -1037,6 +1051,22 @@ def main():
                      "value": world * ch_samples_step * n_sus / (sus_ms * 1e-3) / 1e6, "unit": UNIT,
                      "clocks": sampler2.stop() if rank == 0 else None}
 
+    # ---- C5 on N GPUs: every rank runs its 32-channel share (12 GPS L1 + 12 Galileo E1 + 8 GPS L5 at 50 Msps) at the same time;
+    # with N = 8 that is BASELINE configs[4] (256 channels, three signals) ------------------------------------------------------
+    c5_multi = None
+    if not args.no_extra and world > 1:
+        try:
+            barrier()
+            share = other_configs(torch, capi, dev, tstream, steps=10, only=["C5_per_gpu_share"])["C5_per_gpu_share"]
+            tms = torch.tensor([share.get("ms_per_step", float("nan"))], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms_max = float(tms.item())
+            c5_multi = {"workload": f"C5 share x {world} GPUs = {32 * world} channels at 50 Msps x 1 s, three signals, ranks concurrent, no collective",
+                        "ms_per_step_max_over_ranks": ms_max,
+                        "value": world * share["channel_samples_per_step"] / (ms_max * 1e-3) / 1e6, "unit": UNIT}
+        except Exception as ex:
+            c5_multi = {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -1082,7 +1112,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config_dict(world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
             "stream_msps": value / N_CH, "prompt_over_noise": prompt_snr, "engine_timer_check_ms": check_ms,
-            "acq": acq, "closed_loop": closed, "sustained": sustained, "other_configs": extra,
+            "acq": acq, "closed_loop": closed, "sustained": sustained, "other_configs": extra, "c5_multi_gpu": c5_multi,
             "coalesced_class_interface": coalesced, "numa": numa}
     print(json.dumps(line))
     if dist is not None:
