@@ -504,6 +504,33 @@ def bench_acq(torch, capi, eng, dev, steps, warmup, with_cpu, dist=None, rank=0,
         with whole_host():
             out["cpu_baseline"] = cpu_baseline_acq(iq)
     acq.close()
+    if world == 1:
+        # a front end at 16.368 Msps: N = 16 368 = 2^4 * 3 * 11 * 31 goes through chirp-z (M = 32 768) on the same kernels
+        try:
+            fs2, n2, dmax2 = 16_368_000, 16368, 5000
+            bins2 = int(np.ceil(2 * dmax2 / ACQ_DSTEP)) + 1
+            cz = capi.PcpsAcquisition(eng, fs_in=fs2, samples_per_ms=float(n2), samples_per_chip=16, doppler_max=dmax2, doppler_step=ACQ_DSTEP,
+                                      n_code_slots=ACQ_PRNS)
+            for p in range(1, ACQ_PRNS + 1):
+                cz.set_local_code(p - 1, gps_ca_code_complex_sampled(p, fs2))
+            slots_all = np.arange(ACQ_PRNS, dtype=np.uint32)
+            x2 = torch.randn((n2, 2), device=dev, dtype=torch.float32)
+            r2d = torch.zeros(ACQ_PRNS * capi.ACQ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                cz.search_dev(x2.data_ptr(), slots_all, r2d.data_ptr())
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                cz.search_dev(x2.data_ptr(), slots_all, r2d.data_ptr())
+            c1.record()
+            torch.cuda.synchronize()
+            msz = c0.elapsed_time(c1) / 10
+            out["chirp_z_16368"] = {"workload": f"{ACQ_PRNS} PRNs x {cz.conf.num_doppler_bins} Doppler bins x N=16368 (16.368 Msps, 1 ms), chirp-z with M=32768",
+                                    "ms_per_sweep": msz, "value": ACQ_PRNS / (msz * 1e-3), "unit": "acquisitions/s"}
+            cz.close()
+        except Exception as ex:
+            out["chirp_z_16368"] = {"error": repr(ex)}
     return out
 
 

@@ -203,7 +203,19 @@ bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* 
     // fast path: somebody has already put these samples into the band (every block of the flowgraph offers the same stream)
     if (abs_index >= d_band_lo[band].load(std::memory_order_acquire) && abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
 
-    std::unique_lock<std::mutex> lk(d_band_mu[band]);
+    // One producer at a time.  The others do not queue on the mutex (32 hand-overs of a contended lock cost more than the
+    // copy itself): whoever gets it copies, the rest watch the band's written range, which usually comes to cover them.
+    std::unique_lock<std::mutex> lk(d_band_mu[band], std::try_to_lock);
+    for (int spins = 0; !lk.owns_lock(); spins++)
+        {
+            if (abs_index >= d_band_lo[band].load(std::memory_order_acquire) && abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
+            if (d_stop.load(std::memory_order_relaxed)) return false;
+            if (spins < 64)
+                B200_CPU_RELAX();
+            else
+                std::this_thread::yield();
+            if ((spins & 7) == 7) (void)lk.try_lock();
+        }
     if (abs_index >= d_band_lo[band].load(std::memory_order_acquire) && abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
     // back-pressure: never overwrite what a slower active channel of this band still needs.  A channel that stopped calling
     // (stalled test thread, block torn down without idle()) must not wedge the rest: after the timeout laggards go idle.

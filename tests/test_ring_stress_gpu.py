@@ -55,14 +55,31 @@ print("RESULT " + json.dumps({"bad": bad, "launches": launches, "sha": hashlib.s
 '''
 
 
+def _source_hash():
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for pat in ("gnss_sdr_b200/csrc/*", "include/*.h"):
+        for f in sorted(glob.glob(os.path.join(ROOT, pat))):
+            h.update(os.path.basename(f).encode())
+            with open(f, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
 def build_variant(stages, stress):
+    """Same sources as the production library with -DSH_STAGES / -DSH_STRESS.  Staleness is decided on a hash of the sources
+    (kept beside the .so), not on file times: a snapshot copied to another machine keeps contents, not necessarily mtimes."""
     from gnss_sdr_b200 import build as b
     os.makedirs(os.path.join(ROOT, "gnss_sdr_b200", "variants"), exist_ok=True)
     out = os.path.join(ROOT, "gnss_sdr_b200", "variants", f"libb200gnss_ring{stages}_{'stress' if stress else 'plain'}.so")
-    import glob
-    newest = max(os.path.getmtime(f) for pat in ("csrc/*", "../include/*.h") for f in glob.glob(os.path.join(ROOT, "gnss_sdr_b200", pat)))
-    if not os.path.exists(out) or os.path.getmtime(out) < newest:
+    want = _source_hash()
+    stamp = out + ".srchash"
+    have = open(stamp).read().strip() if os.path.exists(stamp) else ""
+    if not os.path.exists(out) or have != want:
         b.build(extra=[f"-DSH_STAGES={stages}", f"-DSH_STRESS={1 if stress else 0}"], out=out)
+        with open(stamp, "w") as fh:
+            fh.write(want)
     return out
 
 
