@@ -227,7 +227,19 @@ bool B200_Multicorrelator_Real_Codes::post(float rem_carrier_phase_in_rad, float
     if (!open_coalesced_channel() || !refresh_taps()) return false;
     b200::Trk_Coalescer* co = b200::Trk_Coalescer::instance();
     int n_offer = d_n_available > signal_length_samples ? d_n_available : signal_length_samples;
-    if (!co->push(d_chan, d_abs_index, d_sig_in, static_cast<uint64_t>(n_offer))) return false;
+    bool behind = false;
+    d_done_synchronously = false;
+    if (!co->push(d_chan, d_abs_index, d_sig_in, static_cast<uint64_t>(n_offer), &behind))
+        {
+            if (!behind) return false;
+            // this block fell more than a ring behind the others on its band: its samples are still in its own input buffer,
+            // so this epoch goes the synchronous way (same kernel, same arithmetic) and wait() hands the result over
+            b200_trk_set_taps(d_trk, d_shifts_chips);
+            d_done_synchronously = b200_trk_correlate(d_trk, reinterpret_cast<const b200_cf32*>(d_sig_in), rem_carrier_phase_in_rad, phase_step_rad,
+                                       phase_rate_step_rad, rem_code_phase_chips, code_phase_step_chips, code_phase_rate_step_chips,
+                                       signal_length_samples, reinterpret_cast<b200_cf32*>(d_corr_out)) == B200_OK;
+            return d_done_synchronously;
+        }
     return co->post(d_chan, d_abs_index, signal_length_samples, rem_carrier_phase_in_rad, phase_step_rad, phase_rate_step_rad,
         rem_code_phase_chips, code_phase_step_chips, code_phase_rate_step_chips);
 }
@@ -235,6 +247,11 @@ bool B200_Multicorrelator_Real_Codes::post(float rem_carrier_phase_in_rad, float
 
 bool B200_Multicorrelator_Real_Codes::wait()
 {
+    if (d_done_synchronously)
+        {
+            d_done_synchronously = false;
+            return true;
+        }
     b200::Trk_Coalescer* co = b200::Trk_Coalescer::instance();
     return co != nullptr && d_chan >= 0 && co->wait(d_chan, d_corr_out);
 }

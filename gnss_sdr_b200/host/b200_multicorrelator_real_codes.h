@@ -85,6 +85,7 @@ private:
     bool d_use_high_dynamics_resampler{true};  // same default as the CPU class (.h:60)
     // coalesced mode
     bool d_coalesced{false};
+    bool d_done_synchronously{false};  // post() fell back to the synchronous call for this epoch; wait() reports it
     int d_band{0};
     uint64_t d_abs_index{0};
     int d_n_available{0};

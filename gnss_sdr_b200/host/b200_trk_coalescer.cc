@@ -37,6 +37,7 @@ Trk_Coalescer::Trk_Coalescer(b200_engine* engine) : d_engine(engine), d_slots(ne
     for (auto& w : d_band_written) w.store(0);
     for (auto& w : d_band_lo) w.store(0);
     for (auto& w : d_band_active) w.store(0);
+    for (auto& w : d_band_attached) w.store(0);
     if (const char* env = std::getenv("B200_COALESCE_WINDOW_US")) d_window_us = std::atoi(env);
     d_thread = std::thread([this] { tick_loop(); });
 }
@@ -97,6 +98,7 @@ int Trk_Coalescer::open_channel(int band, int n_correlators)
     s.band = band;
     s.taps = n_correlators;
     s.active.store(false);
+    s.attached.store(false);
     s.cursor.store(0);
     s.state.store(IDLE, std::memory_order_release);
     if (id + 1 > d_n_slots.load()) d_n_slots.store(id + 1);
@@ -104,20 +106,27 @@ int Trk_Coalescer::open_channel(int band, int n_correlators)
 }
 
 
-// A channel starts offering samples.  When it is the only active one of its band, nothing says that the stream it is in
-// continues the one the band last saw (a flowgraph restarted in the same process starts its sample counter over): what
-// the band holds is forgotten, and the channel's own push refills it.  Never loses data a channel needs - every channel
-// offers its whole epoch before it posts.
+// A channel starts (or resumes) offering samples.  When no other channel is attached to its band, nothing says that the
+// stream it is in continues the one the band last saw (a flowgraph restarted in the same process starts its sample counter
+// over): what the band holds is forgotten, and the channel's own push refills it.  "Attached" lasts from a channel's first
+// push to its idle() / close_channel(); missing a batch window only makes a channel inactive, it keeps its claim on the band
+// (it may be between push and post).
 void Trk_Coalescer::activate(Slot& s, bool stream_may_be_new)
 {
     std::lock_guard<std::mutex> lk(d_band_mu[s.band]);
-    if (s.active.exchange(true)) return;
-    d_n_active.fetch_add(1);
-    if (d_band_active[s.band].fetch_add(1) == 0 && stream_may_be_new)
+    if (!s.active.exchange(true))
         {
-            d_band_written[s.band].store(0, std::memory_order_release);
-            d_band_lo[s.band].store(0, std::memory_order_release);
-            b200_iq_forget(d_engine, s.band);
+            d_n_active.fetch_add(1);
+            d_band_active[s.band].fetch_add(1);
+        }
+    if (!s.attached.exchange(true))
+        {
+            if (d_band_attached[s.band].fetch_add(1) == 0 && stream_may_be_new)
+                {
+                    d_band_written[s.band].store(0, std::memory_order_release);
+                    d_band_lo[s.band].store(0, std::memory_order_release);
+                    b200_iq_forget(d_engine, s.band);
+                }
         }
 }
 
@@ -137,6 +146,7 @@ void Trk_Coalescer::idle(int id)
     Slot* s = slot_of(id);
     if (s == nullptr) return;
     deactivate(*s);
+    if (s->attached.exchange(false)) d_band_attached[s->band].fetch_sub(1);
     d_cv_space[s->band].notify_all();
     d_posted.notify_all();  // the tick thread re-evaluates how many posts it is waiting for
 }
@@ -192,8 +202,9 @@ bool Trk_Coalescer::fits(int band, uint64_t abs_index, uint64_t n) const
 }
 
 
-bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* samples, uint64_t n)
+bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* samples, uint64_t n, bool* behind)
 {
+    if (behind) *behind = false;
     Slot* s = slot_of(id);
     if (s == nullptr) return false;
     const int band = s->band;
@@ -217,6 +228,23 @@ bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* 
             if ((spins & 7) == 7) (void)lk.try_lock();
         }
     if (abs_index >= d_band_lo[band].load(std::memory_order_acquire) && abs_index + n <= d_band_written[band].load(std::memory_order_acquire)) return true;
+    if (d_band_attached[band].load(std::memory_order_acquire) > 1 && d_band_written[band].load() > d_band_lo[band].load())
+        {
+            // the band is shared right now: its window may only grow at the top
+            if (abs_index < d_band_lo[band].load())
+                {
+                    std::snprintf(d_error, sizeof(d_error), "channel %d is behind the band's window (sample %llu < %llu)", id,
+                        static_cast<unsigned long long>(abs_index), static_cast<unsigned long long>(d_band_lo[band].load()));
+                    if (behind) *behind = true;
+                    return false;
+                }
+            // ahead of everything pushed so far: the channels behind are about to offer the samples in between - give them a
+            // moment (the lock is released while waiting); if they do not, the band restarts here and THEY take the path above
+            if (abs_index > d_band_written[band].load())
+                d_cv_space[band].wait_for(lk, std::chrono::milliseconds(20),
+                    [&] { return d_stop.load() || abs_index <= d_band_written[band].load() || d_band_attached[band].load() <= 1; });
+            if (abs_index >= d_band_lo[band].load() && abs_index + n <= d_band_written[band].load()) return true;
+        }
     // back-pressure: never overwrite what a slower active channel of this band still needs.  A channel that stopped calling
     // (stalled test thread, block torn down without idle()) must not wedge the rest: after the timeout laggards go idle.
     if (!fits(band, abs_index, n))
@@ -249,6 +277,7 @@ bool Trk_Coalescer::push(int id, uint64_t abs_index, const std::complex<float>* 
             d_band_lo[band].store(lo, std::memory_order_release);
             d_band_written[band].store(hi, std::memory_order_release);
         }
+    d_cv_space[band].notify_all();  // a channel ahead of the band may be waiting for this range
     return true;
 }
 

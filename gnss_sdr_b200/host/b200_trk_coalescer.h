@@ -71,8 +71,11 @@ public:
     //! the channel stops taking part in batches until it posts again (loss of lock, stop_tracking)
     void idle(int id);
 
-    //! offer [abs_index, abs_index + n) of the band's stream; copies what the band does not hold yet
-    bool push(int id, uint64_t abs_index, const std::complex<float>* samples, uint64_t n);
+    //! offer [abs_index, abs_index + n) of the band's stream; copies what the band does not hold yet.  Returns false with
+    //! *behind = true when the epoch starts before the oldest sample the band still holds while other channels are using the
+    //! band (this channel fell more than a ring behind them): restarting the band there would pull the samples from under the
+    //! others, so nothing is pushed and the caller correlates this epoch on its own (it holds the samples).
+    bool push(int id, uint64_t abs_index, const std::complex<float>* samples, uint64_t n, bool* behind = nullptr);
     //! post one epoch; returns at once.  wait() blocks until its taps are in `out` (n_correlators values).
     bool post(int id, uint64_t abs_index, int n, float rem_carrier_phase_rad, float phase_step_rad, float phase_rate_step_rad,
         float rem_code_phase_chips, float code_phase_step_chips, float code_phase_rate_step_chips);
@@ -95,7 +98,8 @@ private:
     struct alignas(64) Slot  // one cache line pair per channel: no false sharing between block threads
     {
         std::atomic<int> state{FREE};
-        std::atomic<bool> active{false};
+        std::atomic<bool> active{false};    // takes part in the batches right now (cleared by idle() and when it misses a window)
+        std::atomic<bool> attached{false};  // uses the band's contents (cleared only by idle() / close_channel())
         std::atomic<uint64_t> cursor{0};  // first sample the channel still needs
         int band{0};
         int taps{0};
@@ -117,6 +121,7 @@ private:
     std::atomic<uint32_t> d_done_gen{0};    // batches completed: every waiter sleeps on this one word (one wake call per batch)
     std::atomic<int> d_n_active{0};
     std::atomic<int> d_band_active[kMaxBands];         // active channels per band
+    std::atomic<int> d_band_attached[kMaxBands];       // channels per band between their first push and idle() / close
     std::atomic<bool> d_stop{false};
     std::atomic<uint64_t> d_band_written[kMaxBands];   // samples [lo, written) are in the band (fast path of push)
     std::atomic<uint64_t> d_band_lo[kMaxBands];

@@ -133,7 +133,7 @@ def test_c2_full_size_signal_prompt_dominates(capi, oracle):
 
 
 # ---------------------------------------------------------------------------------------------------------------- acquisition
-ACQ_FS, ACQ_N, DMAX, DSTEP = 25_000_000, 25000, 10000, 250
+ACQ_FS, ACQ_N, DMAX, DSTEP = 25_000_000, 25000, 10125, 250     # 81 bins (bench.py's C4)
 
 
 @pytest.fixture(scope="module")
@@ -166,7 +166,8 @@ def test_c4_sweep_equals_single_prn_searches(c4):
 
 
 def test_c4_circular_shift_moves_the_peak_only(c4):
-    """PCPS is a circular correlation over the 1 ms block: rotating the block by s samples moves every code phase by s."""
+    """PCPS is a circular correlation over the 1 ms block: rotating the block by s samples moves every code phase by s.  (The
+    statistic moves a little too: the carrier is not periodic in the block, the rotation puts its phase jump elsewhere.)"""
     acq, iq, present = c4
     base = acq.search(iq, np.arange(32))
     for s in (1, 777, 12500, 24999):
@@ -175,7 +176,7 @@ def test_c4_circular_shift_moves_the_peak_only(c4):
             b, g = base[p - 1], got[p - 1]
             assert int(g["index_time"]) == (int(b["index_time"]) + s) % ACQ_N, (p, s)
             assert int(g["index_doppler"]) == int(b["index_doppler"])
-            assert abs(g["test_statistics"] - b["test_statistics"]) / b["test_statistics"] < 2e-4
+            assert abs(g["test_statistics"] - b["test_statistics"]) / b["test_statistics"] < 1e-2
 
 
 def test_c4_frequency_shift_moves_one_doppler_bin(c4):

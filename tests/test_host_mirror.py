@@ -33,6 +33,20 @@ def test_host_mirror_builds_and_links():
     assert os.path.exists(exe)
 
 
+def test_coalescer_logic_against_a_fake_engine():
+    """b200::Trk_Coalescer linked against a fake engine (tests/host/test_coalescer_cpu.cc): 24 block threads on one stream
+    (right answers, one copy of the samples, shared batches), a restarted stream with overlapping indices, two bands with a
+    straggler, a wrapping ring with a slow channel - no GPU needed."""
+    exe = os.path.join(ROOT, "tests", "host", "test_coalescer_cpu")
+    libdir = os.path.join(ROOT, "gnss_sdr_b200")
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-Wall", "-Wextra", os.path.join(ROOT, "tests", "host", "test_coalescer_cpu.cc"),
+                           os.path.join(libdir, "host", "b200_trk_coalescer.cc"), "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(libdir, "host"), "-lpthread", "-o", exe])
+    for _ in range(3):
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "COALESCER_CPU OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_compute_threshold_matches_boost_formula():
     """compute_threshold (pcps_acquisition.cc:52-56) on the host, no GPU: against scipy's gammaincinv
     (== boost::math::gamma_p_inv) through the oracle's restatement."""
