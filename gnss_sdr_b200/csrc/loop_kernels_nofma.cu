@@ -258,11 +258,19 @@ __device__ bool lock_status(LoopDev& L, float2 P_accu, double coh_integration_ti
     return true;
 }
 
-// general_work case 2 after do_correlation_step, then consume_each.  Returns true when a record was logged.
-__device__ bool loop_update(LoopDev& L, const float2* t, unsigned int* rec)
+// general_work case 2 after do_correlation_step, then consume_each, in three parts that touch DISJOINT members of LoopDev so
+// that the persistent kernel can run them on different warps at the same time (the serial double-precision chain of one
+// thread was 40 % of an epoch):
+//   loop_lock_part    the bit-synchronisation time limit and cn0_and_tracking_lock_status (:1167-1224): Prompt_buffer,
+//                     cn0_estimation_counter, the two smoothers, CN0_SNV_dB_Hz, carrier_lock_test, the fail counters;
+//   loop_track_part   run_dll_pll (:1260-1347) and update_tracking_vars (:1409-1483): discriminators, loop filters, NCO and
+//                     remnant-phase members, current_prn_length_samples, epochs;
+//   loop_record_part  log_data (:1599-1694) from the members the other two left behind.
+// loop_update() is their sequential composition in the reference's order and is what every other caller uses.
+__device__ __forceinline__ void loop_taps(const b200_trk_loop_conf& c, const float2* t, float2& VE, float2& E, float2& P, float2& Lt, float2& VL)
 {
-    const b200_trk_loop_conf& c = L.c;
-    float2 VE = make_float2(0.f, 0.f), VL = make_float2(0.f, 0.f), E, P, Lt;
+    VE = make_float2(0.f, 0.f);
+    VL = make_float2(0.f, 0.f);
     if (c.veml)
         {
             VE = t[0];
@@ -277,109 +285,161 @@ __device__ bool loop_update(LoopDev& L, const float2* t, unsigned int* rec)
             P = t[1];
             Lt = t[2];
         }
-    L.spc = c.early_late_space_chips;
-    bool logged = false;
+}
+
+__device__ bool loop_lock_part(LoopDev& L, const float2* t)
+{
+    const b200_trk_loop_conf& c = L.c;
+    float2 VE, E, P, Lt, VL;
+    loop_taps(c, t, VE, E, P, Lt, VL);
+    L.spc = c.early_late_space_chips;   // (nobody reads the member: the DLL discriminator takes the value from the configuration)
     if (c.bit_synchronization_time_limit_s < (L.nitems_read - L.acq_sample_stamp) / static_cast<unsigned long long>(static_cast<int>(c.fs_in)))
         L.carrier_lock_fail_counter = 300000;
-    if (!lock_status(L, P, c.code_period))
+    return lock_status(L, P, c.code_period);
+}
+
+__device__ void loop_lost_lock(LoopDev& L)
+{
+    clear_tracking_vars(L);
+    L.state = 0;
+    L.loss_of_lock = 1;
+}
+
+__device__ void loop_track_part(LoopDev& L, const float2* t)
+{
+    const b200_trk_loop_conf& c = L.c;
+    float2 VE, E, P, Lt, VL;
+    loop_taps(c, t, VE, E, P, Lt, VL);
+    const float spc = c.early_late_space_chips;
+    // ---- run_dll_pll
+    if (L.cloop)
+        L.carr_phase_error_hz = (P.x != 0.0f ? static_cast<double>(atanf_cr(P.y / P.x)) : 0.0) / kTwoPi;
+    else
+        L.carr_phase_error_hz = static_cast<double>(atan2f_cr(P.y, P.x)) / kTwoPi;
+    const float T = static_cast<float>(L.current_correlation_time_s);
+    if ((L.pull_in_transitory && c.enable_fll_pull_in) || c.enable_fll_steady_state)
         {
-            clear_tracking_vars(L);
-            L.state = 0;
-            L.loss_of_lock = 1;
+            double diff_atan = atanf_cr(P.y / P.x) - atanf_cr(L.P_accu_old.y / L.P_accu_old.x);
+            if (isnan(diff_atan)) diff_atan = 0;
+            L.carr_freq_error_hz = phase_unwrap(diff_atan) / (L.current_correlation_time_s - 0.0) / kTwoPi;
+            L.P_accu_old = P;
+            if (L.pull_in_transitory && c.enable_fll_pull_in)
+                L.carr_error_filt_hz = carrier_filter(L, static_cast<float>(L.carr_freq_error_hz), 0.0f, T);
+            else
+                L.carr_error_filt_hz = carrier_filter(L, static_cast<float>(L.carr_freq_error_hz), static_cast<float>(L.carr_phase_error_hz), T);
         }
     else
         {
-            // ---- run_dll_pll
-            if (L.cloop)
-                L.carr_phase_error_hz = (P.x != 0.0f ? static_cast<double>(atanf_cr(P.y / P.x)) : 0.0) / kTwoPi;
-            else
-                L.carr_phase_error_hz = static_cast<double>(atan2f_cr(P.y, P.x)) / kTwoPi;
-            const float T = static_cast<float>(L.current_correlation_time_s);
-            if ((L.pull_in_transitory && c.enable_fll_pull_in) || c.enable_fll_steady_state)
-                {
-                    double diff_atan = atanf_cr(P.y / P.x) - atanf_cr(L.P_accu_old.y / L.P_accu_old.x);
-                    if (isnan(diff_atan)) diff_atan = 0;
-                    L.carr_freq_error_hz = phase_unwrap(diff_atan) / (L.current_correlation_time_s - 0.0) / kTwoPi;
-                    L.P_accu_old = P;
-                    if (L.pull_in_transitory && c.enable_fll_pull_in)
-                        L.carr_error_filt_hz = carrier_filter(L, static_cast<float>(L.carr_freq_error_hz), 0.0f, T);
-                    else
-                        L.carr_error_filt_hz = carrier_filter(L, static_cast<float>(L.carr_freq_error_hz), static_cast<float>(L.carr_phase_error_hz), T);
-                }
-            else
-                {
-                    L.carr_error_filt_hz = carrier_filter(L, 0.0f, static_cast<float>(L.carr_phase_error_hz), T);
-                }
-            L.carrier_doppler_hz = L.carr_error_filt_hz;
-            if (c.veml)
-                {
-                    const double Early = sqrtf(VE.x * VE.x + VE.y * VE.y + E.x * E.x + E.y * E.y);
-                    const double Late = sqrtf(Lt.x * Lt.x + Lt.y * Lt.y + VL.x * VL.x + VL.y * VL.y);
-                    const double E_plus_L = Early + Late;
-                    L.code_error_chips = (E_plus_L == 0.0) ? 0.0 : (Early - Late) / E_plus_L;
-                }
-            else
-                {
-                    const double P_early = hypotf_cr(E.x, E.y);
-                    const double P_late = hypotf_cr(Lt.x, Lt.y);
-                    const double E_plus_L = P_early + P_late;
-                    L.code_error_chips = (E_plus_L == 0.0) ? 0.0 : ((c.y_intercept - c.slope * L.spc) / c.slope) * (P_early - P_late) / E_plus_L;
-                }
-            L.code_error_filt_chips = code_filter_apply(L, static_cast<float>(L.code_error_chips));
-            L.code_freq_chips = c.code_chip_rate - L.code_error_filt_chips;
-            if (c.carrier_aiding) L.code_freq_chips += L.carrier_doppler_hz * c.code_chip_rate / c.signal_carrier_freq;
-            // ---- update_tracking_vars
-            const double T_chip_seconds = 1.0 / L.code_freq_chips;
-            const double T_prn_seconds = T_chip_seconds * static_cast<double>(static_cast<int>(c.code_length_chips));
-            const double T_prn_samples = T_prn_seconds * c.fs_in;
-            const double K_blk_samples = T_prn_samples + L.rem_code_phase_samples;
-            L.current_prn_length_samples = static_cast<int>(floor(K_blk_samples));
-            const double len = static_cast<double>(L.current_prn_length_samples);
-            L.carrier_phase_step_rad = kTwoPi * (L.carrier_doppler_hz + 0.0) / c.fs_in;
-            const double adv = L.carrier_phase_step_rad * len + 0.5 * L.carrier_phase_rate_step_rad * len * len;
-            L.rem_carr_phase_rad += static_cast<float>(adv);
-            L.rem_carr_phase_rad = static_cast<float>(fmod(static_cast<double>(L.rem_carr_phase_rad), kTwoPi));
-            L.acc_carrier_phase_rad -= adv;
-            L.code_phase_step_chips = L.code_freq_chips / c.fs_in;
-            L.rem_code_phase_samples = K_blk_samples - len;
-            L.rem_code_phase_chips = L.code_freq_chips * L.rem_code_phase_samples / c.fs_in;
-            // ---- log_data
-            if (rec)
-                {
-                    const unsigned long long stamp = L.nitems_read + static_cast<unsigned long long>(static_cast<long long>(L.current_prn_length_samples));
-                    rec[0] = __float_as_uint(c.veml ? hypotf_cr(VE.x, VE.y) : 0.0f);
-                    rec[1] = __float_as_uint(hypotf_cr(E.x, E.y));
-                    rec[2] = __float_as_uint(hypotf_cr(P.x, P.y));
-                    rec[3] = __float_as_uint(hypotf_cr(Lt.x, Lt.y));
-                    rec[4] = __float_as_uint(c.veml ? hypotf_cr(VL.x, VL.y) : 0.0f);
-                    rec[5] = __float_as_uint(P.x);
-                    rec[6] = __float_as_uint(P.y);
-                    rec[7] = static_cast<unsigned int>(stamp);
-                    rec[8] = static_cast<unsigned int>(stamp >> 32);
-                    rec[9] = __float_as_uint(static_cast<float>(L.acc_carrier_phase_rad));
-                    rec[10] = __float_as_uint(static_cast<float>(L.carrier_doppler_hz));
-                    rec[11] = __float_as_uint(static_cast<float>(L.carrier_phase_rate_step_rad * c.fs_in * c.fs_in / kTwoPi));
-                    rec[12] = __float_as_uint(static_cast<float>(L.code_freq_chips));
-                    rec[13] = __float_as_uint(static_cast<float>(L.code_phase_rate_step_chips * c.fs_in * c.fs_in));
-                    rec[14] = __float_as_uint(static_cast<float>(L.carr_phase_error_hz));
-                    rec[15] = __float_as_uint(static_cast<float>(L.carr_error_filt_hz));
-                    rec[16] = __float_as_uint(static_cast<float>(L.code_error_chips));
-                    rec[17] = __float_as_uint(static_cast<float>(L.code_error_filt_chips));
-                    rec[18] = __float_as_uint(static_cast<float>(L.CN0_SNV_dB_Hz));
-                    rec[19] = __float_as_uint(static_cast<float>(L.carrier_lock_test));
-                    rec[20] = __float_as_uint(static_cast<float>(L.rem_code_phase_samples));
-                    const unsigned long long aux2 = static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(stamp)));
-                    rec[21] = static_cast<unsigned int>(aux2);
-                    rec[22] = static_cast<unsigned int>(aux2 >> 32);
-                    rec[23] = c.prn;
-                    rec[24] = 0u;  // TOW (telemetry stays on the host)
-                    rec[25] = 0u;
-                    rec[26] = 0u;  // WN
-                }
-            logged = true;
-            L.epochs++;
+            L.carr_error_filt_hz = carrier_filter(L, 0.0f, static_cast<float>(L.carr_phase_error_hz), T);
         }
+    L.carrier_doppler_hz = L.carr_error_filt_hz;
+    if (c.veml)
+        {
+            const double Early = sqrtf(VE.x * VE.x + VE.y * VE.y + E.x * E.x + E.y * E.y);
+            const double Late = sqrtf(Lt.x * Lt.x + Lt.y * Lt.y + VL.x * VL.x + VL.y * VL.y);
+            const double E_plus_L = Early + Late;
+            L.code_error_chips = (E_plus_L == 0.0) ? 0.0 : (Early - Late) / E_plus_L;
+        }
+    else
+        {
+            const double P_early = hypotf_cr(E.x, E.y);
+            const double P_late = hypotf_cr(Lt.x, Lt.y);
+            const double E_plus_L = P_early + P_late;
+            L.code_error_chips = (E_plus_L == 0.0) ? 0.0 : ((c.y_intercept - c.slope * spc) / c.slope) * (P_early - P_late) / E_plus_L;
+        }
+    L.code_error_filt_chips = code_filter_apply(L, static_cast<float>(L.code_error_chips));
+    L.code_freq_chips = c.code_chip_rate - L.code_error_filt_chips;
+    if (c.carrier_aiding) L.code_freq_chips += L.carrier_doppler_hz * c.code_chip_rate / c.signal_carrier_freq;
+    // ---- update_tracking_vars
+    const double T_chip_seconds = 1.0 / L.code_freq_chips;
+    const double T_prn_seconds = T_chip_seconds * static_cast<double>(static_cast<int>(c.code_length_chips));
+    const double T_prn_samples = T_prn_seconds * c.fs_in;
+    const double K_blk_samples = T_prn_samples + L.rem_code_phase_samples;
+    L.current_prn_length_samples = static_cast<int>(floor(K_blk_samples));
+    const double len = static_cast<double>(L.current_prn_length_samples);
+    L.carrier_phase_step_rad = kTwoPi * (L.carrier_doppler_hz + 0.0) / c.fs_in;
+    const double adv = L.carrier_phase_step_rad * len + 0.5 * L.carrier_phase_rate_step_rad * len * len;
+    L.rem_carr_phase_rad += static_cast<float>(adv);
+    L.rem_carr_phase_rad = static_cast<float>(fmod(static_cast<double>(L.rem_carr_phase_rad), kTwoPi));
+    L.acc_carrier_phase_rad -= adv;
+    L.code_phase_step_chips = L.code_freq_chips / c.fs_in;
+    L.rem_code_phase_samples = K_blk_samples - len;
+    L.rem_code_phase_chips = L.code_freq_chips * L.rem_code_phase_samples / c.fs_in;
+    L.epochs++;
+}
+
+// the five correlator magnitudes of the dump record (abs_VE, abs_E, abs_P, abs_L, abs_VL)
+__device__ __forceinline__ float loop_record_magnitude(const b200_trk_loop_conf& c, const float2* t, int which)
+{
+    float2 VE, E, P, Lt, VL;
+    loop_taps(c, t, VE, E, P, Lt, VL);
+    switch (which)
+        {
+        case 0: return c.veml ? hypotf_cr(VE.x, VE.y) : 0.0f;
+        case 1: return hypotf_cr(E.x, E.y);
+        case 2: return hypotf_cr(P.x, P.y);
+        case 3: return hypotf_cr(Lt.x, Lt.y);
+        default: return c.veml ? hypotf_cr(VL.x, VL.y) : 0.0f;
+        }
+}
+
+__device__ __forceinline__ unsigned long long loop_record_stamp(const LoopDev& L)
+{
+    return L.nitems_read + static_cast<unsigned long long>(static_cast<long long>(L.current_prn_length_samples));
+}
+
+// mags: the five magnitudes (computed here when nullptr); stamp: loop_record_stamp() taken BEFORE loop_consume()
+__device__ void loop_record_part(const LoopDev& L, const float2* t, const float* mags, unsigned long long stamp, unsigned int* rec)
+{
+    const b200_trk_loop_conf& c = L.c;
+    float2 VE, E, P, Lt, VL;
+    loop_taps(c, t, VE, E, P, Lt, VL);
+    for (int q = 0; q < 5; q++) rec[q] = __float_as_uint(mags ? mags[q] : loop_record_magnitude(c, t, q));
+    rec[5] = __float_as_uint(P.x);
+    rec[6] = __float_as_uint(P.y);
+    rec[7] = static_cast<unsigned int>(stamp);
+    rec[8] = static_cast<unsigned int>(stamp >> 32);
+    rec[9] = __float_as_uint(static_cast<float>(L.acc_carrier_phase_rad));
+    rec[10] = __float_as_uint(static_cast<float>(L.carrier_doppler_hz));
+    rec[11] = __float_as_uint(static_cast<float>(L.carrier_phase_rate_step_rad * c.fs_in * c.fs_in / kTwoPi));
+    rec[12] = __float_as_uint(static_cast<float>(L.code_freq_chips));
+    rec[13] = __float_as_uint(static_cast<float>(L.code_phase_rate_step_chips * c.fs_in * c.fs_in));
+    rec[14] = __float_as_uint(static_cast<float>(L.carr_phase_error_hz));
+    rec[15] = __float_as_uint(static_cast<float>(L.carr_error_filt_hz));
+    rec[16] = __float_as_uint(static_cast<float>(L.code_error_chips));
+    rec[17] = __float_as_uint(static_cast<float>(L.code_error_filt_chips));
+    rec[18] = __float_as_uint(static_cast<float>(L.CN0_SNV_dB_Hz));
+    rec[19] = __float_as_uint(static_cast<float>(L.carrier_lock_test));
+    rec[20] = __float_as_uint(static_cast<float>(L.rem_code_phase_samples));
+    const unsigned long long aux2 = static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(stamp)));
+    rec[21] = static_cast<unsigned int>(aux2);
+    rec[22] = static_cast<unsigned int>(aux2 >> 32);
+    rec[23] = c.prn;
+    rec[24] = 0u;  // TOW (telemetry stays on the host)
+    rec[25] = 0u;
+    rec[26] = 0u;  // WN
+}
+
+__device__ __forceinline__ void loop_consume(LoopDev& L)
+{
     L.nitems_read += static_cast<unsigned long long>(static_cast<long long>(L.current_prn_length_samples));  // consume_each
+}
+
+// Returns true when a record was logged.
+__device__ bool loop_update(LoopDev& L, const float2* t, unsigned int* rec)
+{
+    bool logged = false;
+    if (!loop_lock_part(L, t))
+        {
+            loop_lost_lock(L);
+        }
+    else
+        {
+            loop_track_part(L, t);
+            if (rec) loop_record_part(L, t, nullptr, loop_record_stamp(L), rec);
+            logged = true;
+        }
+    loop_consume(L);
     return logged;
 }
 
@@ -422,9 +482,12 @@ __global__ void trk_loop_cycle_kernel(LoopDev* loops, int n_loops, int mode, Loo
 #ifndef B200_LOOP_THREADS
 #define B200_LOOP_THREADS 256
 #endif
+#ifndef B200_LOOP_SERIAL_UPDATE
+#define B200_LOOP_SERIAL_UPDATE 0
+#endif
 constexpr int kLoopThreads = B200_LOOP_THREADS;
 
-__global__ void __launch_bounds__(kLoopThreads) trk_loop_persistent_kernel(LoopDev* loops, int n_loops, int max_epochs, LoopAvail avail,
+__global__ void __launch_bounds__(kLoopThreads, 512 / kLoopThreads > 0 ? 512 / kLoopThreads : 1) trk_loop_persistent_kernel(LoopDev* loops, int n_loops, int max_epochs, LoopAvail avail,
     const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, unsigned int* records, int rec_capacity, int* n_records,
     int tbl_cap)
 {
@@ -432,7 +495,12 @@ __global__ void __launch_bounds__(kLoopThreads) trk_loop_persistent_kernel(LoopD
     float* smem_tbl = smem;
     float2* smem_red = reinterpret_cast<float2*>(smem + tbl_cap);
     LoopDev* sL = reinterpret_cast<LoopDev*>(smem_red + (kLoopThreads / 32) * B200_MAX_TAPS);
+    LoopDev* sBackup = sL + 1;   // the state before the current update (see the loop)
     __shared__ b200_trk_item s_item;
+    __shared__ int s_lock_ok;
+    __shared__ float s_mags[5];
+    __shared__ unsigned long long s_stamp;
+    __shared__ unsigned int* s_rec;
     __shared__ int s_go;
     __shared__ int s_tbl_cache[2];  // chip-index window held in smem_tbl (process_item<.., REUSE>)
 
@@ -454,16 +522,92 @@ __global__ void __launch_bounds__(kLoopThreads) trk_loop_persistent_kernel(LoopD
     bool have_taps = false;
     float2 t[B200_MAX_TAPS];
 
+#ifdef B200_LOOP_PROFILE
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
+    __shared__ long long s_pf_lock;
+#define PF_MARK(slot)                 \
+    if (tid == 0)                     \
+        {                             \
+            const long long now_ = clock64(); \
+            pf[slot] += now_ - pc;    \
+            pc = now_;                \
+        }
+    if (tid == 0) pc = clock64();
+    if (tid == 32) s_pf_lock = 0;
+#else
+#define PF_MARK(slot)
+#endif
     for (int k = 0; k <= max_epochs; k++)
         {
+            PF_MARK(0)   // correlation of the previous iteration (incl. its barrier)
+#if B200_LOOP_SERIAL_UPDATE
+            if (have_taps && tid == 0) s_lock_ok = -1;   // A/B build: the whole update on thread 0, as before
+#else
+            if (have_taps)
+                {
+                    // Loop update of epoch k-1 on three warps at once (every thread holds the taps t[]):
+                    //   warp 0 / lane 0   run_dll_pll + update_tracking_vars, speculating that lock holds
+                    //   warp 1 / lane 0   the lock detectors (C/N0 estimator, carrier lock test, counters)
+                    //   warp 2 / lanes<5  the five magnitudes of the dump record
+                    // The parts write disjoint members of the state.  When the lock verdict is "lost" (once per run at most) the
+                    // state is put back from the copy taken below and the update is replayed in the reference's order.
+                    {
+                        const unsigned int* src = reinterpret_cast<const unsigned int*>(sL);
+                        unsigned int* dst = reinterpret_cast<unsigned int*>(sBackup);
+                        for (int w = tid; w < static_cast<int>(sizeof(LoopDev) / 4); w += kLoopThreads) dst[w] = src[w];
+                    }
+                    __syncthreads();
+                    PF_MARK(1)   // state copy + barrier
+                    if (tid == 0)
+                        {
+                            loop_track_part(*sL, t);
+                            s_stamp = loop_record_stamp(*sL);
+                            s_rec = (records && k_rec < rec_capacity) ? records + (static_cast<size_t>(i) * rec_capacity + k_rec) * kLoopRecordWords : nullptr;
+                        }
+                    else if (tid == 32)
+                        {
+#ifdef B200_LOOP_PROFILE
+                            const long long a_ = clock64();
+#endif
+                            s_lock_ok = loop_lock_part(*sL, t) ? 1 : 0;
+#ifdef B200_LOOP_PROFILE
+                            s_pf_lock += clock64() - a_;
+#endif
+                        }
+                    else if (tid >= 64 && tid < 69)
+                        s_mags[tid - 64] = loop_record_magnitude(sL->c, t, tid - 64);
+                    PF_MARK(2)   // track part (thread 0 alone)
+                    __syncthreads();
+                    PF_MARK(3)   // waiting for the lock part / magnitudes
+                    // the dump record goes out from warp 1 while thread 0 consumes the epoch and prepares the next one: in the
+                    // tracking state neither of those writes a member the record reads (the sample stamp was taken above)
+                    if (tid == 32 && s_lock_ok > 0 && s_rec != nullptr) loop_record_part(*sL, t, s_mags, s_stamp, s_rec);
+                }
+#endif
             if (tid == 0)
                 {
                     if (have_taps)
                         {
                             unsigned int* rec = nullptr;
                             if (records && k_rec < rec_capacity) rec = records + (static_cast<size_t>(i) * rec_capacity + k_rec) * kLoopRecordWords;
-                            if (loop_update(*sL, t, rec)) k_rec++;
+                            if (s_lock_ok < 0)
+                                {
+                                    if (loop_update(*sL, t, rec)) k_rec++;
+                                }
+                            else if (s_lock_ok)
+                                {
+                                    loop_consume(*sL);
+                                    k_rec++;
+                                }
+                            else
+                                {
+                                    const unsigned int* src = reinterpret_cast<const unsigned int*>(sBackup);
+                                    unsigned int* dst = reinterpret_cast<unsigned int*>(sL);
+                                    for (int w = 0; w < static_cast<int>(sizeof(LoopDev) / 4); w++) dst[w] = src[w];
+                                    if (loop_update(*sL, t, rec)) k_rec++;
+                                }
                         }
+                    PF_MARK(4)   // record + consume
                     int go = 0;
                     if (k < max_epochs)
                         {
@@ -475,7 +619,9 @@ __global__ void __launch_bounds__(kLoopThreads) trk_loop_persistent_kernel(LoopD
                         }
                     s_go = go;
                 }
+            PF_MARK(5)   // prepare
             __syncthreads();
+            PF_MARK(6)   // barrier
             if (!s_go) break;
             if (taps == 3)
                 {
@@ -493,6 +639,12 @@ __global__ void __launch_bounds__(kLoopThreads) trk_loop_persistent_kernel(LoopD
                 }
             have_taps = true;
         }
+#ifdef B200_LOOP_PROFILE
+    if (tid == 0 && i == 0)
+        printf("LOOP_PROFILE loop 0, %d epochs, cycles per epoch: correlation %lld | state copy %lld | track part %lld | wait for lock part %lld (lock part itself %lld) | "
+               "record %lld | prepare %lld | barrier %lld\n", k_rec, pf[0] / k_rec, pf[1] / k_rec, pf[2] / k_rec, pf[3] / k_rec, s_pf_lock / k_rec, pf[4] / k_rec,
+            pf[5] / k_rec, pf[6] / k_rec);
+#endif
     __syncthreads();
     if (tid == 0) sL->pending = 0;
     __syncthreads();
@@ -513,7 +665,7 @@ int launch_loop_persistent(LoopDev* loops, int n_loops, int max_epochs, const Lo
     const int cap_limit = (200 * 1024 - 4096) / 4;
     if (tbl_cap > cap_limit) tbl_cap = cap_limit;
     tbl_cap = (tbl_cap + 3) & ~3;
-    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kLoopThreads / 32) * B200_MAX_TAPS * sizeof(float2) + sizeof(LoopDev);
+    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kLoopThreads / 32) * B200_MAX_TAPS * sizeof(float2) + 2 * sizeof(LoopDev);
     static DeviceOnce once;
     const int once_dev = once.begin();
     if (once_dev >= 0)
