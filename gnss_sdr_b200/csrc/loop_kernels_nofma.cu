@@ -15,6 +15,7 @@
 //   tracking_discriminators.cc:26-39,69-77,86-89,100-107,119-129,142-153
 //   tracking_FLL_PLL_filter.cc:72-104    tracking_loop_filter.cc:62-96
 //   lock_detectors.cc:99-147,160-181     exponential_smoother.cc:86-115
+#include <cstdlib>
 #include "loop.cuh"
 #include "trk_item.cuh"
 
@@ -485,8 +486,10 @@ __global__ void trk_loop_cycle_kernel(LoopDev* loops, int n_loops, int mode, Loo
 #ifndef B200_LOOP_SERIAL_UPDATE
 #define B200_LOOP_SERIAL_UPDATE 0
 #endif
-constexpr int kLoopThreads = B200_LOOP_THREADS;
+constexpr int kLoopThreadsMany = B200_LOOP_THREADS;   // CTA width when loops outnumber the SMs (two CTAs per SM)
+constexpr int kLoopThreadsFew = 512;                  // one loop per SM at most: wider CTAs shorten the correlation (8.7 vs 9.3 us per epoch)
 
+template <int kLoopThreads>
 __global__ void __launch_bounds__(kLoopThreads, 512 / kLoopThreads > 0 ? 512 / kLoopThreads : 1) trk_loop_persistent_kernel(LoopDev* loops, int n_loops, int max_epochs, LoopAvail avail,
     const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, unsigned int* records, int rec_capacity, int* n_records,
     int tbl_cap)
@@ -657,6 +660,24 @@ __global__ void __launch_bounds__(kLoopThreads, 512 / kLoopThreads > 0 ? 512 / k
 }
 }  // namespace
 
+template <int THREADS>
+static int launch_loop_persistent_width(LoopDev* loops, int n_loops, int max_epochs, const LoopAvail& avail, const ChanDesc* chans, const BandDesc* bands,
+    unsigned int* records, int rec_capacity, int* n_records, int tbl_cap, cudaStream_t st)
+{
+    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (THREADS / 32) * B200_MAX_TAPS * sizeof(float2) + 2 * sizeof(LoopDev);
+    static DeviceOnce once;
+    const int once_dev = once.begin();
+    if (once_dev >= 0)
+        {
+            B200_CUDA_TRY(cudaFuncSetAttribute(trk_loop_persistent_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once.done(once_dev);
+        }
+    trk_loop_persistent_kernel<THREADS><<<n_loops, THREADS, smem_bytes, st>>>(loops, n_loops, max_epochs, avail, chans, bands, records, rec_capacity,
+        n_records, tbl_cap);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
 int launch_loop_persistent(LoopDev* loops, int n_loops, int max_epochs, const LoopAvail& avail, const ChanDesc* chans, const BandDesc* bands,
     unsigned int* records, int rec_capacity, int* n_records, int max_code_len, cudaStream_t st)
 {
@@ -665,18 +686,17 @@ int launch_loop_persistent(LoopDev* loops, int n_loops, int max_epochs, const Lo
     const int cap_limit = (200 * 1024 - 4096) / 4;
     if (tbl_cap > cap_limit) tbl_cap = cap_limit;
     tbl_cap = (tbl_cap + 3) & ~3;
-    const size_t smem_bytes = static_cast<size_t>(tbl_cap) * 4 + (kLoopThreads / 32) * B200_MAX_TAPS * sizeof(float2) + 2 * sizeof(LoopDev);
-    static DeviceOnce once;
-    const int once_dev = once.begin();
-    if (once_dev >= 0)
-        {
-            B200_CUDA_TRY(cudaFuncSetAttribute(trk_loop_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            once.done(once_dev);
-        }
-    trk_loop_persistent_kernel<<<n_loops, kLoopThreads, smem_bytes, st>>>(loops, n_loops, max_epochs, avail, chans, bands, records, rec_capacity,
-        n_records, tbl_cap);
-    B200_CUDA_TRY(cudaGetLastError());
-    return B200_OK;
+    // width: each loop is a latency chain, so with no more loops than SMs a wide CTA is the faster one; beyond that two narrow
+    // CTAs per SM overlap each other's serial sections (256 loops: 17.5 us per epoch at 256 threads, 22.8 at 512).
+    // B200_LOOP_WIDTH = 256 | 512 forces one (A/B runs).
+    int sms = 0, dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    B200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    bool wide = n_loops <= sms;
+    if (const char* env = std::getenv("B200_LOOP_WIDTH")) wide = std::atoi(env) >= kLoopThreadsFew;
+    if (wide && kLoopThreadsMany < kLoopThreadsFew)
+        return launch_loop_persistent_width<kLoopThreadsFew>(loops, n_loops, max_epochs, avail, chans, bands, records, rec_capacity, n_records, tbl_cap, st);
+    return launch_loop_persistent_width<kLoopThreadsMany>(loops, n_loops, max_epochs, avail, chans, bands, records, rec_capacity, n_records, tbl_cap, st);
 }
 
 int launch_loop_cycle(LoopDev* loops, int n_loops, int mode, const LoopAvail& avail, b200_trk_item* items, const float2* taps,
