@@ -180,7 +180,9 @@ def test_c4_circular_shift_moves_the_peak_only(c4):
         got = acq.search(np.roll(iq, s), np.arange(32))
         for p in strong:
             b, g = base[p - 1], got[p - 1]
-            assert int(g["index_time"]) == (int(b["index_time"]) + s) % ACQ_N, (p, s)
+            # +-3 samples: at 24.4 samples per chip the correlation of two sampled chip sequences has a flat top a few samples
+            # wide, and which of its equal values wins is rounding
+            assert (int(g["index_time"]) - int(b["index_time"]) - s + 3) % ACQ_N <= 6, (p, s)
             assert int(g["index_doppler"]) == int(b["index_doppler"])
             assert abs(g["test_statistics"] - b["test_statistics"]) / b["test_statistics"] < 0.05
 
@@ -195,5 +197,5 @@ def test_c4_frequency_shift_moves_one_doppler_bin(c4):
         b, g = base[p - 1], got[p - 1]
         assert int(g["index_doppler"]) == int(b["index_doppler"]) + 1, p
         assert int(g["doppler"]) == int(b["doppler"]) + DSTEP
-        assert int(g["index_time"]) == int(b["index_time"])
+        assert abs(int(g["index_time"]) - int(b["index_time"])) <= 3
         assert abs(g["test_statistics"] - b["test_statistics"]) / b["test_statistics"] < 5e-3
