@@ -1,4 +1,4 @@
-"""BASELINE.json's full sizes (C2: 32 channels x 1000 epochs x 25 000 samples; C4: 32 PRNs x 81 Doppler bins x 25 000 points)
+"""BASELINE.json's full sizes (C2: 32 channels x 1000 epochs x 25 000 samples; C4: 32 PRNs x 80-81 Doppler bins x 25 000 points)
 checked through size-independent properties - the CPU oracle cannot cover 8e8 channel-samples in seconds, the properties can:
   tracking     exact linearity on integer-valued samples, batch-splitting invariance, the two kernels agreeing bit for bit,
                the oracle on a random handful of the 32 000 work items;
@@ -133,7 +133,7 @@ def test_c2_full_size_signal_prompt_dominates(capi, oracle):
 
 
 # ---------------------------------------------------------------------------------------------------------------- acquisition
-ACQ_FS, ACQ_N, DMAX, DSTEP = 25_000_000, 25000, 10125, 250     # 81 bins (bench.py's C4)
+ACQ_FS, ACQ_N, DMAX, DSTEP = 25_000_000, 25000, 10000, 250     # C4's grid moved by half a bin: whole-kHz carriers sit ON a bin (80 bins)
 
 
 @pytest.fixture(scope="module")
@@ -157,12 +157,12 @@ def c4(capi, oracle):
 
 def test_c4_sweep_equals_single_prn_searches(c4):
     acq, iq, present = c4
-    assert acq.conf.num_doppler_bins == 81
+    assert acq.conf.num_doppler_bins == 80
     sweep = acq.search(iq, np.arange(32))
     for p in range(32):
         assert acq.search(iq, [p])[0] == sweep[p], p
     from oracle.acq_np import compute_threshold
-    th = compute_threshold(0.001, ACQ_N, 81, 1)
+    th = compute_threshold(0.001, ACQ_N, 80, 1)
     # (whole-kHz Dopplers are the worst case for C/A cross-correlation - the code's spectral lines sit 1 kHz apart - so a
     # satellite or two may stay under the threshold; nothing that is not there may cross it)
     detected = {p + 1 for p in range(32) if sweep[p]["test_statistics"] > th}
