@@ -17,6 +17,11 @@
 //   lock_detectors.cc:99-147,160-181     exponential_smoother.cc:86-115
 #include <cstdlib>
 #include "loop.cuh"
+// A persistent CTA has the SM to itself (8-16 warps): its tile loop may want more loads in flight than the batch kernel's, which
+// shares the SM with three other CTAs.  B200_LOOP_TILE_UNROLL sets it for this translation unit only (tools/loop_ab.sh).
+#ifdef B200_LOOP_TILE_UNROLL
+#define TRK_TILE_UNROLL_3 B200_LOOP_TILE_UNROLL
+#endif
 #include "trk_item.cuh"
 
 namespace b200
