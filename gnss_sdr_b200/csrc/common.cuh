@@ -88,7 +88,7 @@ constexpr int kTrkTablePad = 64;            // extra entries of the extended cod
 // Launchers (trk_kernels.cu).  All pointers are device-accessible.
 int launch_trk_batch(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands,
     float2* out, int out_stride, int slices, float2* partial, unsigned int* counters,
-    int max_code_len, int taps_uniform, cudaStream_t stream);
+    int max_code_len, int taps_uniform, cudaStream_t stream, unsigned int taps_mask = 0u);
 size_t trk_partial_elems(int n_items, int slices);
 // shared-window kernel (trk_shared_kernel.cu): groups of 8 items share one copy of the samples
 int launch_trk_shared(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands, float2* out,

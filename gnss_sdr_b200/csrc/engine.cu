@@ -55,6 +55,7 @@ int upload_tables(b200_engine* e)
         }
     e->max_code_len = 0;
     e->taps_uniform = -1;
+    e->taps_mask = 0u;
     e->any_high_dyn = false;
     if (n > 0)
         {
@@ -65,6 +66,7 @@ int upload_tables(b200_engine* e)
                     if (cd[i].code_len > e->max_code_len) e->max_code_len = cd[i].code_len;
                     if (cd[i].code == nullptr) continue;
                     if (cd[i].high_dyn) e->any_high_dyn = true;
+                    e->taps_mask |= 1u << cd[i].taps;
                     if (e->taps_uniform == -1)
                         e->taps_uniform = cd[i].taps;
                     else if (e->taps_uniform != cd[i].taps)
@@ -684,8 +686,18 @@ extern "C"
                 e->taps_uniform, e->stream);
         else
             rc = launch_trk_batch(items_dev, n_items, e->chans_dev, e->bands_dev, reinterpret_cast<float2*>(out_dev), out_stride,
-                slices, e->partial, e->counters, e->max_code_len, e->taps_uniform, e->stream);
-        if (rc == B200_OK) e->launches++;
+                slices, e->partial, e->counters, e->max_code_len, e->taps_uniform, e->stream, e->taps_uniform == 0 ? e->taps_mask : 0u);
+        if (rc == B200_OK)
+            {
+                // a batch with several tap counts on the per-item path is one launch per specialised kernel (trk_kernels.cu)
+                int n_launch = 1;
+                if (!use_shared && e->taps_uniform == 0 && e->taps_mask != 0u)
+                    {
+                        const unsigned int special = e->taps_mask & ((1u << 1) | (1u << 3) | (1u << 5));
+                        n_launch = __builtin_popcount(special) + ((e->taps_mask & ~special) ? 1 : 0);
+                    }
+                e->launches += static_cast<uint64_t>(n_launch);
+            }
         return rc;
     }
 

@@ -173,7 +173,7 @@ int batch_slices(int n_items)
 int correlate_loop_items(b200_engine* e, int n, int slices)
 {
     int rc = launch_trk_batch(e->loop_items_dev, n, e->chans_dev, e->bands_dev, e->loop_taps_dev, kLoopTapStride, slices, e->partial,
-        e->counters, e->max_code_len, e->taps_uniform, e->stream);
+        e->counters, e->max_code_len, e->taps_uniform, e->stream, e->taps_uniform == 0 ? e->taps_mask : 0u);
     if (rc == B200_OK) e->launches++;
     return rc;
 }

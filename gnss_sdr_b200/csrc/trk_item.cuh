@@ -11,12 +11,15 @@
 // tiles of the packed main loop unrolled per thread (one 16-byte load each): memory-level parallelism vs registers.  Measured
 // on B200 (tools/ab_item.sh): with five taps (C3, Galileo E1) 4.66 ms at 4, 3.92 at 8, 3.89 at 16 (= a whole re-seed group:
 // the kernel is waiting on L2, more loads in flight is what it wants); with three taps (distinct-IQ C2) 0.612 ms at 4, 0.633 at
-// 8, 0.908 at 2.
+// 8, 0.908 at 2; the one-tap data correlator of a tracked pilot (C3 + pilot) 6.50 ms at 4, 6.18 at 8, 6.14 at 16.
 #ifndef TRK_TILE_UNROLL_3
 #define TRK_TILE_UNROLL_3 4
 #endif
 #ifndef TRK_TILE_UNROLL_5
 #define TRK_TILE_UNROLL_5 16
+#endif
+#ifndef TRK_TILE_UNROLL_1
+#define TRK_TILE_UNROLL_1 16
 #endif
 
 namespace b200
@@ -25,6 +28,7 @@ namespace
 {
 constexpr int kTileUnroll3 = TRK_TILE_UNROLL_3;   // (#pragma unroll takes constant expressions, not macros)
 constexpr int kTileUnroll5 = TRK_TILE_UNROLL_5;
+constexpr int kTileUnroll1 = TRK_TILE_UNROLL_1;   // one tap: the data prompt of a tracked pilot
 
 struct ItemCtx
 {
@@ -174,7 +178,7 @@ __device__ __forceinline__ void correlate_tiles_fast(const ItemCtx& cx, const fl
         {
             const int tg_end = min(tg + kTrkReseed, tile_end);
             float2 zr = zr2, zi = zi2;   // running phasors inside the group
-#pragma unroll (TAPS >= 4 ? kTileUnroll5 : kTileUnroll3)
+#pragma unroll (TAPS >= 4 ? kTileUnroll5 : (TAPS == 1 ? kTileUnroll1 : kTileUnroll3))
             for (int tile = tg; tile < tg_end; tile++)
                 {
                     float4 v;

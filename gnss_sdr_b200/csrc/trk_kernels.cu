@@ -74,8 +74,10 @@ __device__ __forceinline__ void run_item(const b200_trk_item& it, const ChanDesc
 template <int TAPS_T>
 __global__ void __launch_bounds__(kTrkThreads) trk_correlate_kernel(const b200_trk_item* __restrict__ items, int n_items,
     const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, float2* __restrict__ out, int out_stride,
-    int slices, float2* partial, unsigned int* counters, int tbl_cap)
+    int slices, float2* partial, unsigned int* counters, int tbl_cap, unsigned int only_mask)
 {
+    // only_mask != 0: a batch with several tap counts runs as one launch per specialisation; this launch serves the items whose
+    // channel has (1 << taps) in the mask and leaves the others to their own launch
     extern __shared__ __align__(16) float smem[];
     float* smem_tbl = smem;
     float2* smem_red = reinterpret_cast<float2*>(smem + tbl_cap);
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_correlate_kernel(const b200_t
             const int slice = w - item_id * slices;
             const b200_trk_item it = items[item_id];
             const ChanDesc& ch = chans[it.channel];
+            if (only_mask != 0u && ((1u << ch.taps) & only_mask) == 0u) continue;   // uniform per CTA iteration
             const BandDesc bd = bands[ch.band];
             if (w != static_cast<int>(blockIdx.x)) __syncthreads();  // smem reuse across items
             if (it.n <= 0)
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_correlate_kernel(const b200_t
 
 template <int T>
 int launch_one(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands, float2* out,
-    int out_stride, int slices, float2* partial, unsigned int* counters, int tbl_cap, size_t smem_bytes, cudaStream_t stream)
+    int out_stride, int slices, float2* partial, unsigned int* counters, int tbl_cap, size_t smem_bytes, cudaStream_t stream, unsigned int only_mask = 0u)
 {
     static DeviceOnce once;
     const int once_dev = once.begin();
@@ -129,7 +132,8 @@ int launch_one(const b200_trk_item* items, int n_items, const ChanDesc* chans, c
     const long long work = static_cast<long long>(n_items) * slices;
     // plain grid for moderate sizes, grid-stride beyond (keeps blockIdx math in int)
     const int grid = static_cast<int>(work < (1LL << 20) ? work : (1LL << 20));
-    trk_correlate_kernel<T><<<grid, kTrkThreads, smem_bytes, stream>>>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap);
+    trk_correlate_kernel<T><<<grid, kTrkThreads, smem_bytes, stream>>>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap,
+        only_mask);
     B200_CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }
@@ -142,7 +146,7 @@ size_t trk_partial_elems(int n_items, int slices)
 
 int launch_trk_batch(const b200_trk_item* items, int n_items, const ChanDesc* chans, const BandDesc* bands,
     float2* out, int out_stride, int slices, float2* partial, unsigned int* counters,
-    int max_code_len, int taps_uniform, cudaStream_t stream)
+    int max_code_len, int taps_uniform, cudaStream_t stream, unsigned int taps_mask)
 {
     if (n_items <= 0) return B200_OK;
     if (slices < 1) slices = 1;
@@ -156,8 +160,21 @@ int launch_trk_batch(const b200_trk_item* items, int n_items, const ChanDesc* ch
         case 1: return launch_one<1>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
         case 3: return launch_one<3>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
         case 5: return launch_one<5>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
-        default: return launch_one<0>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
+        default: break;
         }
+    // Several tap counts in one batch (a tracked pilot's 5 + 1 taps, a multi-signal receiver): one launch per specialised
+    // kernel, each serving its own items - the generic kernel (tap count read per item) needs 128 registers and halves the
+    // occupancy (C5 share and C3 + pilot ran on it).  Tap counts without a specialisation still take the generic kernel.
+    if (taps_mask == 0u) return launch_one<0>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream);
+    int rc = B200_OK;
+    if (taps_mask & (1u << 1)) rc = launch_one<1>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream, 1u << 1);
+    if (rc == B200_OK && (taps_mask & (1u << 3)))
+        rc = launch_one<3>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream, 1u << 3);
+    if (rc == B200_OK && (taps_mask & (1u << 5)))
+        rc = launch_one<5>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream, 1u << 5);
+    const unsigned int others = taps_mask & ~((1u << 1) | (1u << 3) | (1u << 5));
+    if (rc == B200_OK && others) rc = launch_one<0>(items, n_items, chans, bands, out, out_stride, slices, partial, counters, tbl_cap, smem_bytes, stream, others);
+    return rc;
 }
 
 }  // namespace b200
