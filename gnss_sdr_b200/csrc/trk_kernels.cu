@@ -71,8 +71,15 @@ __device__ __forceinline__ void run_item(const b200_trk_item& it, const ChanDesc
 
 // TAPS_T > 0: every channel in the launch has exactly TAPS_T taps (specialised registers).
 // TAPS_T == 0: taps read per item.
+// No minimum-blocks hint by default: ptxas then settles on 64 registers = 4 CTAs per SM, which measures best by far
+// (tools/ab_item.sh, C3: 3.89 ms; TRK_MIN_BLOCKS=2 -> 128 registers 4.11 ms, =3 -> 80 registers 7.37 ms).
+#ifdef TRK_MIN_BLOCKS
+#define TRK_LAUNCH_BOUNDS __launch_bounds__(kTrkThreads, TRK_MIN_BLOCKS)
+#else
+#define TRK_LAUNCH_BOUNDS __launch_bounds__(kTrkThreads)
+#endif
 template <int TAPS_T>
-__global__ void __launch_bounds__(kTrkThreads) trk_correlate_kernel(const b200_trk_item* __restrict__ items, int n_items,
+__global__ void TRK_LAUNCH_BOUNDS trk_correlate_kernel(const b200_trk_item* __restrict__ items, int n_items,
     const ChanDesc* __restrict__ chans, const BandDesc* __restrict__ bands, float2* __restrict__ out, int out_stride,
     int slices, float2* partial, unsigned int* counters, int tbl_cap, unsigned int only_mask)
 {
